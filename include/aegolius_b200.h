@@ -1,0 +1,216 @@
+/*
+ * aegolius_b200.h — C ABI of libaegolius_b200.so (B200 / sm_100a evaluator for SPOMSO's SDF hot path).
+ *
+ * The reference (SPOMSO 1.4.0, pure Python) has no FFI: its boundary for this path is the Python method
+ *   GenericGeometry.create(co) -> ndarray[(N,), f64]        Code/spomso/spomso/cores/geom.py:29-43
+ *   GenericGeometry.propagate(co, *params)                  Code/spomso/spomso/cores/geom.py:45-60
+ *   sdf_point_cloud_3d / sdf_point_cloud_2d(co, points)     Code/spomso/spomso/cores/sdf_3D.py:283-286, sdf_2D.py:221-224
+ *   from_sdf(sdf, co_resolution)                            Code/spomso/spomso/cores/vector_functions.py:130-139
+ * Each entry point below names the reference interface it replaces. The host side (Python, ctypes) flattens
+ * the SPOMSO object tree into an `ab_program` (linear op list) and calls these functions; see INTEGRATION.md.
+ *
+ * Conventions: every function returns AB_OK (0) or a negative ab_status; the message for the last error of the
+ * calling thread is returned by ab_last_error(). No exceptions cross the boundary. The caller owns every buffer.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream). Device entry points are asynchronous on
+ * `stream`; *_host entry points block until the result is in the host buffer.
+ */
+#ifndef AEGOLIUS_B200_H
+#define AEGOLIUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB_VERSION 100 /* 0.1.0 */
+
+typedef enum ab_status {
+  AB_OK = 0,
+  AB_EINVAL = -1,          /* bad argument / malformed program */
+  AB_EUNSUPPORTED_OP = -2, /* opcode unknown to this build */
+  AB_ECUDA = -3,           /* CUDA runtime error (message has the cudaError string) */
+  AB_ETOOLARGE = -4,       /* program exceeds AB_MAX_OPS / AB_MAX_ARGS / slot limits */
+  AB_ENODEVICE = -5        /* no CUDA device: there is NO CPU fallback */
+} ab_status;
+
+typedef enum ab_dtype { AB_F32 = 0, AB_F64 = 1 } ab_dtype;
+
+/* What to compute besides the field value (forward-mode dual numbers inside the interpreter). */
+typedef enum ab_grad_mode {
+  AB_GRAD_NONE = 0,
+  AB_GRAD_SPATIAL = 1, /* d field / d(x,y,z): analytic counterpart of from_sdf (vector_functions.py:130-139) */
+  AB_GRAD_PARAM = 2    /* d field / d theta for one scalar parameter: replaces jacfwd(geometry, argnums=k),
+                          Code/examples/autodiff/gradient_map_3D.py:84. Needs ab_program.dargs. */
+} ab_grad_mode;
+
+/* Limits of one program (it travels to the kernel as a __grid_constant__ parameter, i.e. constant bank 0). */
+#define AB_MAX_OPS 640
+#define AB_MAX_ARGS 2816
+#define AB_MAX_PSLOTS 16
+#define AB_MAX_VSLOTS 16
+#define AB_MAX_BLOBS 4
+
+/* One interpreter instruction (8 bytes). `a`/`b` are small immediates (slot numbers, axis, flags),
+ * `arg` is the offset of this op's first argument in ab_program.args. */
+typedef struct ab_op {
+  uint16_t opcode;
+  uint8_t a;
+  uint8_t b;
+  uint32_t arg;
+} ab_op;
+
+/* Opcodes. State per grid point: coordinate p=(x,y,z), accumulator acc, P-slots (saved coordinates),
+ * V-slots (saved values). Reference semantics cited per group; exact formulas in DESIGN.md §3. */
+typedef enum ab_opcode {
+  AB_OP_END = 0,
+  /* --- stack --- (children of a combine node all start from the parent's coordinates: combine.py:129-135) */
+  AB_OP_SAVE_P = 1,  /* P[a] = p */
+  AB_OP_LOAD_P = 2,  /* p = P[a] */
+  AB_OP_PUSH_V = 3,  /* V[a] = acc */
+  /* --- coordinate ops --- */
+  AB_OP_AFFINE = 8,      /* 12 args M(3x3 row-major), b: p = M p + b. Folded apply_ec_transforms (transformations.py:232-242),
+                            shear_* (modifications.py:579-774), rotate_sdf (:1308), mirror/linear_instancing frames (:978-985) */
+  AB_OP_TRANSLATE = 9,   /* 3 args b: p = p + b (move_sdf :1268; pure moves) */
+  AB_OP_SCALE_P = 10,    /* 1 arg k: p = p * k (rounding_cs :120-144, scale_sdf :1289) */
+  AB_OP_ELONGATE = 11,   /* 6 args lo(3),hi(3): p -= min(max(p,lo),hi)  (elongation :75-98) */
+  AB_OP_TWIST = 12,      /* 1 arg pitch (twist :502-527) */
+  AB_OP_BEND = 13,       /* 8 args (bend :529-577) */
+  AB_OP_ABSX_SUB = 14,   /* 1 arg h: x = |x| - h (mirror core :991-993) */
+  AB_OP_SYMMETRY = 15,   /* a = axis: p[a] = |p[a]| (symmetry :932-955) */
+  AB_OP_ROTSYM = 16,     /* 2 args angle, radius (rotational_symmetry :1020-1031, after its pre-rotation as AFFINE) */
+  AB_OP_REVOLVE = 17,    /* 1 arg radius (revolution :411-436) */
+  AB_OP_AXIS_REVOLVE = 18, /* 3 args radius, cos, sin (axis_revolution :438-472) */
+  AB_OP_REP_INF = 19,    /* 6 args d(3), d/2(3) (infinite_repetition :803-825) */
+  AB_OP_REP_FIN = 20,    /* 12 args c,d,s,s/2 (finite_repetition :827-873) */
+  AB_OP_LIN_INST = 21,   /* a = (n>2); 6 args (linear_instancing :1035-1088, after its frame as AFFINE) */
+  AB_OP_CURVE_INST = 22, /* a = mode (0 positions only, 1 positions + 3x3 frames); args: n, then n records
+                            (curve_instancing :1090-1132, aligned :1134-1196, fully aligned :1198-1266) */
+  AB_OP_ZERO_Z = 23,     /* z = 0 */
+  /* --- value ops --- */
+  AB_OP_ROUND = 32,      /* acc -= r (rounding :100) */
+  AB_OP_ABS = 33,        /* boundary :146 */
+  AB_OP_NEG = 34,        /* invert :277 */
+  AB_OP_SIGN = 35,       /* sign :301 */
+  AB_OP_ONION = 36,      /* |acc| - t (onion :371) */
+  AB_OP_CONCENTRIC = 37, /* |acc - h| (concentric :390) */
+  AB_OP_SCALE_V = 38,    /* acc *= k (node scale, transformations.py:242) */
+  AB_OP_EXTRUDE_BEGIN = 39, /* a = V slot; 1 arg h/2: V[a] = |z| - h/2 ; z = 0 (extrusion :474-500) */
+  AB_OP_EXTRUDE_END = 40,   /* a = V slot */
+  /* post-processing value maps (post_processing.py:380-560; wrappers modifications.py:1361-1587) */
+  AB_OP_PP_SIGMOID = 48, AB_OP_PP_POS_SIGMOID = 49, AB_OP_PP_CAPPED_EXP = 50, AB_OP_PP_HARD_BIN = 51,
+  AB_OP_PP_LINEAR = 52, AB_OP_PP_RELU = 53, AB_OP_PP_SMOOTH_RELU = 54, AB_OP_PP_SLOWSTART = 55,
+  AB_OP_PP_GAUSS_BOUNDARY = 56, AB_OP_PP_GAUSS_FALLOFF = 57,
+  /* --- combine ops: acc = f(V[a], acc)  (combine.py:51-78) --- */
+  AB_OP_C_UNION = 64, AB_OP_C_INTERSECT = 65, AB_OP_C_SUBTRACT = 66, AB_OP_C_SUM = 67, AB_OP_C_DIFF = 68,
+  AB_OP_C_SMIN2 = 69,     /* smoothmin_poly2, 1 arg w (combine.py:12-18) */
+  AB_OP_C_SMIN3 = 70,     /* smoothmin_poly3 (combine.py:20-26) */
+  AB_OP_C_SMAX3 = 71,     /* -smin3(-a,-b) */
+  AB_OP_C_SSUB3 = 72,     /* -smin3(-a, b) */
+  AB_OP_C_BOLTZ_INT = 73, /* smoothmax_boltz(a, b) (combine.py:29-34) */
+  AB_OP_C_BOLTZ_SUB = 74, /* smoothmax_boltz(a,-b) */
+  /* --- 3D primitives: acc = sdf(p) (sdf_3D.py) --- */
+  AB_OP_P_SPHERE = 96, AB_OP_P_CYLINDER = 97, AB_OP_P_BOX = 98, AB_OP_P_TORUS = 99, AB_OP_P_CHAINLINK = 100,
+  AB_OP_P_BRAID = 101, AB_OP_P_ARC3D = 102, AB_OP_P_PLANE = 103, AB_OP_P_UPLANE = 104, AB_OP_P_SEGMENT = 105,
+  AB_OP_P_CONE = 106, AB_OP_P_OINF_CONE = 107, AB_OP_P_INF_CONE = 108, AB_OP_P_SOLID_ANGLE = 109,
+  AB_OP_P_TRIANGLE3D = 110, AB_OP_P_QUAD3D = 111, AB_OP_P_SEGLINE = 112, AB_OP_P_AXIS = 113,
+  AB_OP_P_POINT_CLOUD = 114, /* a = dim (2|3), b = blob index: brute-force min distance (sdf_3D.py:283-286) */
+  /* --- 2D primitives (sdf_2D.py), evaluated on (x,y) --- */
+  AB_OP_P_CIRCLE = 128, AB_OP_P_NEU_CIRCLE = 129, AB_OP_P_BOX2D = 130, AB_OP_P_SEGMENT2D = 131,
+  AB_OP_P_RBOX2D = 132, AB_OP_P_TRIANGLE2D = 133, AB_OP_P_ARC = 134, AB_OP_P_SECTOR = 135,
+  AB_OP_P_INF_SECTOR = 136, AB_OP_P_NGON = 137, AB_OP_P_SEGLINE2D = 138,
+  AB_OP__COUNT = 160
+} ab_opcode;
+
+/* A point cloud (or other bulk table) referenced by an op. `data` is (dim, count) row-major float64 on the host
+ * (SPOMSO's own layout, geom_3d.py:759-777) when on_device == 0, or a device pointer to `count` float4
+ * (x, y, z, 0) records prepared by ab_cloud_upload when on_device == 1. */
+typedef struct ab_blob {
+  const void* data;
+  uint64_t count;
+  int32_t dim;
+  int32_t on_device;
+} ab_blob;
+
+typedef struct ab_program {
+  const ab_op* ops;
+  uint32_t n_ops;
+  const double* args;  /* fp64 pool; narrowed to fp32 by the library for AB_F32 */
+  uint32_t n_args;
+  const double* dargs; /* d args / d theta (AB_GRAD_PARAM only), same length as args, else NULL */
+  const ab_blob* blobs;
+  uint32_t n_blobs;
+  uint32_t n_pslots;   /* P-slots used (<= AB_MAX_PSLOTS) */
+  uint32_t n_vslots;   /* V-slots used (<= AB_MAX_VSLOTS) */
+} ab_program;
+
+/* Regular grid exactly as generate_grid builds it (helper_functions.py:23-93): per axis
+ * np.linspace(-size/2, size/2, res); flat index k = (ix*res[1] + iy)*res[2] + iz (z fastest).
+ * 2D grids: res[2] = 1, size[2] = 0. The slab [slab_begin, slab_end) is a range of ix planes; outputs are
+ * indexed from the slab's first point. */
+typedef struct ab_grid {
+  double size[3];
+  uint32_t res[3];
+  uint32_t slab_begin;
+  uint32_t slab_end;
+} ab_grid;
+
+int ab_version(void);
+const char* ab_last_error(void);
+/* Number of CUDA devices visible (0 => every compute call returns AB_ENODEVICE). */
+int ab_device_count(void);
+
+/* Replaces GenericGeometry.create(co) for co produced by generate_grid (geom.py:29-43): coordinates are
+ * regenerated in-kernel. out: device pointer, (slab points,) of dtype. out_grad: device pointer (3, grad_stride)
+ * of dtype for AB_GRAD_SPATIAL, (1, grad_stride) for AB_GRAD_PARAM, NULL for AB_GRAD_NONE. */
+int ab_eval_grid(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out, void* out_grad,
+                 uint64_t grad_stride, int device, void* stream);
+
+/* Replaces GenericGeometry.create(co) for arbitrary co (geom.py:29-43). co: DEVICE pointer (3, co_stride) of
+ * co_dtype (SPOMSO hands in float64). */
+int ab_eval_points(const ab_program* prog, const void* co, int co_dtype, uint64_t co_stride, uint64_t n, int dtype,
+                   int grad_mode, void* out, void* out_grad, uint64_t grad_stride, int device, void* stream);
+
+/* Host-buffer variants (what the Python drop-in calls when the user wants a NumPy array back): allocate/reuse
+ * device scratch, run, copy the result to `out_host` (pinned or pageable), synchronise. */
+int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out_host,
+                      void* out_grad_host, uint64_t grad_stride, int device);
+int ab_eval_points_host(const ab_program* prog, const double* co_host, uint64_t co_stride, uint64_t n, int dtype,
+                        int grad_mode, void* out_host, void* out_grad_host, uint64_t grad_stride, int device);
+
+/* Replaces sdf_point_cloud_3d / sdf_point_cloud_2d (sdf_3D.py:283-286, sdf_2D.py:221-224) on a grid: unsigned
+ * distance to the nearest cloud point, brute force, exact (q-p)^2 form. cloud: DEVICE float4 records from
+ * ab_cloud_upload. */
+int ab_nn_grid(const void* cloud_dev, uint64_t m, int dim, const ab_grid* grid, int dtype, void* out, int device,
+               void* stream);
+int ab_nn_points(const void* cloud_dev, uint64_t m, int dim, const void* co, int co_dtype, uint64_t co_stride,
+                 uint64_t n, int dtype, void* out, int device, void* stream);
+
+/* Converts a host (dim, m) float64 cloud into the device record layout; *out_dev is cudaMalloc'ed (free with
+ * ab_device_free). */
+int ab_cloud_upload(const double* points_host, uint64_t m, int dim, uint64_t row_stride, int device, void** out_dev);
+
+/* Replaces from_sdf (vector_functions.py:130-139): np.gradient of the reshaped field (unit spacing, 2nd-order
+ * central inside, 1st-order one-sided on the faces) and, if normalize != 0, batch_normalize
+ * (vector_modification_functions.py:14-20). field: DEVICE (points of the whole grid) of dtype; out: DEVICE
+ * (dims, out_stride). The slab selects which ix planes are written (halo planes are read from `field`, which
+ * must hold planes [max(slab_begin-1,0), min(slab_end+1,res0)) starting at `field_plane0`). */
+int ab_fd_gradient(const void* field, uint32_t field_plane0, const ab_grid* grid, int dims, int dtype, int normalize,
+                   void* out, uint64_t out_stride, int device, void* stream);
+
+/* Device / pinned-host memory helpers for callers without their own CUDA allocator (ctypes users). */
+int ab_device_alloc(uint64_t bytes, int device, void** out_dev);
+int ab_device_free(void* dev, int device);
+int ab_host_alloc_pinned(uint64_t bytes, void** out_host);
+int ab_host_free_pinned(void* host);
+int ab_memcpy_d2h(void* dst_host, const void* src_dev, uint64_t bytes, int device, void* stream);
+int ab_memcpy_h2d(void* dst_dev, const void* src_host, uint64_t bytes, int device, void* stream);
+int ab_stream_sync(int device, void* stream);
+
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+uint64_t ab_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEGOLIUS_B200_H */

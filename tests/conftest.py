@@ -1,0 +1,50 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "reference: needs the SPOMSO sources under /root/reference (build container only)")
+
+
+def has_cuda():
+    try:
+        from aegolius_b200 import cabi
+        return cabi.device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    ref = os.path.isdir("/root/reference/Code/spomso")
+    for item in items:
+        if "reference" in item.keywords and not ref:
+            item.add_marker(pytest.mark.skip(reason="/root/reference not present (GPU box)"))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "scenarios.npz")
+    return np.load(path, allow_pickle=False)
+
+
+def golden_names():
+    path = os.path.join(ROOT, "tests", "golden", "scenarios.npz")
+    with np.load(path, allow_pickle=False) as d:
+        return [str(n) for n in d["__names__"]]
+
+
+def load_case(golden, name):
+    from aegolius_b200.program import Program
+    keys = {k[len(name) + 1:]: golden[k] for k in golden.files if k.startswith(name + "/")}
+    prog = Program.from_arrays(keys, prefix="prog_")
+    return dict(prog=prog, expected=keys["expected"], size=tuple(float(s) for s in keys["size"]),
+                res=tuple(int(r) for r in keys["res"]), extent=float(keys["extent"]))

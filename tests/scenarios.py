@@ -1,0 +1,404 @@
+"""Scenario builders shared by the golden generator (run against the real SPOMSO) and the parity tests (run
+against aegolius_b200.frontend). Each builder takes a namespace `ns` exposing SPOMSO's class names, so the very
+same construction code drives both front ends.
+
+C1/C2/C3 are BASELINE.json's configs as made concrete in SURVEY.md §8(d); the rest cover every primitive,
+modification and combine op of SURVEY.md §8(a) one at a time, plus geometry-building portions of the reference's
+example scripts (Code/examples/scalar/**, plotting stripped).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SCENARIOS = {}
+
+
+def scenario(name, size, res, extent=None):
+    def deco(fn):
+        SCENARIOS[name] = dict(name=name, build=fn, size=size, res=res, extent=extent or max(size))
+        return fn
+    return deco
+
+
+G3 = ((4.0, 4.0, 4.0), (16, 12, 20))     # -> 17 x 13 x 21
+G3B = ((6.0, 6.0, 6.0), (20, 20, 20))    # -> 21^3
+G2 = ((8.0, 8.0), (64, 48))              # -> 65 x 49
+
+
+def spiral(t, radius, height, freq):  # Code/examples/scalar/3D/spiral_instancing_3D.py:16-22
+    x = radius * np.cos(2 * np.pi * freq * t)
+    y = radius * np.sin(2 * np.pi * freq * t)
+    z = height * t - height / 2
+    return np.asarray((x, y, z))
+
+
+def circle_curve(t, radius):
+    return np.asarray((radius * np.cos(2 * np.pi * t), radius * np.sin(2 * np.pi * t)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs
+
+
+def build_c1(ns):
+    s = ns.Sphere(1.0)
+    s.move((0.5, 0, 0))
+    b = ns.Box(1.5, 1.0, 0.8)
+    b.rotate(np.pi / 5, (0, 0, 1))
+    b.move((-0.4, 0.2, 0.1))
+    return ns.CombineGeometry("SMOOTH_UNION2").combine_parametric(s, b, parameters=0.3)
+
+
+scenario("c1_sphere_box_smooth_union", *G3)(build_c1)
+
+
+def build_c2(ns):
+    rng = np.random.default_rng(0)
+
+    def shapes():
+        return [
+            lambda: ns.Circle(0.8), lambda: ns.Rectangle(1.4, 0.9),
+            lambda: ns.RoundedRectangle(1.5, 1.0, (0.1, 0.2, 0.3, 0.15)), lambda: ns.NGon(0.8, 5),
+            lambda: ns.Triangle((-0.6, -0.4), (0.7, -0.3), (0.1, 0.8)), lambda: ns.Sector(0.9, 0.3, 2.0),
+            lambda: _rounded(ns.Arc(0.7, 0.2, 2.4), 0.1),
+        ]
+
+    def _rounded(o, r):
+        o.rounding(r)
+        return o
+
+    makers = shapes()
+    counter = [0]
+
+    def fresh():
+        o = makers[counter[0] % len(makers)]()
+        counter[0] += 1
+        o.rotate(float(rng.uniform(0, 2 * np.pi)), (0, 0, 1))
+        o.rescale(float(rng.uniform(0.6, 1.6)))
+        t = rng.uniform(-2.5, 2.5, size=2)
+        o.move((float(t[0]), float(t[1]), 0.0))
+        return o
+
+    nonparam = ["UNION2", "UNION", "SUBTRACT2", "INTERSECT2", "INTERSECT", "SUM", "DIFFERENCE"]
+    param = ["SMOOTH_UNION2_2", "SMOOTH_UNION2", "SMOOTH_INTERSECT2", "SMOOTH_INTERSECT2_BOLTZMANN",
+             "SMOOTH_SUBTRACT2", "SMOOTH_SUBTRACT2_BOLTZMANN"]
+    acc = fresh()
+    for op in nonparam:
+        if op in ("UNION2", "UNION"):
+            acc = ns.CombineGeometry(op).combine(acc, fresh())
+        else:
+            side = ns.CombineGeometry(op).combine(fresh(), fresh())
+            acc = ns.CombineGeometry("UNION2").combine(acc, side)
+    for op in param:
+        w = float(rng.uniform(0.2, 0.5))
+        if op in ("SMOOTH_UNION2_2", "SMOOTH_UNION2"):
+            acc = ns.CombineGeometry(op).combine_parametric(acc, fresh(), parameters=w)
+        else:
+            side = ns.CombineGeometry(op).combine_parametric(fresh(), fresh(), parameters=w)
+            acc = ns.CombineGeometry("UNION2").combine(acc, side)
+    return acc
+
+
+scenario("c2_composite_2d_all13", *G2)(build_c2)
+
+
+def build_c3(ns):
+    t = ns.Torus(0.25, 0.2)
+    t.elongation((2, 0, 0))
+    t.rotate(np.pi / 2, (0, 1, 0))
+    g = ns.GenericGeometry(t.propagate, ())
+    g.twist(np.pi)
+    g.bend(2.0, 1.0)
+    g.rotational_symmetry(6, 1.5, 0.1)
+    g.fully_aligned_curve_instancing(spiral, (1, 2, 2), (0, 1, 21))
+    s = ns.Sphere(0.4)
+    s.move((0.2, 0, 0))
+    s.onion(0.05)
+    u = ns.CombineGeometry("SMOOTH_UNION2").combine_parametric(g, s, parameters=0.3)
+    u.rounding(0.01)
+    u.mirror((-1, 0, 0), (1, 0, 0))
+    return u
+
+
+scenario("c3_deep_tree", *G3B)(build_c3)
+
+# ---------------------------------------------------------------------------------------------------------------
+# primitives, one per scenario, each with a non-trivial Euclidean transform
+
+
+def _xf(o, k=0):
+    o.rotate(0.4 + 0.3 * k, (0.3, -0.5, 0.8))
+    o.rescale(1.1 + 0.05 * k)
+    o.move((0.2, -0.15, 0.1))
+    return o
+
+
+def _xf2(o, k=0):
+    o.rotate(0.5 + 0.2 * k, (0, 0, 1))
+    o.rescale(1.3)
+    o.move((0.4, -0.3, 0.0))
+    return o
+
+
+PRIMS3 = {
+    "sphere": lambda ns: ns.Sphere(0.9),
+    "box": lambda ns: ns.Box(1.5, 1.0, 0.8),
+    "cylinder": lambda ns: ns.Cylinder(0.6, 1.4),
+    "infinite_cylinder": lambda ns: ns.InfiniteCylinder(0.5),
+    "torus": lambda ns: ns.Torus(0.9, 0.25),
+    "chainlink": lambda ns: ns.ChainLink(0.5, 0.15, 1.2),
+    "braid": lambda ns: ns.Braid(2.0, 0.4, 0.12, 3.0),
+    "arc3d": lambda ns: ns.Arc3D(0.9, 0.15, 0.3, 2.5),
+    "plane": lambda ns: ns.Plane((0.2, 0.4, 1.0), 0.3),
+    "oriented_plane": lambda ns: ns.OrientedPlane((0.2, -0.4, 1.0), 0.25),
+    "line": lambda ns: ns.Line((-0.8, -0.3, 0.2), (0.9, 0.5, -0.4)),
+    "cone": lambda ns: ns.Cone(1.2, 0.5),
+    "infinite_cone": lambda ns: ns.InfiniteCone(0.6),
+    "oriented_infinite_cone": lambda ns: ns.OrientedInfiniteCone(0.6),
+    "solid_angle": lambda ns: ns.SolidAngle(1.0, 0.2, 1.6),
+    "triangle3d": lambda ns: ns.Triangle3D((-0.8, -0.5, 0.1), (0.9, -0.4, -0.2), (0.1, 0.9, 0.4)),
+    "quad": lambda ns: ns.Quad((-0.8, -0.7, 0.0), (0.8, -0.6, 0.1), (0.9, 0.7, 0.0), (-0.7, 0.8, -0.1)),
+    "axis_x": lambda ns: ns.X(0.3),
+    "axis_y": lambda ns: ns.Y(-0.2),
+    "axis_z": lambda ns: ns.Z(0.1),
+    "segmented_line3d_closed": lambda ns: ns.SegmentedLine3D(
+        np.array([[-1.0, 0.5, 0.9, -0.2], [-0.8, -0.9, 0.7, 1.0], [0.0, 0.4, -0.3, 0.2]]), closed=True),
+}
+for _i, (_n, _b) in enumerate(PRIMS3.items()):
+    scenario("prim3_" + _n, *G3)(lambda ns, _b=_b, _i=_i: _xf(_b(ns), _i % 5))
+
+PRIMS2 = {
+    "circle": lambda ns: ns.Circle(1.1),
+    "neu_circle3": lambda ns: ns.NEUCircle(1.0, 3),
+    "neu_circle1": lambda ns: ns.NEUCircle(1.0, 1),
+    "rectangle": lambda ns: ns.Rectangle(2.2, 1.3),
+    "rounded_rectangle": lambda ns: ns.RoundedRectangle(2.4, 1.6, (0.1, 0.3, 0.5, 0.2)),
+    "segment": lambda ns: ns.Segment((-1.2, -0.6), (1.5, 0.9)),
+    "triangle": lambda ns: ns.Triangle((-1.2, -0.8), (1.4, -0.6), (0.2, 1.6)),
+    "arc": lambda ns: ns.Arc(1.4, 0.3, 2.6),
+    "sector": lambda ns: ns.Sector(1.6, 0.4, 2.2),
+    "inf_sector": lambda ns: ns.InfiniteSector(0.3, 1.9),
+    "ngon5": lambda ns: ns.NGon(1.3, 5),
+    "ngon8": lambda ns: ns.NGon(1.1, 8),
+    "segmented_line": lambda ns: ns.SegmentedLine(np.array([[-2.0, -0.5, 0.7, 2.1], [-1.0, 1.2, -0.9, 0.8]])),
+    "segmented_line_closed": lambda ns: ns.SegmentedLine(
+        np.array([[-2.0, -0.5, 0.7, 2.1], [-1.0, 1.2, -0.9, 0.8]]), closed=True),
+}
+for _i, (_n, _b) in enumerate(PRIMS2.items()):
+    scenario("prim2_" + _n, *G2)(lambda ns, _b=_b, _i=_i: _xf2(_b(ns), _i % 4))
+
+# ---------------------------------------------------------------------------------------------------------------
+# modifications, one per scenario
+
+
+def _mod(base, fn):
+    def build(ns):
+        o = base(ns)
+        fn(o)
+        o.rotate(0.35, (0.2, 1.0, 0.4))
+        o.move((0.1, 0.05, -0.1))
+        return o
+    return build
+
+
+_box = lambda ns: ns.Box(0.9, 0.5, 0.35)
+_rect = lambda ns: ns.Rectangle(0.8, 0.5)
+MODS = {
+    "elongation": _mod(lambda ns: ns.Torus(0.4, 0.15), lambda o: o.elongation((0.8, 0.3, 0.2))),
+    "rounding": _mod(_box, lambda o: o.rounding(0.12)),
+    "rounding_cs": _mod(_box, lambda o: o.rounding_cs(0.1, 0.9)),
+    "boundary": _mod(_box, lambda o: o.boundary()),
+    "invert": _mod(_box, lambda o: o.invert()),
+    "sign": _mod(_box, lambda o: o.sign()),
+    "invert_direct": _mod(_box, lambda o: o.invert(direct=True)),
+    "onion": _mod(_box, lambda o: o.onion(0.07)),
+    "concentric": _mod(_box, lambda o: o.concentric(0.2)),
+    "revolution": _mod(_rect, lambda o: o.revolution(0.9)),
+    "axis_revolution": _mod(_rect, lambda o: o.axis_revolution(0.8, 0.5)),
+    "extrusion": _mod(lambda ns: ns.NGon(0.7, 6), lambda o: o.extrusion(0.8)),
+    "twist": _mod(_box, lambda o: o.twist(2.5)),
+    "bend": _mod(lambda ns: ns.Box(2.4, 0.4, 0.3), lambda o: o.bend(1.2, 1.3)),
+    "shear_xz": _mod(_box, lambda o: o.shear_xz(0.4)),
+    "shear_yz": _mod(_box, lambda o: o.shear_yz(0.4)),
+    "shear_xy": _mod(_box, lambda o: o.shear_xy(0.3)),
+    "shear_zy": _mod(_box, lambda o: o.shear_zy(0.3)),
+    "shear_yx": _mod(_box, lambda o: o.shear_yx(0.5)),
+    "shear_zx": _mod(_box, lambda o: o.shear_zx(0.5)),
+    "shear_generic": _mod(_box, lambda o: o.shear(0.35, 1, 2)),
+    "infinite_repetition": _mod(lambda ns: ns.Sphere(0.25), lambda o: o.infinite_repetition((0.9, 1.1, 1.3))),
+    "finite_repetition": _mod(lambda ns: ns.Sphere(0.2), lambda o: o.finite_repetition((2.4, 1.8, 1.2), (4, 3, 2))),
+    "finite_repetition_rescaled": _mod(
+        lambda ns: ns.Sphere(0.2),
+        lambda o: o.finite_repetition_rescaled((2.4, 1.8, 1.2), (4, 3, 2), (0.4, 0.4, 0.4), (0.1, 0.1, 0.1))),
+    "symmetry": _mod(lambda ns: _moved(ns.Box(0.6, 0.4, 0.3), (0.5, 0.2, 0.1)), lambda o: o.symmetry(0)),
+    "mirror": _mod(_box, lambda o: o.mirror((-0.8, -0.2, 0.0), (0.7, 0.4, 0.3))),
+    "rotational_symmetry": _mod(lambda ns: ns.Box(0.5, 0.25, 0.3), lambda o: o.rotational_symmetry(5, 1.0, 0.2)),
+    "linear_instancing": _mod(lambda ns: ns.Sphere(0.2), lambda o: o.linear_instancing(5, (-1.2, -0.3, 0.1), (1.1, 0.6, 0.4))),
+    "linear_instancing2": _mod(lambda ns: ns.Sphere(0.2), lambda o: o.linear_instancing(2, (-1.0, 0.0, 0.0), (1.0, 0.2, 0.0))),
+    "curve_instancing": _mod(lambda ns: ns.Box(0.3, 0.15, 0.2), lambda o: o.curve_instancing(spiral, (1, 2, 2), (0, 1, 13))),
+    "aligned_curve_instancing": _mod(lambda ns: ns.Box(0.3, 0.15, 0.2),
+                                     lambda o: o.aligned_curve_instancing(spiral, (1, 2, 2), (0, 1, 13))),
+    "fully_aligned_curve_instancing": _mod(lambda ns: ns.Box(0.3, 0.15, 0.2),
+                                           lambda o: o.fully_aligned_curve_instancing(spiral, (1, 2, 2), (0, 1, 13))),
+    "curve_instancing_2dcurve": _mod(lambda ns: ns.Sphere(0.15), lambda o: o.curve_instancing(circle_curve, (1.2,), (0, 0.9, 9))),
+    "move_sdf": _mod(_box, lambda o: o.move_sdf((0.3, -0.2, 0.4))),
+    "scale_sdf": _mod(_box, lambda o: o.scale_sdf(1.7)),
+    "rotate_sdf": _mod(_box, lambda o: o.rotate_sdf(np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]))),
+    "chain_twist_elong_round": _mod(_box, lambda o: (o.rounding(0.05), o.elongation((0.2, 0.1, 0.4)), o.twist(1.5))),
+    "pp_sigmoid": _mod(_box, lambda o: o.sigmoid_falloff(2.0, 0.5)),
+    "pp_pos_sigmoid": _mod(_box, lambda o: o.positive_sigmoid_falloff(2.0, 0.5)),
+    "pp_capped_exp": _mod(_box, lambda o: o.capped_exponential(1.5, 0.8)),
+    "pp_hard_bin": _mod(_box, lambda o: o.hard_binarization(0.1)),
+    "pp_linear": _mod(_box, lambda o: o.linear_falloff(1.5, 0.8)),
+    "pp_relu": _mod(_box, lambda o: o.relu(0.7)),
+    "pp_smooth_relu": _mod(_box, lambda o: o.smooth_relu(0.3, 0.7, 0.02)),
+    "pp_slowstart": _mod(_box, lambda o: o.slowstart(0.3, 0.7, 0.02)),
+    "pp_gauss_boundary": _mod(_box, lambda o: o.gaussian_boundary(1.2, 0.6)),
+    "pp_gauss_falloff": _mod(_box, lambda o: o.gaussian_falloff(1.2, 0.6)),
+}
+
+
+def _moved(o, v):
+    o.move(v)
+    return o
+
+
+for _n, _b in MODS.items():
+    scenario("mod_" + _n, *G3)(_b)
+
+# ---------------------------------------------------------------------------------------------------------------
+# the 13 combine ops
+
+
+def _combine(op, w=None, n=2):
+    def build(ns):
+        a = ns.Sphere(0.8)
+        a.move((0.4, 0.1, 0.0))
+        b = ns.Box(1.2, 0.9, 0.7)
+        b.rotate(0.6, (0, 1, 1))
+        b.move((-0.3, 0.0, 0.2))
+        kids = [a, b]
+        if n == 3:
+            c = ns.Torus(0.7, 0.2)
+            c.move((0.0, -0.5, 0.3))
+            kids.append(c)
+        cg = ns.CombineGeometry(op)
+        out = cg.combine(*kids) if w is None else cg.combine_parametric(*kids, parameters=w)
+        out.rotate(0.2, (1, 0, 0))
+        out.rescale(0.9)
+        out.move((0.05, 0.1, -0.05))
+        return out
+    return build
+
+
+for _op in ["UNION2", "SUBTRACT2", "INTERSECT2", "SUM", "DIFFERENCE"]:
+    scenario("comb_" + _op, *G3)(_combine(_op))
+scenario("comb_UNION_3", *G3)(_combine("UNION", n=3))
+scenario("comb_INTERSECT_3", *G3)(_combine("INTERSECT", n=3))
+for _op in ["SMOOTH_UNION2_2", "SMOOTH_UNION2", "SMOOTH_INTERSECT2", "SMOOTH_INTERSECT2_BOLTZMANN",
+            "SMOOTH_SUBTRACT2", "SMOOTH_SUBTRACT2_BOLTZMANN"]:
+    scenario("comb_" + _op, *G3)(_combine(_op, w=0.35))
+scenario("comb_SMOOTH_UNION2_w0", *G3)(_combine("SMOOTH_UNION2", w=0.0))
+
+# ---------------------------------------------------------------------------------------------------------------
+# structure: nesting via propagate, nested combines with modifications on combined nodes
+
+
+def build_nested(ns):  # Code/examples/scalar/3D/basics_3D.py:101-111 pattern
+    box = ns.Box(1.0, 0.6, 0.4)
+    box.move((0.6, 0.0, 0.0))
+    box.rotate(0.7, (0, 0, 1))
+    outer = ns.GenericGeometry(box.propagate, ())
+    outer.twist(1.2)
+    outer.rescale(1.2)
+    outer.move((0.0, 0.3, 0.0))
+    return outer
+
+
+scenario("struct_nested_propagate", *G3)(build_nested)
+
+
+def build_plate(ns):  # Code/examples/scalar/3D/plate_3D.py:62-75 (geometry portion)
+    seg1 = ns.Segment((0.0, 0.0), (1.0, 0.0))
+    seg1.rounding(0.1)
+    arc = ns.Arc(0.5, 0.0, np.pi / 2)
+    arc.rounding(0.1)
+    arc.move((1.0, 0.5, 0.0))
+    profile = ns.CombineGeometry("UNION2").combine(seg1, arc)
+    profile.revolution(0.0)
+    profile.rotate(np.pi / 2, (1, 0, 0))
+    profile.move((0.0, 0.0, -0.3))
+    return profile
+
+
+scenario("struct_plate_revolved_union", *G3)(build_plate)
+
+
+def build_deep_combines(ns):
+    a = ns.Sphere(0.7)
+    b = ns.Cylinder(0.3, 2.0)
+    b.rotate(np.pi / 2, (1, 0, 0))
+    c = ns.Box(1.0, 1.0, 1.0)
+    ab = ns.CombineGeometry("SUBTRACT2").combine(a, b)
+    ab.onion(0.05)
+    cab = ns.CombineGeometry("SMOOTH_INTERSECT2").combine_parametric(c, ab, parameters=0.2)
+    d = ns.Torus(0.9, 0.1)
+    d.move((0, 0, 0.2))
+    e = ns.CombineGeometry("UNION").combine(cab, d, ns.Sphere(0.2))
+    e.symmetry(1)
+    e.rescale(1.3)
+    f = ns.Cone(1.0, 0.4)
+    f.move((1.2, 0.0, 0.0))
+    g = ns.CombineGeometry("SMOOTH_UNION2_2").combine_parametric(f, e, parameters=0.25)
+    return g
+
+
+scenario("struct_deep_combines", *G3)(build_deep_combines)
+
+
+def build_extruded_combo(ns):
+    a = ns.Circle(0.7)
+    b = ns.Rectangle(1.6, 0.5)
+    b.rotate(0.5, (0, 0, 1))
+    u = ns.CombineGeometry("SMOOTH_UNION2").combine_parametric(a, b, parameters=0.2)
+    u.extrusion(0.8)
+    u.rounding(0.05)
+    u.rotate(0.4, (1, 1, 0))
+    return u
+
+
+scenario("struct_extruded_combo", *G3)(build_extruded_combo)
+
+
+def build_2d_mirror_symmetry(ns):  # Code/examples/scalar/2D/mirror_symmetry_2D.py pattern
+    c = ns.Circle(0.5)
+    c.move((1.0, 0.4, 0.0))
+    r = ns.Rectangle(1.0, 0.4)
+    r.move((1.5, -0.6, 0.0))
+    u = ns.CombineGeometry("UNION2").combine(c, r)
+    u.mirror((-1.0, -0.5, 0.0), (1.0, 0.5, 0.0))
+    u.rotational_symmetry(3, 0.5, 0.3)
+    return u
+
+
+scenario("struct_2d_mirror_rotsym", *G2)(build_2d_mirror_symmetry)
+
+
+def make_namespace(kind):
+    """kind = 'reference' (needs /root/reference or an installed spomso) or 'frontend'."""
+    import types
+    ns = types.SimpleNamespace()
+    if kind == "reference":
+        from spomso.cores import geom_2d, geom_3d, combine, geom
+        for m in (geom_2d, geom_3d):
+            for k, v in vars(m).items():
+                if isinstance(v, type):
+                    setattr(ns, k, v)
+        ns.CombineGeometry = combine.CombineGeometry
+        ns.GenericGeometry = geom.GenericGeometry
+    else:
+        from aegolius_b200 import frontend
+        for k, v in vars(frontend).items():
+            if isinstance(v, type):
+                setattr(ns, k, v)
+    return ns
