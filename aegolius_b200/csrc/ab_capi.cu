@@ -1,0 +1,604 @@
+// ab_capi.cu — the C ABI of libaegolius_b200.so (see include/aegolius_b200.h for the contract and the reference
+// interfaces each entry point replaces). Plain pointers and sizes in, status codes out; no torch types.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "ab_kernels_aux.cuh"
+
+using namespace ab;
+
+// ---- error handling ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) return fail(AB_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));    \
+  } while (0)
+
+extern "C" int ab_version(void) { return AB_VERSION; }
+extern "C" const char* ab_last_error(void) { return g_err; }
+extern "C" uint64_t ab_launch_count(void) { return g_launches.load(); }
+extern "C" int ab_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static int use_device(int device) {
+  int n = ab_device_count();
+  if (n == 0) return fail(AB_ENODEVICE, "no CUDA device visible: aegolius_b200 has no CPU fallback");
+  if (device < 0 || device >= n) return fail(AB_EINVAL, "device %d out of range (have %d)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  return AB_OK;
+}
+
+struct DevInfo {
+  int sms = 0;
+  size_t smem_optin = 0;
+  bool ok = false;
+};
+static DevInfo g_dev[64];
+static std::mutex g_dev_mu;
+static int dev_info(int device, DevInfo& out) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!g_dev[device].ok) {
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    g_dev[device].sms = p.multiProcessorCount;
+    g_dev[device].smem_optin = p.sharedMemPerBlockOptin;
+    g_dev[device].ok = true;
+  }
+  out = g_dev[device];
+  return AB_OK;
+}
+
+// ---- program validation ---------------------------------------------------------------------------------------------------
+static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, int* out) {
+  int n = -1;
+  switch (op.opcode) {
+    case AB_OP_END: case AB_OP_SAVE_P: case AB_OP_LOAD_P: case AB_OP_PUSH_V: case AB_OP_SYMMETRY: case AB_OP_ZERO_Z:
+    case AB_OP_ABS: case AB_OP_NEG: case AB_OP_SIGN: case AB_OP_EXTRUDE_END: case AB_OP_C_UNION: case AB_OP_C_INTERSECT:
+    case AB_OP_C_SUBTRACT: case AB_OP_C_SUM: case AB_OP_C_DIFF: case AB_OP_P_POINT_CLOUD:
+      n = 0; break;
+    case AB_OP_SCALE_P: case AB_OP_TWIST: case AB_OP_ABSX_SUB: case AB_OP_REVOLVE: case AB_OP_ROUND: case AB_OP_ONION:
+    case AB_OP_CONCENTRIC: case AB_OP_SCALE_V: case AB_OP_EXTRUDE_BEGIN: case AB_OP_PP_HARD_BIN: case AB_OP_PP_RELU:
+    case AB_OP_C_SMIN2: case AB_OP_C_SMIN3: case AB_OP_C_SMAX3: case AB_OP_C_SSUB3: case AB_OP_C_BOLTZ_INT:
+    case AB_OP_C_BOLTZ_SUB: case AB_OP_P_SPHERE: case AB_OP_P_AXIS: case AB_OP_P_CIRCLE:
+      n = 1; break;
+    case AB_OP_ROTSYM: case AB_OP_PP_SIGMOID: case AB_OP_PP_POS_SIGMOID: case AB_OP_PP_CAPPED_EXP: case AB_OP_PP_LINEAR:
+    case AB_OP_PP_SMOOTH_RELU: case AB_OP_PP_GAUSS_BOUNDARY: case AB_OP_PP_GAUSS_FALLOFF: case AB_OP_P_CYLINDER:
+    case AB_OP_P_TORUS: case AB_OP_P_OINF_CONE: case AB_OP_P_INF_CONE: case AB_OP_P_NEU_CIRCLE: case AB_OP_P_BOX2D:
+      n = 2; break;
+    case AB_OP_TRANSLATE: case AB_OP_AXIS_REVOLVE: case AB_OP_PP_SLOWSTART: case AB_OP_P_BOX: case AB_OP_P_CHAINLINK:
+      n = 3; break;
+    case AB_OP_P_BRAID: case AB_OP_P_PLANE: case AB_OP_P_UPLANE: case AB_OP_P_CONE: case AB_OP_P_ARC:
+      n = 4; break;
+    case AB_OP_P_ARC3D: case AB_OP_P_SEGMENT2D: case AB_OP_P_INF_SECTOR: n = 5; break;
+    case AB_OP_ELONGATE: case AB_OP_REP_INF: case AB_OP_LIN_INST: case AB_OP_P_SOLID_ANGLE: case AB_OP_P_RBOX2D:
+    case AB_OP_P_SECTOR:
+      n = 6; break;
+    case AB_OP_P_SEGMENT: case AB_OP_P_NGON: n = 7; break;
+    case AB_OP_BEND: n = 8; break;
+    case AB_OP_AFFINE: case AB_OP_REP_FIN: n = 12; break;
+    case AB_OP_P_TRIANGLE2D: n = 16; break;
+    case AB_OP_P_TRIANGLE3D: n = 34; break;
+    case AB_OP_P_QUAD3D: n = 44; break;
+    case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: {
+      if (op.arg >= n_args) return fail(AB_EINVAL, "op argument offset out of range");
+      double c = args[op.arg];
+      if (!(c >= 0) || c > 1e6) return fail(AB_EINVAL, "bad element count %g", c);
+      int per = op.opcode == AB_OP_CURVE_INST ? (op.a ? 12 : 3) : (op.opcode == AB_OP_P_SEGLINE ? 3 : 2);
+      n = 1 + (int)c * per;
+    } break;
+    default: return fail(AB_EUNSUPPORTED_OP, "opcode %u is not supported by this build", (unsigned)op.opcode);
+  }
+  *out = n;
+  return AB_OK;
+}
+
+static int validate(const ab_program* prog) {
+  if (!prog || !prog->ops || (prog->n_args && !prog->args)) return fail(AB_EINVAL, "null program");
+  if (prog->n_ops == 0) return fail(AB_EINVAL, "empty program");
+  if (prog->n_ops > AB_MAX_OPS || prog->n_args > AB_MAX_ARGS)
+    return fail(AB_ETOOLARGE, "program too large: %u ops / %u args (limits %d / %d)", prog->n_ops, prog->n_args,
+                AB_MAX_OPS, AB_MAX_ARGS);
+  if (prog->n_pslots > AB_MAX_PSLOTS || prog->n_vslots > AB_MAX_VSLOTS)
+    return fail(AB_ETOOLARGE, "too many stack slots (%u P, %u V)", prog->n_pslots, prog->n_vslots);
+  if (prog->n_blobs > AB_MAX_BLOBS) return fail(AB_ETOOLARGE, "too many blobs");
+  bool have_value = false;
+  for (uint32_t i = 0; i < prog->n_ops; i++) {
+    const ab_op& op = prog->ops[i];
+    int n = 0;
+    int rc = op_arg_count(op, prog->args, prog->n_args, &n);
+    if (rc) return rc;
+    if (n > 0 && (uint64_t)op.arg + n > prog->n_args) return fail(AB_EINVAL, "op %u reads past the argument pool", i);
+    switch (op.opcode) {
+      case AB_OP_SAVE_P: case AB_OP_LOAD_P:
+        if (op.a >= prog->n_pslots) return fail(AB_EINVAL, "op %u: P slot %u >= n_pslots %u", i, op.a, prog->n_pslots);
+        break;
+      case AB_OP_PUSH_V: case AB_OP_EXTRUDE_BEGIN: case AB_OP_EXTRUDE_END:
+        if (op.a >= prog->n_vslots) return fail(AB_EINVAL, "op %u: V slot %u >= n_vslots %u", i, op.a, prog->n_vslots);
+        break;
+      case AB_OP_P_POINT_CLOUD:
+        if (op.b >= prog->n_blobs || !prog->blobs) return fail(AB_EINVAL, "op %u: blob %u missing", i, op.b);
+        if (op.a != 2 && op.a != 3) return fail(AB_EINVAL, "op %u: point cloud dim must be 2 or 3", i);
+        if (prog->blobs[op.b].count == 0 || prog->blobs[op.b].count > 0xffffffffull)
+          return fail(AB_EINVAL, "op %u: point cloud size out of range", i);
+        break;
+      case AB_OP_SYMMETRY: case AB_OP_P_AXIS:
+        if (op.a > 2) return fail(AB_EINVAL, "op %u: axis %u", i, op.a);
+        break;
+      default:
+        if (op.opcode >= AB_OP_C_UNION && op.opcode <= AB_OP_C_BOLTZ_SUB && op.a >= prog->n_vslots)
+          return fail(AB_EINVAL, "op %u: V slot %u >= n_vslots %u", i, op.a, prog->n_vslots);
+    }
+    if (op.opcode >= AB_OP_P_SPHERE) have_value = true;
+    if (op.opcode == AB_OP_END) break;
+  }
+  if (!have_value) return fail(AB_EINVAL, "program has no primitive");
+  return AB_OK;
+}
+
+// ---- grid description -> kernel form ---------------------------------------------------------------------------------------
+static int make_gridk(const ab_grid* grid, GridK& g, uint64_t* n_points) {
+  if (!grid) return fail(AB_EINVAL, "null grid");
+  for (int c = 0; c < 3; c++)
+    if (grid->res[c] == 0) return fail(AB_EINVAL, "grid resolution of 0");
+  if (grid->slab_begin >= grid->slab_end || grid->slab_end > grid->res[0])
+    return fail(AB_EINVAL, "bad slab [%u, %u) for res0 %u", grid->slab_begin, grid->slab_end, grid->res[0]);
+  uint64_t plane = (uint64_t)grid->res[1] * grid->res[2];
+  if (plane > 0x7fffffffull) return fail(AB_ETOOLARGE, "ny*nz does not fit 31 bits");
+  g.n1 = grid->res[1];
+  g.n2 = grid->res[2];
+  g.plane = (uint32_t)plane;
+  g.i0_begin = grid->slab_begin;
+  g.inv_plane = 1.0 / (double)plane;
+  g.inv_n2 = 1.0 / (double)grid->res[2];
+  for (int c = 0; c < 3; c++) {
+    uint32_t n = grid->res[c];
+    double start = -grid->size[c] / 2, stop = grid->size[c] / 2;
+    double step = n > 1 ? (stop - start) / (double)(n - 1) : 0.0;  // np.linspace: delta / div
+    g.last[c] = n - 1;
+    g.start[c] = start;
+    g.stop[c] = n > 1 ? stop : start + 0.0;
+    if (n == 1) g.stop[c] = (grid->size[c] == 0.0) ? 0.0 : start;  // linspace(a, b, 1) == [a]; 2D grids: z = +0
+    g.step[c] = step;
+    g.hi[c] = (float)step;
+    g.lo[c] = (float)(step - (double)g.hi[c]);
+    g.centre[c] = (float)((double)(n - 1) * 0.5);
+  }
+  *n_points = (uint64_t)(grid->slab_end - grid->slab_begin) * plane;
+  return AB_OK;
+}
+
+// ---- blobs (point clouds) ---------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload_cloud(const double* pts, uint64_t m, int dim, uint64_t row_stride, cudaStream_t st, void** out_dev,
+                        bool async) {
+  typedef typename Vec4<T>::type V4;
+  std::vector<V4> rec(m);
+  for (uint64_t i = 0; i < m; i++) {
+    rec[i].x = (T)pts[i];
+    rec[i].y = (T)pts[row_stride + i];
+    rec[i].z = dim == 3 ? (T)pts[2 * row_stride + i] : (T)0;
+    rec[i].w = (T)0;
+  }
+  void* d = nullptr;
+  if (async) {
+    CUDA_TRY(cudaMallocAsync(&d, m * sizeof(V4), st));
+    CUDA_TRY(cudaMemcpyAsync(d, rec.data(), m * sizeof(V4), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // rec is a stack-lifetime staging buffer
+  } else {
+    CUDA_TRY(cudaMalloc(&d, m * sizeof(V4)));
+    CUDA_TRY(cudaMemcpy(d, rec.data(), m * sizeof(V4), cudaMemcpyHostToDevice));
+  }
+  *out_dev = d;
+  return AB_OK;
+}
+
+extern "C" int ab_cloud_upload(const double* points_host, uint64_t m, int dim, uint64_t row_stride, int dtype,
+                               int device, void** out_dev) {
+  if (!points_host || !out_dev || m == 0 || (dim != 2 && dim != 3)) return fail(AB_EINVAL, "bad cloud arguments");
+  int rc = use_device(device);
+  if (rc) return rc;
+  return dtype == AB_F64 ? upload_cloud<double>(points_host, m, dim, row_stride, 0, out_dev, false)
+                         : upload_cloud<float>(points_host, m, dim, row_stride, 0, out_dev, false);
+}
+
+// ---- interpreter launch ----------------------------------------------------------------------------------------------------
+template <typename T>
+struct EvalTarget {
+  int grid_mode;
+  GridK g;
+  const void* co;
+  uint64_t co_stride;
+  int co_is_f64;
+  uint64_t n;
+  T* out;
+  T* grad;
+  uint64_t grad_stride;
+};
+
+template <typename S, typename T>
+static int dispatch_nt(const KParams<T>& kp, int device, cudaStream_t st) {
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  LaunchCfg cfg{di.sms, di.smem_optin};
+  int status = AB_OK;
+  cudaError_t e = launch_interp<S, T>(kp, cfg, st, &status);
+  if (e != cudaSuccess) return fail(AB_ECUDA, "interpreter launch: %s", cudaGetErrorString(e));
+  if (status != AB_OK) return fail(status, "interpreter stacks (%u P, %u V slots) do not fit in shared memory", kp.n_pslots, kp.n_vslots);
+  g_launches++;
+  return AB_OK;
+}
+
+template <typename T>
+static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad_mode, int device, cudaStream_t st) {
+  int rc = validate(prog);
+  if (rc) return rc;
+  if (tg.n == 0) return AB_OK;
+  if (!tg.out) return fail(AB_EINVAL, "null output pointer");
+  if (grad_mode == AB_GRAD_PARAM)
+    return fail(AB_EUNSUPPORTED_OP, "AB_GRAD_PARAM (parameter tangents) is not implemented in this build");
+  if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL) return fail(AB_EINVAL, "bad grad_mode %d", grad_mode);
+  if (grad_mode == AB_GRAD_SPATIAL && (!tg.grad || tg.grad_stride < tg.n))
+    return fail(AB_EINVAL, "gradient output missing or grad_stride < n");
+
+  static thread_local KParams<T> kp;  // ~28 KB: keep it off the stack
+  kp.n = tg.n;
+  kp.out = tg.out;
+  kp.grad = tg.grad;
+  kp.grad_stride = tg.grad_stride;
+  kp.co = tg.co;
+  kp.co_stride = tg.co_stride;
+  kp.co_is_f64 = tg.co_is_f64;
+  kp.grid_mode = tg.grid_mode;
+  kp.g = tg.g;
+  kp.n_ops = prog->n_ops;
+  kp.n_pslots = prog->n_pslots ? prog->n_pslots : 1;
+  kp.n_vslots = prog->n_vslots ? prog->n_vslots : 1;
+  memcpy(kp.ops, prog->ops, sizeof(ab_op) * prog->n_ops);
+  for (uint32_t i = 0; i < prog->n_args; i++) kp.args[i] = (T)prog->args[i];
+
+  std::vector<void*> temp_blobs;
+  for (uint32_t b = 0; b < AB_MAX_BLOBS; b++) {
+    kp.blob[b] = nullptr;
+    kp.blob_count[b] = 0;
+  }
+  for (uint32_t b = 0; b < prog->n_blobs; b++) {
+    const ab_blob& bl = prog->blobs[b];
+    if (!bl.data || bl.count == 0 || bl.count > 0xffffffffull) return fail(AB_EINVAL, "blob %u empty or too large", b);
+    if (bl.on_device) {
+      kp.blob[b] = bl.data;
+    } else {
+      void* d = nullptr;
+      rc = upload_cloud<T>((const double*)bl.data, bl.count, 3, bl.count, st, &d, true);
+      if (rc) return rc;
+      temp_blobs.push_back(d);
+      kp.blob[b] = d;
+    }
+    kp.blob_count[b] = (uint32_t)bl.count;
+  }
+
+  constexpr int WV = sizeof(T) == 4 ? 4 : 2;  // one 128-bit store per thread
+  constexpr int WG = sizeof(T) == 4 ? 2 : 1;  // dual numbers carry 4x the state: halve the points per thread
+  if (grad_mode == AB_GRAD_NONE) rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
+  else rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
+  for (void* d : temp_blobs) cudaFreeAsync(d, st);
+  return rc;
+}
+
+template <typename T>
+static int eval_grid_t(const ab_program* prog, const ab_grid* grid, int grad_mode, void* out, void* out_grad,
+                       uint64_t grad_stride, int device, cudaStream_t st) {
+  EvalTarget<T> tg{};
+  int rc = make_gridk(grid, tg.g, &tg.n);
+  if (rc) return rc;
+  tg.grid_mode = 1;
+  tg.out = (T*)out;
+  tg.grad = (T*)out_grad;
+  tg.grad_stride = grad_stride;
+  return run_program<T>(prog, tg, grad_mode, device, st);
+}
+
+extern "C" int ab_eval_grid(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out,
+                            void* out_grad, uint64_t grad_stride, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (dtype == AB_F32) return eval_grid_t<float>(prog, grid, grad_mode, out, out_grad, grad_stride, device, (cudaStream_t)stream);
+  if (dtype == AB_F64) return eval_grid_t<double>(prog, grid, grad_mode, out, out_grad, grad_stride, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+template <typename T>
+static int eval_points_t(const ab_program* prog, const void* co, int co_dtype, uint64_t co_stride, uint64_t n,
+                         int grad_mode, void* out, void* out_grad, uint64_t grad_stride, int device, cudaStream_t st) {
+  if (n && !co) return fail(AB_EINVAL, "null coordinates");
+  if (co_stride < n) return fail(AB_EINVAL, "co_stride < n");
+  EvalTarget<T> tg{};
+  tg.grid_mode = 0;
+  tg.co = co;
+  tg.co_stride = co_stride;
+  tg.co_is_f64 = co_dtype == AB_F64;
+  tg.n = n;
+  tg.out = (T*)out;
+  tg.grad = (T*)out_grad;
+  tg.grad_stride = grad_stride;
+  return run_program<T>(prog, tg, grad_mode, device, st);
+}
+
+extern "C" int ab_eval_points(const ab_program* prog, const void* co, int co_dtype, uint64_t co_stride, uint64_t n,
+                              int dtype, int grad_mode, void* out, void* out_grad, uint64_t grad_stride, int device,
+                              void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (co_dtype != AB_F32 && co_dtype != AB_F64) return fail(AB_EINVAL, "bad co_dtype %d", co_dtype);
+  if (dtype == AB_F32)
+    return eval_points_t<float>(prog, co, co_dtype, co_stride, n, grad_mode, out, out_grad, grad_stride, device, (cudaStream_t)stream);
+  if (dtype == AB_F64)
+    return eval_points_t<double>(prog, co, co_dtype, co_stride, n, grad_mode, out, out_grad, grad_stride, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+// ---- host-buffer variants: per-device scratch, result copied back --------------------------------------------------------------
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+static Scratch g_scratch[64][3];
+static std::mutex g_scratch_mu;
+static int scratch(int device, int which, size_t bytes, void** out) {
+  Scratch& s = g_scratch[device][which];
+  if (s.cap < bytes) {
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr;
+    s.cap = 0;
+    CUDA_TRY(cudaMalloc(&s.p, bytes));
+    s.cap = bytes;
+  }
+  *out = s.p;
+  return AB_OK;
+}
+
+static int grad_rows(int grad_mode) { return grad_mode == AB_GRAD_SPATIAL ? 3 : (grad_mode == AB_GRAD_PARAM ? 1 : 0); }
+
+extern "C" int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out_host,
+                                 void* out_grad_host, uint64_t grad_stride, int device) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (dtype != AB_F32 && dtype != AB_F64) return fail(AB_EINVAL, "bad dtype %d", dtype);
+  GridK g;
+  uint64_t n = 0;
+  rc = make_gridk(grid, g, &n);
+  if (rc) return rc;
+  if (!out_host) return fail(AB_EINVAL, "null output pointer");
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  const size_t es = dtype == AB_F32 ? 4 : 8;
+  const int rows = grad_rows(grad_mode);
+  if (rows && (!out_grad_host || grad_stride < n)) return fail(AB_EINVAL, "gradient output missing or grad_stride < n");
+  const uint64_t dstride = (n + 3) & ~3ull;
+  void *d_out = nullptr, *d_grad = nullptr;
+  rc = scratch(device, 0, n * es, &d_out);
+  if (rc) return rc;
+  if (rows) {
+    rc = scratch(device, 1, dstride * rows * es, &d_grad);
+    if (rc) return rc;
+  }
+  rc = ab_eval_grid(prog, grid, dtype, grad_mode, d_out, d_grad, dstride, device, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_host, d_out, n * es, cudaMemcpyDeviceToHost, 0));
+  for (int r = 0; r < rows; r++)
+    CUDA_TRY(cudaMemcpyAsync((char*)out_grad_host + (size_t)r * grad_stride * es, (char*)d_grad + (size_t)r * dstride * es,
+                             n * es, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return AB_OK;
+}
+
+extern "C" int ab_eval_points_host(const ab_program* prog, const double* co_host, uint64_t co_stride, uint64_t n,
+                                   int dtype, int grad_mode, void* out_host, void* out_grad_host, uint64_t grad_stride,
+                                   int device) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (dtype != AB_F32 && dtype != AB_F64) return fail(AB_EINVAL, "bad dtype %d", dtype);
+  if (n == 0) return validate(prog);
+  if (!co_host || !out_host) return fail(AB_EINVAL, "null pointer");
+  if (co_stride < n) return fail(AB_EINVAL, "co_stride < n");
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  const size_t es = dtype == AB_F32 ? 4 : 8;
+  const int rows = grad_rows(grad_mode);
+  if (rows && (!out_grad_host || grad_stride < n)) return fail(AB_EINVAL, "gradient output missing or grad_stride < n");
+  const uint64_t dstride = (n + 3) & ~3ull;
+  void *d_out = nullptr, *d_grad = nullptr, *d_co = nullptr;
+  rc = scratch(device, 0, n * es, &d_out);
+  if (rc) return rc;
+  rc = scratch(device, 2, 3 * n * 8, &d_co);
+  if (rc) return rc;
+  if (rows) {
+    rc = scratch(device, 1, dstride * rows * es, &d_grad);
+    if (rc) return rc;
+  }
+  for (int r = 0; r < 3; r++)
+    CUDA_TRY(cudaMemcpyAsync((double*)d_co + (size_t)r * n, co_host + (size_t)r * co_stride, n * 8, cudaMemcpyHostToDevice, 0));
+  rc = ab_eval_points(prog, d_co, AB_F64, n, n, dtype, grad_mode, d_out, d_grad, dstride, device, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_host, d_out, n * es, cudaMemcpyDeviceToHost, 0));
+  for (int r = 0; r < rows; r++)
+    CUDA_TRY(cudaMemcpyAsync((char*)out_grad_host + (size_t)r * grad_stride * es, (char*)d_grad + (size_t)r * dstride * es,
+                             n * es, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return AB_OK;
+}
+
+// ---- point cloud -> distance field -------------------------------------------------------------------------------------------
+template <typename T, int Q, int TILE>
+static int launch_nn(const NNParams<T>& kp, int device, cudaStream_t st) {
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  constexpr int NT = 256;
+  auto kern = ab_nn_kernel<T, Q, NT, TILE>;
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, 0));
+  if (occ < 1) occ = 1;
+  const uint64_t tile_pts = (uint64_t)NT * Q;
+  uint64_t n_tiles = (kp.n + tile_pts - 1) / tile_pts;
+  uint64_t resident = (uint64_t)di.sms * occ;
+  unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+  kern<<<grid, NT, 0, st>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return AB_OK;
+}
+
+template <typename T>
+static int nn_t(const void* cloud, uint64_t m, int dim, int grid_mode, const GridK& g, const void* co, int co_dtype,
+                uint64_t co_stride, uint64_t n, void* out, int device, cudaStream_t st) {
+  if (!cloud || m == 0 || m > 0xffffffffull) return fail(AB_EINVAL, "bad cloud (m = %llu)", (unsigned long long)m);
+  if (dim != 2 && dim != 3) return fail(AB_EINVAL, "dim must be 2 or 3");
+  if (n == 0) return AB_OK;
+  if (!out) return fail(AB_EINVAL, "null output pointer");
+  NNParams<T> kp{};
+  kp.n = n;
+  kp.out = (T*)out;
+  kp.cloud = (const typename Vec4<T>::type*)cloud;
+  kp.m = (uint32_t)m;
+  kp.dim = dim;
+  kp.grid_mode = grid_mode;
+  kp.g = g;
+  kp.co = co;
+  kp.co_stride = co_stride;
+  kp.co_is_f64 = co_dtype == AB_F64;
+  if constexpr (sizeof(T) == 4) return launch_nn<T, 8, 1024>(kp, device, st);
+  else return launch_nn<T, 4, 512>(kp, device, st);
+}
+
+extern "C" int ab_nn_grid(const void* cloud_dev, uint64_t m, int dim, const ab_grid* grid, int dtype, void* out,
+                          int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  GridK g;
+  uint64_t n = 0;
+  rc = make_gridk(grid, g, &n);
+  if (rc) return rc;
+  if (dtype == AB_F32) return nn_t<float>(cloud_dev, m, dim, 1, g, nullptr, 0, 0, n, out, device, (cudaStream_t)stream);
+  if (dtype == AB_F64) return nn_t<double>(cloud_dev, m, dim, 1, g, nullptr, 0, 0, n, out, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+extern "C" int ab_nn_points(const void* cloud_dev, uint64_t m, int dim, const void* co, int co_dtype,
+                            uint64_t co_stride, uint64_t n, int dtype, void* out, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (n && !co) return fail(AB_EINVAL, "null coordinates");
+  if (co_stride < n) return fail(AB_EINVAL, "co_stride < n");
+  GridK g{};
+  if (dtype == AB_F32) return nn_t<float>(cloud_dev, m, dim, 0, g, co, co_dtype, co_stride, n, out, device, (cudaStream_t)stream);
+  if (dtype == AB_F64) return nn_t<double>(cloud_dev, m, dim, 0, g, co, co_dtype, co_stride, n, out, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+// ---- from_sdf ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int fd_t(const void* field, uint32_t plane0, const ab_grid* grid, int dims, int normalize, void* out,
+                uint64_t out_stride, int device, cudaStream_t st) {
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  FDParams<T> kp{};
+  kp.field = (const T*)field;
+  kp.plane0 = plane0;
+  for (int c = 0; c < 3; c++) kp.res[c] = grid->res[c];
+  kp.slab_begin = grid->slab_begin;
+  kp.slab_end = grid->slab_end;
+  kp.dims = dims;
+  kp.normalize = normalize;
+  kp.out = (T*)out;
+  kp.out_stride = out_stride;
+  const uint64_t n = (uint64_t)(grid->slab_end - grid->slab_begin) * grid->res[1] * (dims == 3 ? grid->res[2] : 1);
+  if (out_stride < n) return fail(AB_EINVAL, "out_stride < slab points");
+  constexpr int NT = 256;
+  uint64_t blocks = (n + NT - 1) / NT;
+  uint64_t cap = (uint64_t)di.sms * 16;
+  unsigned gridDim = (unsigned)(blocks < cap ? blocks : cap);
+  ab_fd_kernel<T, NT><<<gridDim, NT, 0, st>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return AB_OK;
+}
+
+extern "C" int ab_fd_gradient(const void* field, uint32_t field_plane0, const ab_grid* grid, int dims, int dtype,
+                              int normalize, void* out, uint64_t out_stride, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (!field || !out || !grid) return fail(AB_EINVAL, "null pointer");
+  if (dims != 2 && dims != 3) return fail(AB_EINVAL, "dims must be 2 or 3");
+  if (grid->slab_begin >= grid->slab_end || grid->slab_end > grid->res[0]) return fail(AB_EINVAL, "bad slab");
+  if (field_plane0 > grid->slab_begin) return fail(AB_EINVAL, "field does not cover the slab");
+  if (grid->slab_begin > 0 && field_plane0 > grid->slab_begin - 1) return fail(AB_EINVAL, "field lacks the lower halo plane");
+  if (dtype == AB_F32) return fd_t<float>(field, field_plane0, grid, dims, normalize, out, out_stride, device, (cudaStream_t)stream);
+  if (dtype == AB_F64) return fd_t<double>(field, field_plane0, grid, dims, normalize, out, out_stride, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+// ---- memory helpers ---------------------------------------------------------------------------------------------------------------
+extern "C" int ab_device_alloc(uint64_t bytes, int device, void** out_dev) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (!out_dev) return fail(AB_EINVAL, "null pointer");
+  CUDA_TRY(cudaMalloc(out_dev, bytes ? bytes : 1));
+  return AB_OK;
+}
+extern "C" int ab_device_free(void* dev, int device) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  CUDA_TRY(cudaFree(dev));
+  return AB_OK;
+}
+extern "C" int ab_host_alloc_pinned(uint64_t bytes, void** out_host) {
+  if (!out_host) return fail(AB_EINVAL, "null pointer");
+  if (ab_device_count() == 0) return fail(AB_ENODEVICE, "no CUDA device visible");
+  CUDA_TRY(cudaHostAlloc(out_host, bytes ? bytes : 1, cudaHostAllocDefault));
+  return AB_OK;
+}
+extern "C" int ab_host_free_pinned(void* host) {
+  CUDA_TRY(cudaFreeHost(host));
+  return AB_OK;
+}
+extern "C" int ab_memcpy_d2h(void* dst_host, const void* src_dev, uint64_t bytes, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return AB_OK;
+}
+extern "C" int ab_memcpy_h2d(void* dst_dev, const void* src_host, uint64_t bytes, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return AB_OK;
+}
+extern "C" int ab_stream_sync(int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return AB_OK;
+}

@@ -1,0 +1,476 @@
+// ab_ops.cuh — the interpreter's operations, written once over S (Pack or Dual<Pack>) and the scalar type T of the
+// argument pool. Each function restates the reference semantics cited next to it (paths relative to
+// Code/spomso/spomso/cores/); host-side constant folding is described in aegolius_b200/program.py.
+#pragma once
+#include "ab_math.cuh"
+
+namespace ab {
+
+template <typename S>
+struct Pt {
+  S x, y, z;
+};
+
+// ---- coordinate ops -------------------------------------------------------------------------------------------------
+
+// p = M p + b : folded apply_ec_transforms (transformations.py:232-242), shears, frames
+template <typename S, typename T>
+AB_DEV void op_affine(Pt<S>& p, const T* a) {
+  S nx = fma_(p.x, a[0], fma_(p.y, a[1], fma_(p.z, a[2], a[9])));
+  S ny = fma_(p.x, a[3], fma_(p.y, a[4], fma_(p.z, a[5], a[10])));
+  S nz = fma_(p.x, a[6], fma_(p.y, a[7], fma_(p.z, a[8], a[11])));
+  p.x = nx;
+  p.y = ny;
+  p.z = nz;
+}
+template <typename S, typename T>
+AB_DEV void op_translate(Pt<S>& p, const T* a) {
+  p.x = p.x + a[0];
+  p.y = p.y + a[1];
+  p.z = p.z + a[2];
+}
+template <typename S, typename T>
+AB_DEV void op_scale_p(Pt<S>& p, const T* a) {
+  p.x = p.x * a[0];
+  p.y = p.y * a[0];
+  p.z = p.z * a[0];
+}
+// modifications.py:91-93  q = p - clip(p, -e/2, e/2)
+template <typename S, typename T>
+AB_DEV void op_elongate(Pt<S>& p, const T* a) {
+  p.x = p.x - clamp_(p.x, a[0], a[3]);
+  p.y = p.y - clamp_(p.y, a[1], a[4]);
+  p.z = p.z - clamp_(p.z, a[2], a[5]);
+}
+// modifications.py:516-522
+template <typename S, typename T>
+AB_DEV void op_twist(Pt<S>& p, const T* a) {
+  S s, c;
+  sincos_(p.z * a[0], s, c);
+  S nx = c * p.x - s * p.y;
+  S ny = s * p.x + c * p.y;
+  p.x = nx;
+  p.y = ny;
+}
+// modifications.py:545-573; args r, angle/2, cos, sin, r*angle/2, r*sin, r*(1-cos), r*(angle/2)
+template <typename S, typename T>
+AB_DEV void op_bend(Pt<S>& p, const T* a) {
+  const T r = a[0], c = a[2], s = a[3], thr = a[4], rs = a[5], r1c = a[6], rha = a[7];
+  S qy = p.y - r;
+  S phi = atan2_(p.x, -qy);
+  S ny = norm2_(p.x, qy) - r;
+  S nx = phi * r;
+  Mask<S::width> straight = ge_(abs_(nx), thr);
+  if (any_(straight)) {
+    S sg = sign_(p.x);
+    S w0 = p.x - sg * rs;
+    S w1 = p.y - r1c;
+    Mask<S::width> pos = ge_(p.x, T(0));
+    S sw1 = w1 * s, sw0 = w0 * s;
+    S wr0 = select_(pos, fma_(w0, c, sw1), fma_(w0, c, -sw1));
+    S wr1 = select_(pos, fma_(w1, c, -sw0), fma_(w1, c, sw0));
+    wr0 = wr0 + sg * rha;
+    nx = select_(straight, wr0, nx);
+    ny = select_(straight, wr1, ny);
+  }
+  p.x = nx;
+  p.y = ny;
+}
+// modifications.py:991-993
+template <typename S, typename T>
+AB_DEV void op_absx_sub(Pt<S>& p, const T* a) { p.x = abs_(p.x) - a[0]; }
+// modifications.py:1023-1029 (pre-rotation emitted as AFFINE); args angle, radius
+template <typename S, typename T>
+AB_DEV void op_rotsym(Pt<S>& p, const T* a) {
+  const T ang = a[0], rad = a[1];
+  S phi = atan2_(p.y, p.x);
+  phi = select_(lt_(phi, T(0)), phi + T(6.283185307179586476925286766559), phi);
+  phi = mod_(phi, ang) - T(0.5) * ang;
+  S rr = norm2_(p.x, p.y);
+  S s, c;
+  sincos_(phi, s, c);
+  p.x = rr * c - rad;
+  p.y = rr * s;
+}
+// modifications.py:427-431
+template <typename S, typename T>
+AB_DEV void op_revolve(Pt<S>& p, const T* a) {
+  p.x = norm2_(p.x, p.z) - a[0];
+  p.z = constant_like(p.z, T(0));
+}
+// modifications.py:455-467; args radius, cos, sin
+template <typename S, typename T>
+AB_DEV void op_axis_revolve(Pt<S>& p, const T* a) {
+  const T rad = a[0], c = a[1], s = a[2];
+  S xr = fma_(p.x, c, p.y * s);
+  S yr = fma_(p.y, c, -(p.x * s));
+  S m = norm2_(xr, p.z);
+  p.x = fma_(m, c, -(yr * s)) - rad;
+  p.y = fma_(m, s, yr * c);
+  p.z = constant_like(p.z, T(0));
+}
+// modifications.py:819-820; args d(3), d/2(3)
+template <typename S, typename T>
+AB_DEV void op_rep_inf(Pt<S>& p, const T* a) {
+  p.x = mod_(p.x + a[3], a[0]) - a[3];
+  p.y = mod_(p.y + a[4], a[1]) - a[4];
+  p.z = mod_(p.z + a[5], a[2]) - a[5];
+}
+// modifications.py:847-868 per axis; args c(3), d(3), s(3), s/2(3)
+template <typename S, typename T>
+AB_DEV S rep_fin_axis(const S& q, T c, T d, T s, T sh) {
+  Mask<S::width> inner = ge_(q, -d) & le_(q, d);
+  S v = abs_(q) - c;
+  v = select_(lt_(q, T(0)), -v, v);
+  S u = mod_(q - d, s) - sh;
+  return select_(inner, u, v);
+}
+template <typename S, typename T>
+AB_DEV void op_rep_fin(Pt<S>& p, const T* a) {
+  p.x = rep_fin_axis(p.x, a[0], a[3], a[6], a[9]);
+  p.y = rep_fin_axis(p.y, a[1], a[4], a[7], a[10]);
+  p.z = rep_fin_axis(p.z, a[2], a[5], a[8], a[11]);
+}
+// modifications.py:1069-1083 (frame emitted as AFFINE); args l/2, s, d, lo, hi, off ; inner = (n > 2)
+template <typename S, typename T>
+AB_DEV void op_lin_inst(Pt<S>& p, const T* a, int inner_on) {
+  S v = abs_(p.x) - a[0];
+  v = select_(lt_(p.x, T(0)), -v, v);
+  if (inner_on) {
+    S u = mod_(p.x - a[5], a[1]) - a[2];
+    v = select_(ge_(p.x, a[3]) & le_(p.x, a[4]), u, v);
+  }
+  p.x = v;
+}
+// modifications.py:1120-1127 / 1183-1191 / 1253-1261: nearest instance (exhaustive argmin replaces the KD-tree), then
+// subtract its position and, for the aligned variants, rotate into its frame. Record = pos(3) [+ rows dx,dy,dz (9)].
+template <typename S, typename T>
+AB_DEV void op_curve_inst(Pt<S>& p, const T* a, int mode) {
+  const int n = (int)a[0];
+  const int stride = mode ? 12 : 3;
+  const T* rec = a + 1;
+  constexpr int W = S::width;
+  auto vx = value_of(p.x), vy = value_of(p.y), vz = value_of(p.z);
+  T best[W];
+  int idx[W];
+#pragma unroll
+  for (int i = 0; i < W; i++) {
+    best[i] = T(3.0e38);
+    idx[i] = 0;
+  }
+  for (int j = 0; j < n; j++) {
+    const T cx = rec[j * stride], cy = rec[j * stride + 1], cz = rec[j * stride + 2];
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+      T dx = vx.v[i] - cx, dy = vy.v[i] - cy, dz = vz.v[i] - cz;
+      T d2 = s_fma(dx, dx, s_fma(dy, dy, dz * dz));
+      if (d2 < best[i]) {
+        best[i] = d2;
+        idx[i] = j;
+      }
+    }
+  }
+  // gather the chosen record per lane (divergent constant reads: a handful per point, off the critical path)
+  Pack<T, W> r[12];
+#pragma unroll
+  for (int i = 0; i < W; i++) {
+    const T* q = rec + idx[i] * stride;
+#pragma unroll
+    for (int k = 0; k < 12; k++)
+      if (k < stride) r[k].v[i] = q[k];
+  }
+  S dx = add_lane(p.x, -r[0]), dy = add_lane(p.y, -r[1]), dz = add_lane(p.z, -r[2]);
+  if (mode) {
+    p.x = mul_lane(dx, r[3]) + mul_lane(dy, r[4]) + mul_lane(dz, r[5]);
+    p.y = mul_lane(dx, r[6]) + mul_lane(dy, r[7]) + mul_lane(dz, r[8]);
+    p.z = mul_lane(dx, r[9]) + mul_lane(dy, r[10]) + mul_lane(dz, r[11]);
+  } else {
+    p.x = dx;
+    p.y = dy;
+    p.z = dz;
+  }
+}
+
+// ---- value ops --------------------------------------------------------------------------------------------------------
+
+// modifications.py:489-497
+template <typename S, typename T>
+AB_DEV S op_extrude_end(const S& d, const S& w1) {
+  S o0 = max_(d, T(0)), o1 = max_(w1, T(0));
+  return min_(max_(d, w1), T(0)) + norm2_(o0, o1);
+}
+
+// ---- combine ops (combine.py:12-78) --------------------------------------------------------------------------------------
+template <typename S, typename T>
+AB_DEV S smin_poly2(const S& x, const S& y, T w) {  // combine.py:12-18
+  S h = max_(w - abs_(x - y), T(0)) * s_rcp(w);
+  return min_(x, y) - h * h * (w * T(0.25));
+}
+template <typename S, typename T>
+AB_DEV S smin_poly3(const S& x, const S& y, T w) {  // combine.py:20-26
+  S h = max_(w - abs_(x - y), T(0)) * s_rcp(w);
+  return min_(x, y) - h * h * h * (w * T(1.0 / 6.0));
+}
+// combine.py:29-34, evaluated in the shifted form (x e^{(x-m)/a} + y e^{(y-m)/a}) / (e^{(x-m)/a} + e^{(y-m)/a}),
+// m = max(x,y): algebraically identical, but does not overflow in fp32 where exp(x/a) would for x/a > 88.
+template <typename S, typename T>
+AB_DEV S smax_boltz(const S& x, const S& y, T w) {
+  const T iw = s_rcp(w);
+  S m = (w > T(0)) ? max_(x, y) : min_(x, y);
+  S e1 = exp_((x - m) * iw);
+  S e2 = exp_((y - m) * iw);
+  return div_(x * e1 + y * e2, e1 + e2);
+}
+
+// ---- 3D primitives (sdf_3D.py) ----------------------------------------------------------------------------------------------
+template <typename S, typename T>
+AB_DEV S prim_sphere(const Pt<S>& p, const T* a) { return norm3_(p.x, p.y, p.z) - a[0]; }  // :25-27
+template <typename S, typename T>
+AB_DEV S prim_cylinder(const Pt<S>& p, const T* a) {  // :30-37 ; args radius, height/2
+  S d0 = norm2_(p.x, p.y) - a[0];
+  S d1 = abs_(p.z) - a[1];
+  return min_(max_(d0, d1), T(0)) + norm2_(max_(d0, T(0)), max_(d1, T(0)));
+}
+template <typename S, typename T>
+AB_DEV S prim_box(const Pt<S>& p, const T* a) {  // :40-47 ; args half sizes
+  S q0 = abs_(p.x) - a[0], q1 = abs_(p.y) - a[1], q2 = abs_(p.z) - a[2];
+  return norm3_(max_(q0, T(0)), max_(q1, T(0)), max_(q2, T(0))) + min_(max_(q0, max_(q1, q2)), T(0));
+}
+template <typename S, typename T>
+AB_DEV S prim_torus(const Pt<S>& p, const T* a) {  // :50-53
+  return norm2_(norm2_(p.x, p.y) - a[0], p.z) - a[1];
+}
+template <typename S, typename T>
+AB_DEV S prim_chainlink(const Pt<S>& p, const T* a) {  // :56-61 ; args R, r, length/2
+  S xx = p.x - clamp_(p.x, -a[2], a[2]);
+  return norm2_(norm2_(xx, p.y) - a[0], p.z) - a[1];
+}
+template <typename S, typename T>
+AB_DEV S prim_braid(const Pt<S>& p, const T* a) {  // :64-75 ; args length/2, R, r, pitch
+  S s, c;
+  sincos_(p.z * a[3], s, c);
+  S xr = c * p.x - s * p.y;
+  S yr = s * p.x + c * p.y;
+  S zz = p.z - clamp_(p.z, -a[0], a[0]);
+  return norm2_(norm2_(xr, zz) - a[1], yr) - a[2];
+}
+// shared by sdf_arc (sdf_2D.py:85-102) and sdf_arc_3d (sdf_3D.py:78-96): rotate by the centre angle, fold, subtract
+// the closest point on the arc. args C, S, R, ea
+template <typename S, typename T>
+AB_DEV void arc_core(const S& x, const S& y, T C, T Sn, T R, T ea, S& dx, S& dy) {
+  S xr = fma_(x, C, y * Sn);
+  S yr = abs_(fma_(y, C, -(x * Sn)));
+  S psi = clamp_(atan2_(yr, xr), T(0), ea);
+  S s, c;
+  sincos_(psi, s, c);
+  dx = xr - c * R;
+  dy = yr - s * R;
+}
+template <typename S, typename T>
+AB_DEV S prim_arc3d(const Pt<S>& p, const T* a) {  // args R, r, C, S, ea
+  S dx, dy;
+  arc_core(p.x, p.y, a[2], a[3], a[0], a[4], dx, dy);
+  return norm3_(dx, dy, p.z) - a[1];
+}
+template <typename S, typename T>
+AB_DEV S prim_plane(const Pt<S>& p, const T* a) {  // :99-102
+  return fma_(p.x, a[0], fma_(p.y, a[1], p.z * a[2])) - a[3];
+}
+template <typename S, typename T>
+AB_DEV S prim_uplane(const Pt<S>& p, const T* a) {  // :105-108
+  return abs_(fma_(p.x, a[0], fma_(p.y, a[1], p.z * a[2]))) - a[3];
+}
+template <typename S, typename T>
+AB_DEV S prim_segment(const Pt<S>& p, const T* a) {  // :111-118 ; args a(3), ba(3), dot(ba,ba)
+  S px = p.x - a[0], py = p.y - a[1], pz = p.z - a[2];
+  S h = clamp_(fma_(px, a[3], fma_(py, a[4], pz * a[5])) * s_rcp(a[6]), T(0), T(1));
+  return norm3_(px - h * a[3], py - h * a[4], pz - h * a[5]);
+}
+template <typename S, typename T>
+AB_DEV S prim_cone(const Pt<S>& p, const T* a) {  // :121-136 ; args q0, q1, zoff, dot(q,q)
+  const T q0 = a[0], q1 = a[1];
+  S w0 = norm2_(p.x, p.y), w1 = p.z - a[2];
+  S t = clamp_(fma_(w0, q0, w1 * q1) * s_rcp(a[3]), T(0), T(1));
+  S a0 = w0 - t * q0, a1 = w1 - t * q1;
+  S b0 = w0 - clamp_(w0 * s_rcp(q0), T(0), T(1)) * q0, b1 = w1 - q1;
+  S d = min_(fma_(a0, a0, a1 * a1), fma_(b0, b0, b1 * b1));
+  S s = max_(-(w0 * q1 - w1 * q0), -(w1 - q1));
+  return mul_lane(sqrt_(d), value_sign(s));
+}
+template <typename S, typename T>
+AB_DEV S prim_inf_cone(const Pt<S>& p, const T* a, bool oriented) {  // :139-157 ; args sin, cos
+  const T v0 = a[0], v1 = a[1];
+  S q0 = norm2_(p.x, p.y), q1 = -p.z;
+  S t = max_(fma_(q0, v0, q1 * v1), T(0));
+  S d = norm2_(q0 - t * v0, q1 - t * v1);
+  if (oriented) d = select_(lt_(q0 * v1 - q1 * v0, T(0)), -d, d);
+  return d;
+}
+// shared by sdf_sector (sdf_2D.py:105-129) and sdf_solid_angle (sdf_3D.py:160-183) after rotation + fold
+template <typename S, typename T>
+AB_DEV S sector_core(const S& x, const S& y, T radius, T ad, T cad, T sad) {
+  S phi = atan2_(y, x);
+  S psi = clamp_(phi, T(0), ad);
+  S s, c;
+  sincos_(psi, s, c);
+  S length = norm2_(x - c * radius, y - s * radius);
+  S t = clamp_(fma_(x, cad, y * sad), T(0), radius);
+  S m = norm2_(x - t * cad, y - t * sad);
+  Mask<S::width> msk = le_(norm2_(x, y), radius) & le_(phi, ad);
+  S out = min_(m, length);
+  return select_(msk, -out, out);
+}
+template <typename S, typename T>
+AB_DEV S prim_solid_angle(const Pt<S>& p, const T* a) {  // args radius, C, S, ad, cos ad, sin ad
+  S xr = fma_(p.x, a[1], p.y * a[2]);
+  S yr = norm2_(fma_(p.y, a[1], -(p.x * a[2])), p.z);
+  return sector_core(xr, yr, a[0], a[3], a[4], a[5]);
+}
+template <typename S, typename T>
+AB_DEV S dot3(const T* u, const S& x, const S& y, const S& z) { return fma_(x, u[0], fma_(y, u[1], z * u[2])); }
+template <typename S, typename T>
+AB_DEV S edge_sq(const T* s, T ss, const S& x, const S& y, const S& z) {  // one term of sdf_3D.py:203-206
+  S h = clamp_(dot3(s, x, y, z) * s_rcp(ss), T(0), T(1));
+  S t0 = h * s[0] - x, t1 = h * s[1] - y, t2 = h * s[2] - z;
+  return fma_(t0, t0, fma_(t1, t1, t2 * t2));
+}
+template <typename S, typename T>
+AB_DEV S prim_triangle3d(const Pt<S>& p, const T* g) {  // :186-214 ; layout in program.py
+  S ax = p.x - g[0], ay = p.y - g[1], az = p.z - g[2];
+  S bx = p.x - g[3], by = p.y - g[4], bz = p.z - g[5];
+  S cx = p.x - g[6], cy = p.y - g[7], cz = p.z - g[8];
+  auto sg = value_of(sign_(dot3(g + 21, ax, ay, az))) + value_of(sign_(dot3(g + 24, bx, by, bz))) +
+            value_of(sign_(dot3(g + 27, cx, cy, cz)));
+  S ex1 = min_(min_(edge_sq(g + 9, g[30], ax, ay, az), edge_sq(g + 12, g[31], bx, by, bz)),
+               edge_sq(g + 15, g[32], cx, cy, cz));
+  S dn = dot3(g + 18, ax, ay, az);
+  S ex2 = dn * dn * s_rcp(g[33]);
+  return sqrt_(select_(lt_(sg, T(2)), ex1, ex2));
+}
+template <typename S, typename T>
+AB_DEV S prim_quad3d(const Pt<S>& p, const T* g) {  // :217-250
+  S ax = p.x - g[0], ay = p.y - g[1], az = p.z - g[2];
+  S bx = p.x - g[3], by = p.y - g[4], bz = p.z - g[5];
+  S cx = p.x - g[6], cy = p.y - g[7], cz = p.z - g[8];
+  S dx = p.x - g[9], dy = p.y - g[10], dz = p.z - g[11];
+  auto sg = value_of(sign_(dot3(g + 27, ax, ay, az))) + value_of(sign_(dot3(g + 30, bx, by, bz))) +
+            value_of(sign_(dot3(g + 33, cx, cy, cz))) + value_of(sign_(dot3(g + 36, dx, dy, dz)));
+  S ex1 = min_(min_(edge_sq(g + 21, g[42], dx, dy, dz), edge_sq(g + 18, g[41], cx, cy, cz)),
+               min_(edge_sq(g + 12, g[39], ax, ay, az), edge_sq(g + 15, g[40], bx, by, bz)));
+  S dn = dot3(g + 24, ax, ay, az);
+  S ex2 = dn * dn * s_rcp(g[43]);
+  return sqrt_(select_(lt_(sg, T(3)), ex1, ex2));
+}
+template <typename S, typename T>
+AB_DEV S prim_segline(const Pt<S>& p, const T* a, int dim) {  // sdf_3D.py:264-271 / sdf_2D.py:191-198
+  const int n = (int)a[0];
+  const T* pts = a + 1;
+  S best = constant_like(p.x, T(1e32));  // squared: the reference starts from 1e16 on the distance
+  for (int i = 0; i + 1 < n; i++) {
+    const T* u = pts + i * dim;
+    const T* v = u + dim;
+    T bx = v[0] - u[0], by = v[1] - u[1], bz = dim == 3 ? v[2] - u[2] : T(0);
+    T bb = s_fma(bx, bx, s_fma(by, by, bz * bz));
+    S px = p.x - u[0], py = p.y - u[1];
+    S d2;
+    if (dim == 3) {
+      S pz = p.z - u[2];
+      S h = clamp_(fma_(px, bx, fma_(py, by, pz * bz)) * s_rcp(bb), T(0), T(1));
+      S t0 = px - h * bx, t1 = py - h * by, t2 = pz - h * bz;
+      d2 = fma_(t0, t0, fma_(t1, t1, t2 * t2));
+    } else {
+      S h = clamp_(fma_(px, bx, py * by) * s_rcp(bb), T(0), T(1));
+      S t0 = px - h * bx, t1 = py - h * by;
+      d2 = fma_(t0, t0, t1 * t1);
+    }
+    best = min_(best, d2);
+  }
+  return sqrt_(best);
+}
+
+// ---- 2D primitives (sdf_2D.py) ----------------------------------------------------------------------------------------------
+template <typename S, typename T>
+AB_DEV S prim_circle(const Pt<S>& p, const T* a) { return norm2_(p.x, p.y) - a[0]; }  // :12-14
+template <typename S, typename T>
+AB_DEV S prim_neu_circle(const Pt<S>& p, const T* a) {  // :17-19 ; args radius, order
+  const T ord = a[1];
+  S ax = abs_(p.x), ay = abs_(p.y);
+  if (isinf(ord)) return max_(ax, ay) - a[0];
+  if (ord == T(1)) return ax + ay - a[0];
+  if (ord == T(2)) return norm2_(ax, ay) - a[0];
+  return pow_(pow_(ax, ord) + pow_(ay, ord), s_rcp(ord)) - a[0];
+}
+template <typename S, typename T>
+AB_DEV S prim_box2d(const Pt<S>& p, const T* a) {  // :22-28
+  S d0 = abs_(p.x) - a[0], d1 = abs_(p.y) - a[1];
+  return norm2_(max_(d0, T(0)), max_(d1, T(0))) + min_(max_(d0, d1), T(0));
+}
+template <typename S, typename T>
+AB_DEV S prim_segment2d(const Pt<S>& p, const T* a) {  // :31-38 ; args a(2), ba(2), dot
+  S px = p.x - a[0], py = p.y - a[1];
+  S h = clamp_(fma_(px, a[2], py * a[3]) * s_rcp(a[4]), T(0), T(1));
+  return norm2_(px - h * a[2], py - h * a[3]);
+}
+template <typename S, typename T>
+AB_DEV S prim_rbox2d(const Pt<S>& p, const T* a) {  // :41-57 ; args hx, hy, r0..r3
+  constexpr int W = S::width;
+  auto vx = value_of(p.x), vy = value_of(p.y);
+  Pack<T, W> r;
+#pragma unroll
+  for (int i = 0; i < W; i++)
+    r.v[i] = (vy.v[i] > T(0)) ? ((vx.v[i] < T(0)) ? a[5] : a[4]) : ((vx.v[i] > T(0)) ? a[3] : a[2]);
+  S d0 = add_lane(abs_(p.x) - a[0], r), d1 = add_lane(abs_(p.y) - a[1], r);
+  return norm2_(max_(d0, T(0)), max_(d1, T(0))) + add_lane(min_(max_(d0, d1), T(0)), -r);
+}
+template <typename S, typename T>
+AB_DEV S prim_triangle2d(const Pt<S>& p, const T* g) {  // :60-82 ; args p0,p1,p2,e0,e1,e2,ee(3),s
+  S d0, d1;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const T ex = g[6 + 2 * i], ey = g[7 + 2 * i];
+    S v0 = p.x - g[2 * i], v1 = p.y - g[2 * i + 1];
+    S h = clamp_(fma_(v0, ex, v1 * ey) * s_rcp(g[12 + i]), T(0), T(1));
+    S q0 = v0 - h * ex, q1 = v1 - h * ey;
+    S dd = fma_(q0, q0, q1 * q1);
+    S cr = (v0 * ey - v1 * ex) * g[15];
+    d0 = i ? min_(d0, dd) : dd;
+    d1 = i ? min_(d1, cr) : cr;
+  }
+  return -mul_lane(sqrt_(d0), value_sign(d1));
+}
+template <typename S, typename T>
+AB_DEV S prim_arc(const Pt<S>& p, const T* a) {  // :85-102 ; args R, C, S, ea
+  S dx, dy;
+  arc_core(p.x, p.y, a[1], a[2], a[0], a[3], dx, dy);
+  return norm2_(dx, dy);
+}
+template <typename S, typename T>
+AB_DEV S prim_sector(const Pt<S>& p, const T* a) {  // :105-129
+  S xr = fma_(p.x, a[1], p.y * a[2]);
+  S yr = abs_(fma_(p.y, a[1], -(p.x * a[2])));
+  return sector_core(xr, yr, a[0], a[3], a[4], a[5]);
+}
+template <typename S, typename T>
+AB_DEV S prim_inf_sector(const Pt<S>& p, const T* a) {  // :132-150 ; args C, S, ad, cos ad, sin ad
+  S xr = fma_(p.x, a[0], p.y * a[1]);
+  S yr = abs_(fma_(p.y, a[0], -(p.x * a[1])));
+  S phi = atan2_(yr, xr);
+  S t = max_(fma_(xr, a[3], yr * a[4]), T(0));
+  S m = norm2_(xr - t * a[3], yr - t * a[4]);
+  return mul_lane(m, value_sign(phi - a[2]));
+}
+template <typename S, typename T>
+AB_DEV S prim_ngon(const Pt<S>& p, const T* a) {  // :153-177 ; args radius, alpha, tx, ty, nox, noy, l
+  S phi = atan2_(p.y, p.x);
+  phi = select_(lt_(phi, T(0)), phi + T(6.283185307179586476925286766559), phi);
+  phi = mod_(phi, a[1]);
+  S rr = norm2_(p.x, p.y);
+  S s, c;
+  sincos_(phi, s, c);
+  S q0 = c * rr - a[0], q1 = s * rr;
+  S h = clamp_(fma_(q0, a[2], q1 * a[3]), T(0), a[6]);
+  S len = norm2_(q0 - h * a[2], q1 - h * a[3]);
+  return mul_lane(len, value_sign(fma_(q0, a[4], q1 * a[5])));
+}
+
+}  // namespace ab

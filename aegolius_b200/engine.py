@@ -1,0 +1,298 @@
+"""Evaluation front door: the drop-in for GenericGeometry.create(co) (Code/spomso/spomso/cores/geom.py:29-43),
+from_sdf (vector_functions.py:130-139) and sdf_point_cloud_* (sdf_3D.py:283-286, sdf_2D.py:221-224).
+
+    field = aegolius_b200.create(obj, co)                        # obj: SPOMSO object or frontend object
+    field, grad = aegolius_b200.create(obj, co, grad="spatial")  # analytic gradient (forward-mode duals)
+    aegolius_b200.patch()                                        # rebind spomso's GenericGeometry.create
+
+Everything is computed by libaegolius_b200.so on the GPU; if the library or a device is missing the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import cabi
+from .grid import GridSpec, detect_grid
+from .program import Program, flatten
+from . import opcodes as oc
+
+_DT = {"f32": (cabi.AB_F32, np.float32), "f64": (cabi.AB_F64, np.float64),
+       "float32": (cabi.AB_F32, np.float32), "float64": (cabi.AB_F64, np.float64),
+       np.float32: (cabi.AB_F32, np.float32), np.float64: (cabi.AB_F64, np.float64)}
+
+
+def library_path():
+    return cabi.LIB_PATH
+
+
+def _dtype(dtype):
+    try:
+        return _DT[dtype]
+    except (KeyError, TypeError):
+        return _DT[np.dtype(dtype).type]
+
+
+def _as_program(obj) -> Program:
+    return obj if isinstance(obj, Program) else flatten(obj)
+
+
+def _grad_mode(grad):
+    if grad in (None, False, "none"):
+        return cabi.AB_GRAD_NONE, 0
+    if grad in (True, "spatial", "xyz"):
+        return cabi.AB_GRAD_SPATIAL, 3
+    raise ValueError(f"unknown grad mode {grad!r} (use None or 'spatial')")
+
+
+def slab_ranges(n_planes: int, parts: int):
+    """np.array_split(range(n_planes), parts) as (begin, end) pairs: contiguous x-slabs."""
+    base, extra = divmod(n_planes, parts)
+    out, s = [], 0
+    for r in range(parts):
+        e = s + base + (1 if r < extra else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+class PinnedArray:
+    """Page-locked host buffer exposed as a numpy array (for the D2H leg of create())."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        cabi.check(cabi.lib().ab_host_alloc_pinned(nbytes, C.byref(p)))
+        self._ptr = p
+        buf = (C.c_char * max(1, nbytes)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            cabi.lib().ab_host_free_pinned(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def create(obj, co, *, dtype="f32", grad=None, device=0, out=None, out_grad=None, slab=None):
+    """Evaluates the SDF of `obj` on `co`.
+
+    obj   : SPOMSO GenericGeometry (any subclass), aegolius_b200 frontend object, or a flattened Program.
+    co    : GridSpec / GridCoords / plain (3,N) float64 array. Arrays produced by SPOMSO's generate_grid are
+            recognised (grid mode: coordinates are regenerated in-kernel); anything else is uploaded (points mode).
+    dtype : "f32" (default) or "f64" (bit-compatible output type with the reference, tighter parity).
+    grad  : None or "spatial" -> returns (field, gradient (3,N)).
+    slab  : (x0, x1) plane range of a grid to evaluate (multi-GPU sharding along the slowest axis).
+    Returns a numpy array (N,) of `dtype` (and the (3,N) gradient).
+    """
+    prog = _as_program(obj)
+    code, npdt = _dtype(dtype)
+    gmode, rows = _grad_mode(grad)
+    spec = detect_grid(co)
+    cp = cabi.CProgram(prog)
+    lib = cabi.lib()
+    if spec is not None:
+        x0, x1 = (0, spec.res[0]) if slab is None else slab
+        n = (x1 - x0) * spec.res[1] * spec.res[2]
+        g = cabi.make_grid(spec.size, spec.res, (x0, x1))
+    else:
+        if slab is not None:
+            raise ValueError("slab= needs grid coordinates")
+        co = np.ascontiguousarray(np.asarray(co, dtype=np.float64))
+        if co.ndim != 2 or co.shape[0] not in (2, 3):
+            raise ValueError(f"coordinates must have shape (3, N) or (2, N), got {co.shape}")
+        if co.shape[0] == 2:
+            co = np.concatenate([co, np.zeros((1, co.shape[1]))], axis=0)
+        n = co.shape[1]
+    field = out if out is not None else np.empty(n, dtype=npdt)
+    if field.dtype != npdt or field.size != n or not field.flags.c_contiguous:
+        raise ValueError("out= must be a C-contiguous array of the evaluation dtype with N elements")
+    gptr, gstride, g_arr = None, 0, None
+    if rows:
+        g_arr = out_grad if out_grad is not None else np.empty((rows, n), dtype=npdt)
+        if g_arr.dtype != npdt or g_arr.shape != (rows, n) or not g_arr.flags.c_contiguous:
+            raise ValueError("out_grad= must be a C-contiguous (3, N) array of the evaluation dtype")
+        gptr, gstride = g_arr.ctypes.data, n
+    if n == 0:
+        return (field, g_arr) if rows else field
+    if spec is not None:
+        cabi.check(lib.ab_eval_grid_host(cp.ref(), C.byref(g), code, gmode, field.ctypes.data, gptr, gstride, device))
+    else:
+        cabi.check(lib.ab_eval_points_host(cp.ref(), co.ctypes.data, n, n, code, gmode, field.ctypes.data, gptr,
+                                           gstride, device))
+    return (field, g_arr) if rows else field
+
+
+def create_with_gradient(obj, co, **kw):
+    return create(obj, co, grad="spatial", **kw)
+
+
+# ---- device-resident evaluation (torch owns the memory and the stream) ------------------------------------------------------
+
+
+def create_torch(obj, spec: GridSpec, *, dtype="f32", grad=None, device=0, slab=None, out=None, out_grad=None):
+    """Grid evaluation into torch CUDA tensors on the current torch stream (no host copy). Returns field
+    (and gradient (3,N) view of a row-padded buffer)."""
+    import torch
+    prog = _as_program(obj)
+    code, npdt = _dtype(dtype)
+    tdt = torch.float32 if code == cabi.AB_F32 else torch.float64
+    gmode, rows = _grad_mode(grad)
+    x0, x1 = (0, spec.res[0]) if slab is None else slab
+    n = (x1 - x0) * spec.res[1] * spec.res[2]
+    dev = torch.device("cuda", device)
+    field = out if out is not None else torch.empty(n, dtype=tdt, device=dev)
+    gbuf, gptr, stride = None, None, 0
+    if rows:
+        stride = (n + 3) // 4 * 4
+        gbuf = out_grad if out_grad is not None else torch.empty((rows, stride), dtype=tdt, device=dev)
+        gptr, stride = gbuf.data_ptr(), gbuf.stride(0)
+    cp = cabi.CProgram(prog)
+    g = cabi.make_grid(spec.size, spec.res, (x0, x1))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    cabi.check(cabi.lib().ab_eval_grid(cp.ref(), C.byref(g), code, gmode, field.data_ptr(), gptr, stride, device,
+                                       C.c_void_p(stream)))
+    return (field, gbuf[:, :n]) if rows else field
+
+
+# ---- from_sdf ------------------------------------------------------------------------------------------------------------------
+
+
+def from_sdf(sdf_, co_resolution, *, dtype=None, device=0, normalize=True):
+    """vector_functions.py:130-139: unit-spacing np.gradient of the reshaped field + batch_normalize, on the GPU.
+    `sdf_` is a host array of N = prod(co_resolution) values; returns (dims, N)."""
+    res = tuple(int(r) for r in np.asarray(co_resolution).reshape(-1))
+    dims = len(res)
+    if dims not in (2, 3):
+        raise ValueError("co_resolution must have 2 or 3 entries")
+    f = np.asarray(sdf_)
+    if dtype is None:
+        dtype = "f32" if f.dtype == np.float32 else "f64"
+    code, npdt = _dtype(dtype)
+    f = np.ascontiguousarray(f.reshape(-1), dtype=npdt)
+    n = int(np.prod(res))
+    if f.size != n:
+        raise ValueError(f"Cannot reshape the pattern with shape {f.shape}")
+    if any(r < 2 for r in res):
+        raise ValueError("Shape of array too small to calculate a numerical gradient, at least 2 elements are "
+                         "required.")
+    lib = cabi.lib()
+    d_f, d_o = C.c_void_p(), C.c_void_p()
+    stride = (n + 3) // 4 * 4
+    cabi.check(lib.ab_device_alloc(n * f.itemsize, device, C.byref(d_f)))
+    try:
+        cabi.check(lib.ab_device_alloc(dims * stride * f.itemsize, device, C.byref(d_o)))
+        try:
+            cabi.check(lib.ab_memcpy_h2d(d_f, f.ctypes.data, n * f.itemsize, device, None))
+            g = cabi.make_grid((0.0, 0.0, 0.0), res + ((1,) if dims == 2 else ()))
+            cabi.check(lib.ab_fd_gradient(d_f, 0, C.byref(g), dims, code, 1 if normalize else 0, d_o, stride, device,
+                                          None))
+            out = np.empty((dims, n), dtype=npdt)
+            for r in range(dims):
+                cabi.check(lib.ab_memcpy_d2h(out[r].ctypes.data, d_o.value + r * stride * f.itemsize, n * f.itemsize,
+                                             device, None))
+            cabi.check(lib.ab_stream_sync(device, None))
+        finally:
+            lib.ab_device_free(d_o, device)
+    finally:
+        lib.ab_device_free(d_f, device)
+    return out
+
+
+class VectorFieldFromSDF:
+    """geom_vector.py:188-198: VectorFieldFromSDF(co_resolution).create(sdf_flat)."""
+
+    def __init__(self, co_resolution):
+        self.co_resolution = co_resolution
+
+    def create(self, sdf_, **kw):
+        return from_sdf(sdf_, self.co_resolution, **kw)
+
+
+# ---- point clouds ----------------------------------------------------------------------------------------------------------------
+
+
+def point_cloud_sdf(co, points, *, dim=3, dtype="f32", device=0, slab=None):
+    """sdf_point_cloud_3d / sdf_point_cloud_2d (sdf_3D.py:283-286, sdf_2D.py:221-224): unsigned distance to the
+    nearest cloud point with the dedicated tiled brute-force kernel."""
+    code, npdt = _dtype(dtype)
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
+    if pts.ndim != 2 or pts.shape[0] < dim:
+        raise ValueError(f"points must have shape ({dim}, M)")
+    m = pts.shape[1]
+    lib = cabi.lib()
+    spec = detect_grid(co)
+    d_cloud, d_out, d_co = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    cabi.check(lib.ab_cloud_upload(pts.ctypes.data, m, dim, pts.shape[1], code, device, C.byref(d_cloud)))
+    try:
+        if spec is not None:
+            x0, x1 = (0, spec.res[0]) if slab is None else slab
+            n = (x1 - x0) * spec.res[1] * spec.res[2]
+        else:
+            co = np.ascontiguousarray(np.asarray(co, dtype=np.float64))
+            n = co.shape[1]
+        out = np.empty(n, dtype=npdt)
+        if n == 0:
+            return out
+        cabi.check(lib.ab_device_alloc(n * out.itemsize, device, C.byref(d_out)))
+        try:
+            if spec is not None:
+                g = cabi.make_grid(spec.size, spec.res, (x0, x1))
+                cabi.check(lib.ab_nn_grid(d_cloud, m, dim, C.byref(g), code, d_out, device, None))
+            else:
+                rows = co.shape[0]
+                cabi.check(lib.ab_device_alloc(rows * n * 8, device, C.byref(d_co)))
+                cabi.check(lib.ab_memcpy_h2d(d_co, co.ctypes.data, rows * n * 8, device, None))
+                cabi.check(lib.ab_nn_points(d_cloud, m, dim, d_co, cabi.AB_F64, n, n, code, d_out, device, None))
+            cabi.check(lib.ab_memcpy_d2h(out.ctypes.data, d_out, n * out.itemsize, device, None))
+            cabi.check(lib.ab_stream_sync(device, None))
+        finally:
+            lib.ab_device_free(d_out, device)
+            if d_co.value:
+                lib.ab_device_free(d_co, device)
+    finally:
+        lib.ab_device_free(d_cloud, device)
+    return out
+
+
+# ---- drop-in patch of an installed SPOMSO ---------------------------------------------------------------------------------------
+
+_PATCHED = {}
+
+
+def patch(dtype="f64", device=0):
+    """Rebinds spomso.cores.geom.GenericGeometry.create/propagate to the GPU path. Trees that cannot be flattened
+    raise NotImplementedError (there is no silent fallback)."""
+    from spomso.cores import geom
+
+    if "create" in _PATCHED:
+        return
+    _PATCHED["create"] = geom.GenericGeometry.create
+    _PATCHED["propagate"] = geom.GenericGeometry.propagate
+
+    def _create(self, co):
+        return create(self, co, dtype=dtype, device=device)
+
+    def _propagate(self, co, *parameters_):
+        return create(self, co, dtype=dtype, device=device)
+
+    _propagate.__name__ = "propagate"  # introspect.py recognises nested nodes by this name
+    _create.__name__ = "create"
+    geom.GenericGeometry.create = _create
+    geom.GenericGeometry.propagate = _propagate
+
+
+def unpatch():
+    if "create" in _PATCHED:
+        from spomso.cores import geom
+        geom.GenericGeometry.create = _PATCHED.pop("create")
+        geom.GenericGeometry.propagate = _PATCHED.pop("propagate")

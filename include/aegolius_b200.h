@@ -122,9 +122,9 @@ typedef enum ab_opcode {
   AB_OP__COUNT = 160
 } ab_opcode;
 
-/* A point cloud (or other bulk table) referenced by an op. `data` is (dim, count) row-major float64 on the host
- * (SPOMSO's own layout, geom_3d.py:759-777) when on_device == 0, or a device pointer to `count` float4
- * (x, y, z, 0) records prepared by ab_cloud_upload when on_device == 1. */
+/* A point cloud referenced by an op. `data` is (3, count) row-major float64 on the host (SPOMSO's own layout,
+ * geom_3d.py:759-777; 2D clouds carry a zero z row) when on_device == 0, or a device pointer to `count`
+ * (x, y, z, 0) records of the evaluation dtype (float4 / double4) prepared by ab_cloud_upload when on_device == 1. */
 typedef struct ab_blob {
   const void* data;
   uint64_t count;
@@ -186,9 +186,10 @@ int ab_nn_grid(const void* cloud_dev, uint64_t m, int dim, const ab_grid* grid, 
 int ab_nn_points(const void* cloud_dev, uint64_t m, int dim, const void* co, int co_dtype, uint64_t co_stride,
                  uint64_t n, int dtype, void* out, int device, void* stream);
 
-/* Converts a host (dim, m) float64 cloud into the device record layout; *out_dev is cudaMalloc'ed (free with
- * ab_device_free). */
-int ab_cloud_upload(const double* points_host, uint64_t m, int dim, uint64_t row_stride, int device, void** out_dev);
+/* Converts a host (dim, m) float64 cloud (row stride in elements) into device (x, y, z, 0) records of `dtype`;
+ * *out_dev is cudaMalloc'ed (free with ab_device_free). */
+int ab_cloud_upload(const double* points_host, uint64_t m, int dim, uint64_t row_stride, int dtype, int device,
+                    void** out_dev);
 
 /* Replaces from_sdf (vector_functions.py:130-139): np.gradient of the reshaped field (unit spacing, 2nd-order
  * central inside, 1st-order one-sided on the faces) and, if normalize != 0, batch_normalize

@@ -1,0 +1,100 @@
+"""GPU parity for the two non-interpreter kernels (point cloud -> SDF, from_sdf) and the C-ABI error paths."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import interp_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(m, seed=0):
+    rng = np.random.default_rng(seed)
+    x, y = rng.uniform(-1, 1, m), rng.uniform(-1, 1, m)
+    z = 0.2 * np.sin(3 * x) * np.cos(2 * y) + 0.01 * rng.normal(size=m)
+    return np.stack([x, y, z])
+
+
+@pytest.mark.parametrize("m", [1, 37, 1024, 5000])
+def test_point_cloud_grid_matches_exhaustive_oracle(m):
+    import aegolius_b200 as ab
+    pts = _cloud(m)
+    spec = ab.GridSpec((2.5, 2.5, 1.5), (20, 16, 12))
+    exp = interp_np.point_cloud_distance(spec.materialize(), pts)
+    got64 = ab.point_cloud_sdf(spec, pts, dtype="f64")
+    assert np.max(np.abs(got64 - exp)) <= 1e-12 * 2.5
+    got32 = ab.point_cloud_sdf(spec, pts, dtype="f32")
+    assert np.max(np.abs(got32 - exp)) <= 1e-5 * 2.5
+
+
+def test_point_cloud_2d_and_points_mode():
+    import aegolius_b200 as ab
+    pts = _cloud(777, seed=3)
+    rng = np.random.default_rng(5)
+    co = rng.uniform(-1.2, 1.2, size=(3, 3001))
+    exp3 = interp_np.point_cloud_distance(co, pts, dim=3)
+    exp2 = interp_np.point_cloud_distance(co, pts, dim=2)
+    assert np.max(np.abs(ab.point_cloud_sdf(co, pts, dim=3, dtype="f64") - exp3)) <= 1e-12 * 2.4
+    assert np.max(np.abs(ab.point_cloud_sdf(co, pts, dim=2, dtype="f64") - exp2)) <= 1e-12 * 2.4
+    assert np.max(np.abs(ab.point_cloud_sdf(co, pts, dim=3, dtype="f32") - exp3)) <= 1e-5 * 2.4
+
+
+def test_point_cloud_leaf_inside_a_tree_matches_oracle():
+    """PointCloud3D(points).onion(t) under a transform, the pointcloud_terrain_3D.py:39-47 pattern."""
+    import aegolius_b200 as ab
+    pts = _cloud(2000, seed=9)
+    pc = ab.PointCloud3D(pts)
+    pc.onion(0.03)
+    pc.rotate(0.3, (0, 0, 1))
+    pc.move((0.1, 0.0, 0.05))
+    prog = ab.flatten(pc)
+    spec = ab.GridSpec((2.5, 2.5, 1.5), (16, 16, 12))
+    exp = interp_np.run_grid(prog, spec.size, spec.res)
+    assert np.max(np.abs(ab.create(prog, spec, dtype="f64") - exp)) <= 1e-12 * 2.5
+    assert np.max(np.abs(ab.create(prog, spec, dtype="f32") - exp)) <= 1e-5 * 2.5
+
+
+@pytest.mark.parametrize("res", [(9, 7, 11), (13, 5), (2, 2, 2), (33, 2, 3)])
+def test_from_sdf_matches_np_gradient_semantics(res):
+    import aegolius_b200 as ab
+    rng = np.random.default_rng(2)
+    f = rng.normal(size=int(np.prod(res)))
+    f[:3] = 0.0
+    exp = interp_np.from_sdf(f, res)
+    got = ab.from_sdf(f, res)
+    assert got.shape == exp.shape and got.dtype == np.float64
+    assert np.max(np.abs(got - exp)) < 1e-13
+    got32 = ab.from_sdf(f.astype(np.float32), res)
+    assert got32.dtype == np.float32
+    assert np.max(np.abs(got32 - exp)) < 5e-5  # fp32 field: differences of O(1) values
+    flat = np.zeros(int(np.prod(res)))
+    assert not np.any(ab.from_sdf(flat, res))  # zero vectors stay zero (batch_normalize mask)
+
+
+def test_c_abi_rejects_bad_programs_with_messages():
+    from aegolius_b200 import cabi, flatten, Sphere, GridSpec
+    import aegolius_b200 as ab
+    prog = flatten(Sphere(1.0))
+    bad = ab.Program(prog.ops.copy(), prog.args.copy(), [], 1, 1)
+    bad.ops["opcode"][0] = 159  # unknown opcode
+    with pytest.raises(cabi.AegoliusError) as e:
+        ab.create(bad, GridSpec((2, 2, 2), (4, 4, 4)))
+    assert e.value.code == cabi.AB_EUNSUPPORTED_OP and "opcode" in str(e.value)
+    bad2 = ab.Program(prog.ops.copy(), prog.args[:0].copy(), [], 1, 1)
+    with pytest.raises(cabi.AegoliusError) as e:
+        ab.create(bad2, GridSpec((2, 2, 2), (4, 4, 4)))
+    assert e.value.code == cabi.AB_EINVAL
+    with pytest.raises(cabi.AegoliusError):
+        ab.create(prog, GridSpec((2, 2, 2), (4, 4, 4)), device=99)
+    # empty input: no launch, empty result
+    out = ab.create(prog, np.zeros((3, 0)))
+    assert out.shape == (0,)
+
+
+def test_launch_counter_counts_kernels():
+    import aegolius_b200 as ab
+    from aegolius_b200 import cabi
+    n0 = cabi.launch_count()
+    ab.create(ab.flatten(ab.Sphere(1.0)), ab.GridSpec((2, 2, 2), (8, 8, 8)))
+    assert cabi.launch_count() == n0 + 1
