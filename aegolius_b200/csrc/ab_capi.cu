@@ -171,8 +171,8 @@ static int make_gridk(const ab_grid* grid, GridK& g, uint64_t* n_points) {
   g.n2 = grid->res[2];
   g.plane = (uint32_t)plane;
   g.i0_begin = grid->slab_begin;
-  g.inv_plane = 1.0 / (double)plane;
-  g.inv_n2 = 1.0 / (double)grid->res[2];
+  g.m1 = (uint32_t)(0x100000000ull / grid->res[1] > 0xffffffffull ? 0xffffffffull : 0x100000000ull / grid->res[1]);
+  g.m2 = (uint32_t)(0x100000000ull / grid->res[2] > 0xffffffffull ? 0xffffffffull : 0x100000000ull / grid->res[2]);
   for (int c = 0; c < 3; c++) {
     uint32_t n = grid->res[c];
     double start = -grid->size[c] / 2, stop = grid->size[c] / 2;
@@ -275,9 +275,13 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   kp.grid_mode = tg.grid_mode;
   kp.g = tg.g;
   kp.n_ops = prog->n_ops;
+  while (kp.n_ops > 0 && prog->ops[kp.n_ops - 1].opcode == AB_OP_END) kp.n_ops--;  // no dispatch spent on the terminator
   kp.n_pslots = prog->n_pslots ? prog->n_pslots : 1;
   kp.n_vslots = prog->n_vslots ? prog->n_vslots : 1;
-  memcpy(kp.ops, prog->ops, sizeof(ab_op) * prog->n_ops);
+  for (uint32_t i = 0; i < prog->n_ops; i++) {
+    kp.ops[i] = prog->ops[i];
+    kp.ops[i].opcode = (uint16_t)dense_opcode(prog->ops[i].opcode);  // validated above
+  }
   for (uint32_t i = 0; i < prog->n_args; i++) kp.args[i] = (T)prog->args[i];
 
   std::vector<void*> temp_blobs;
@@ -302,8 +306,34 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
 
   constexpr int WV = sizeof(T) == 4 ? 4 : 2;  // one 128-bit store per thread
   constexpr int WG = sizeof(T) == 4 ? 2 : 1;  // dual numbers carry 4x the state: halve the points per thread
-  if (grad_mode == AB_GRAD_NONE) rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
-  else rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
+  // the kernel indexes points with 32 bits: split big jobs into launches of < 2^31 points (whole planes in grid mode)
+  const uint64_t kMax = 0x7fffffffull - 4096;
+  uint64_t done = 0;
+  rc = AB_OK;
+  while (done < tg.n && rc == AB_OK) {
+    uint64_t chunk = tg.n - done;
+    if (chunk > kMax) {
+      chunk = kMax;
+      if (tg.grid_mode) {
+        uint64_t planes = kMax / tg.g.plane;
+        if (planes == 0) return fail(AB_ETOOLARGE, "one grid plane has more than 2^31 points");
+        chunk = planes * tg.g.plane;
+      } else {
+        chunk &= ~3ull;
+      }
+    }
+    kp.n = chunk;
+    kp.out = tg.out + done;
+    kp.grad = tg.grad ? tg.grad + done : nullptr;
+    if (tg.grid_mode) {
+      kp.g.i0_begin = tg.g.i0_begin + (uint32_t)(done / tg.g.plane);
+    } else {
+      kp.co = (const char*)tg.co + done * (tg.co_is_f64 ? 8 : 4);
+    }
+    if (grad_mode == AB_GRAD_NONE) rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
+    else rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
+    done += chunk;
+  }
   for (void* d : temp_blobs) cudaFreeAsync(d, st);
   return rc;
 }

@@ -23,8 +23,47 @@ struct GridK {
   uint32_t last[3];         // res-1 per axis (for the exact linspace end point)
   double start[3], step[3], stop[3];  // linspace parameters per axis (fp64 path: bit-identical to numpy)
   float hi[3], lo[3], centre[3];      // fp32 path: x = (i - centre) * (hi + lo), one rounding
-  double inv_plane, inv_n2;           // reciprocals for the index split
+  uint32_t m1, m2;                    // floor(2^32 / n1), floor(2^32 / n2): mulhi quotient estimates (one fix-up step)
 };
+
+// quotient / remainder of a small numerator by a runtime constant: q_est = umulhi(t, floor(2^32/n)) is floor(t/n) or one
+// less, so a single correction step makes it exact (also for n == 1).
+AB_DEV void divmod_small(uint32_t t, uint32_t n, uint32_t magic, uint32_t& q, uint32_t& r) {
+  q = __umulhi(t, magic);
+  r = t - q * n;
+  if (r >= n) {
+    q++;
+    r -= n;
+  }
+}
+
+// dense opcode numbering used inside the kernel (the host remaps ab_opcode -> DenseOp so that the dispatch switch
+// compiles to one indexed branch instead of a compare tree)
+#define AB_OPLIST(X)                                                                                                   \
+  X(END) X(SAVE_P) X(LOAD_P) X(PUSH_V) X(AFFINE) X(TRANSLATE) X(SCALE_P) X(ELONGATE) X(TWIST) X(BEND) X(ABSX_SUB)        \
+  X(SYMMETRY) X(ROTSYM) X(REVOLVE) X(AXIS_REVOLVE) X(REP_INF) X(REP_FIN) X(LIN_INST) X(CURVE_INST) X(ZERO_Z) X(ROUND)  \
+  X(ABS) X(NEG) X(SIGN) X(ONION) X(CONCENTRIC) X(SCALE_V) X(EXTRUDE_BEGIN) X(EXTRUDE_END) X(PP_SIGMOID)                \
+  X(PP_POS_SIGMOID) X(PP_CAPPED_EXP) X(PP_HARD_BIN) X(PP_LINEAR) X(PP_RELU) X(PP_SMOOTH_RELU) X(PP_SLOWSTART)          \
+  X(PP_GAUSS_BOUNDARY) X(PP_GAUSS_FALLOFF) X(C_UNION) X(C_INTERSECT) X(C_SUBTRACT) X(C_SUM) X(C_DIFF) X(C_SMIN2)       \
+  X(C_SMIN3) X(C_SMAX3) X(C_SSUB3) X(C_BOLTZ_INT) X(C_BOLTZ_SUB) X(P_SPHERE) X(P_CYLINDER) X(P_BOX) X(P_TORUS)         \
+  X(P_CHAINLINK) X(P_BRAID) X(P_ARC3D) X(P_PLANE) X(P_UPLANE) X(P_SEGMENT) X(P_CONE) X(P_OINF_CONE) X(P_INF_CONE)      \
+  X(P_SOLID_ANGLE) X(P_TRIANGLE3D) X(P_QUAD3D) X(P_SEGLINE) X(P_AXIS) X(P_POINT_CLOUD) X(P_CIRCLE) X(P_NEU_CIRCLE)     \
+  X(P_BOX2D) X(P_SEGMENT2D) X(P_RBOX2D) X(P_TRIANGLE2D) X(P_ARC) X(P_SECTOR) X(P_INF_SECTOR) X(P_NGON) X(P_SEGLINE2D)
+enum DenseOp : uint16_t {
+#define AB_X(name) D_##name,
+  AB_OPLIST(AB_X)
+#undef AB_X
+      D__COUNT
+};
+inline int dense_opcode(int ab_opcode) {
+  switch (ab_opcode) {
+#define AB_X(name) \
+  case AB_OP_##name: return D_##name;
+    AB_OPLIST(AB_X)
+#undef AB_X
+    default: return -1;
+  }
+}
 
 template <typename T>
 struct Vec4;
@@ -39,7 +78,7 @@ struct Vec4<double> {
 
 template <typename T>
 struct KParams {
-  uint64_t n;        // points in this launch
+  uint64_t n;        // points in this launch (< 2^31: the host splits larger slabs on plane boundaries)
   T* out;            // (n,)
   T* grad;           // (K, grad_stride) or nullptr
   uint64_t grad_stride;
@@ -48,6 +87,7 @@ struct KParams {
   int32_t co_is_f64;
   int32_t grid_mode;
   GridK g;
+  uint32_t tile_stride[3];  // (d0, d1, d2): decomposition of gridDim.x * tile points, filled in by the launcher
   uint32_t n_ops, n_pslots, n_vslots;
   const void* blob[AB_MAX_BLOBS];  // (x, y, z, 0) records of T
   uint32_t blob_count[AB_MAX_BLOBS];
@@ -158,11 +198,11 @@ AB_DEV void seed(Pt<Dual<Pack<T, W>, K>>& p, const Pack<T, W>& x, const Pack<T, 
   }
 }
 template <typename T, int W>
-AB_DEV void emit(const KParams<T>& kp, const Pack<T, W>& acc, uint64_t idx, bool aligned) {
+AB_DEV void emit(const KParams<T>& kp, const Pack<T, W>& acc, uint32_t idx, bool aligned) {
   store_pack(kp.out, acc, idx, kp.n, aligned);
 }
 template <typename T, int W, int K>
-AB_DEV void emit(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint64_t idx, bool aligned) {
+AB_DEV void emit(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint32_t idx, bool aligned) {
   store_pack(kp.out, acc.v, idx, kp.n, aligned);
   const bool ga = aligned && (kp.grad_stride % W == 0);
 #pragma unroll
@@ -222,51 +262,66 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
   P* pstack = reinterpret_cast<P*>(smem_raw);                         // [n_pslots*3*cols][NT]
   P* vstack = pstack + (size_t)kp.n_pslots * 3 * SK::cols * NT;       // [n_vslots*cols][NT]
 
-  const uint64_t tile_pts = (uint64_t)NT * W;
-  const uint64_t n_tiles = (kp.n + tile_pts - 1) / tile_pts;
+  const uint32_t tile_pts = (uint32_t)NT * W;
+  const uint32_t n32 = (uint32_t)kp.n;
+  const uint32_t n_tiles = (n32 + tile_pts - 1) / tile_pts;
+  // (ix, iy, iz) of this CTA's first tile: one real division per CTA, then carried additions per tile
+  uint32_t b0 = 0, b1 = 0, b2 = 0;
+  if (kp.grid_mode) {
+    const uint32_t start = blockIdx.x * tile_pts;
+    b0 = start / kp.g.plane;
+    const uint32_t rem = start - b0 * kp.g.plane;
+    b1 = rem / kp.g.n2;
+    b2 = rem - b1 * kp.g.n2;
+  }
 
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint64_t idx = tile * tile_pts + (uint64_t)threadIdx.x * W;  // first local point of this thread
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t idx = tile * tile_pts + threadIdx.x * W;  // first local point of this thread
     P cx, cy, cz;
     if (kp.grid_mode) {
-      // split the flat index of the first point, then walk W points with carries
-      uint64_t k = idx < kp.n ? idx : (kp.n - 1);
-      uint32_t i0 = (uint32_t)((double)k * kp.g.inv_plane);
-      uint64_t rem64 = k - (uint64_t)i0 * kp.g.plane;
-      if ((int64_t)rem64 < 0) { i0--; rem64 += kp.g.plane; }
-      if (rem64 >= kp.g.plane) { i0++; rem64 -= kp.g.plane; }
-      uint32_t rem = (uint32_t)rem64;
-      uint32_t i1 = (uint32_t)((double)rem * kp.g.inv_n2);
-      int32_t r2 = (int32_t)(rem - i1 * kp.g.n2);
-      if (r2 < 0) { i1--; r2 += kp.g.n2; }
-      if ((uint32_t)r2 >= kp.g.n2) { i1++; r2 -= kp.g.n2; }
-      uint32_t i2 = (uint32_t)r2;
-      i0 += kp.g.i0_begin;
-      T c0 = T(0), c1 = T(0);
-      bool fresh = true;
+      uint32_t q, i2, i1, i0;
+      divmod_small(b2 + threadIdx.x * W, kp.g.n2, kp.g.m2, q, i2);
+      divmod_small(b1 + q, kp.g.n1, kp.g.m1, q, i1);
+      i0 = b0 + q + kp.g.i0_begin;
+      if (i2 + W <= kp.g.n2) {  // the W points share one (ix, iy) row: the common case
+        const T c0 = grid_coord(kp.g, 0, i0, T()), c1 = grid_coord(kp.g, 1, i1, T());
 #pragma unroll
-      for (int j = 0; j < W; j++) {
-        if (fresh) {
-          c0 = grid_coord(kp.g, 0, i0, T());
-          c1 = grid_coord(kp.g, 1, i1, T());
-          fresh = false;
+        for (int j = 0; j < W; j++) {
+          cx.v[j] = c0;
+          cy.v[j] = c1;
+          cz.v[j] = grid_coord(kp.g, 2, i2 + j, T());
         }
-        cx.v[j] = c0;
-        cy.v[j] = c1;
-        cz.v[j] = grid_coord(kp.g, 2, i2, T());
-        if (++i2 == kp.g.n2) {
-          i2 = 0;
-          fresh = true;
-          if (++i1 == kp.g.n1) {
-            i1 = 0;
-            ++i0;
+      } else {  // a row boundary falls inside this thread's run
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+          cx.v[j] = grid_coord(kp.g, 0, i0, T());
+          cy.v[j] = grid_coord(kp.g, 1, i1, T());
+          cz.v[j] = grid_coord(kp.g, 2, i2, T());
+          if (++i2 == kp.g.n2) {
+            i2 = 0;
+            if (++i1 == kp.g.n1) {
+              i1 = 0;
+              ++i0;
+            }
           }
         }
       }
+      // advance the tile origin by gridDim.x tiles
+      b2 += kp.tile_stride[2];
+      if (b2 >= kp.g.n2) {
+        b2 -= kp.g.n2;
+        b1++;
+      }
+      b1 += kp.tile_stride[1];
+      if (b1 >= kp.g.n1) {
+        b1 -= kp.g.n1;
+        b0++;
+      }
+      b0 += kp.tile_stride[0];
     } else {
 #pragma unroll
       for (int j = 0; j < W; j++) {
-        uint64_t k = idx + j < kp.n ? idx + j : kp.n - 1;
+        const uint64_t k = idx + j < n32 ? idx + j : n32 - 1;
         if (kp.co_is_f64) {
           const double* c = (const double*)kp.co;
           cx.v[j] = (T)__ldcs(c + k);
@@ -290,123 +345,127 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
       const T* a = kp.args + op.arg;
       const int sa = op.a;
       switch (op.opcode) {
-        case AB_OP_END: pc = kp.n_ops; break;
-        case AB_OP_SAVE_P:
+        case D_END: pc = kp.n_ops; break;
+        case D_SAVE_P:
           SK::st(pstack, sa * 3 + 0, NT, p.x);
           SK::st(pstack, sa * 3 + 1, NT, p.y);
           SK::st(pstack, sa * 3 + 2, NT, p.z);
           break;
-        case AB_OP_LOAD_P:
+        case D_LOAD_P:
           p.x = SK::ld(pstack, sa * 3 + 0, NT);
           p.y = SK::ld(pstack, sa * 3 + 1, NT);
           p.z = SK::ld(pstack, sa * 3 + 2, NT);
           break;
-        case AB_OP_PUSH_V: SK::st(vstack, sa, NT, acc); break;
+        case D_PUSH_V: SK::st(vstack, sa, NT, acc); break;
         // coordinate ops
-        case AB_OP_AFFINE: op_affine(p, a); break;
-        case AB_OP_TRANSLATE: op_translate(p, a); break;
-        case AB_OP_SCALE_P: op_scale_p(p, a); break;
-        case AB_OP_ELONGATE: op_elongate(p, a); break;
-        case AB_OP_TWIST: op_twist(p, a); break;
-        case AB_OP_BEND: op_bend(p, a); break;
-        case AB_OP_ABSX_SUB: op_absx_sub(p, a); break;
-        case AB_OP_SYMMETRY:
+        case D_AFFINE: op_affine(p, a); break;
+        case D_TRANSLATE: op_translate(p, a); break;
+        case D_SCALE_P: op_scale_p(p, a); break;
+        case D_ELONGATE: op_elongate(p, a); break;
+        case D_TWIST: op_twist(p, a); break;
+        case D_BEND: op_bend(p, a); break;
+        case D_ABSX_SUB: op_absx_sub(p, a); break;
+        case D_SYMMETRY:
           if (sa == 0) p.x = abs_(p.x);
           else if (sa == 1) p.y = abs_(p.y);
           else p.z = abs_(p.z);
           break;
-        case AB_OP_ROTSYM: op_rotsym(p, a); break;
-        case AB_OP_REVOLVE: op_revolve(p, a); break;
-        case AB_OP_AXIS_REVOLVE: op_axis_revolve(p, a); break;
-        case AB_OP_REP_INF: op_rep_inf(p, a); break;
-        case AB_OP_REP_FIN: op_rep_fin(p, a); break;
-        case AB_OP_LIN_INST: op_lin_inst(p, a, sa); break;
-        case AB_OP_CURVE_INST: op_curve_inst(p, a, sa); break;
-        case AB_OP_ZERO_Z: p.z = constant_like(p.z, T(0)); break;
+        case D_ROTSYM: op_rotsym(p, a); break;
+        case D_REVOLVE: op_revolve(p, a); break;
+        case D_AXIS_REVOLVE: op_axis_revolve(p, a); break;
+        case D_REP_INF: op_rep_inf(p, a); break;
+        case D_REP_FIN: op_rep_fin(p, a); break;
+        case D_LIN_INST: op_lin_inst(p, a, sa); break;
+        case D_CURVE_INST: op_curve_inst(p, a, sa); break;
+        case D_ZERO_Z: p.z = constant_like(p.z, T(0)); break;
         // value ops
-        case AB_OP_ROUND: acc = acc - a[0]; break;
-        case AB_OP_ABS: acc = abs_(acc); break;
-        case AB_OP_NEG: acc = -acc; break;
-        case AB_OP_SIGN: acc = sign_(acc); break;
-        case AB_OP_ONION: acc = abs_(acc) - a[0]; break;
-        case AB_OP_CONCENTRIC: acc = abs_(acc - a[0]); break;
-        case AB_OP_SCALE_V: acc = acc * a[0]; break;
-        case AB_OP_EXTRUDE_BEGIN:
+        case D_ROUND: acc = acc - a[0]; break;
+        case D_ABS: acc = abs_(acc); break;
+        case D_NEG: acc = -acc; break;
+        case D_SIGN: acc = sign_(acc); break;
+        case D_ONION: acc = abs_(acc) - a[0]; break;
+        case D_CONCENTRIC: acc = abs_(acc - a[0]); break;
+        case D_SCALE_V: acc = acc * a[0]; break;
+        case D_EXTRUDE_BEGIN:
           SK::st(vstack, sa, NT, abs_(p.z) - a[0]);
           p.z = constant_like(p.z, T(0));
           break;
-        case AB_OP_EXTRUDE_END: acc = op_extrude_end<S, T>(acc, SK::ld(vstack, sa, NT)); break;
+        case D_EXTRUDE_END: acc = op_extrude_end<S, T>(acc, SK::ld(vstack, sa, NT)); break;
         // post-processing (post_processing.py:380-560)
-        case AB_OP_PP_SIGMOID: acc = div_(constant_like(acc, a[0]), exp_(acc * (T(4) * s_rcp(a[1]))) + T(1)); break;
-        case AB_OP_PP_POS_SIGMOID:
+        case D_PP_SIGMOID: acc = div_(constant_like(acc, a[0]), exp_(acc * (T(4) * s_rcp(a[1]))) + T(1)); break;
+        case D_PP_POS_SIGMOID:
           acc = div_(constant_like(acc, a[0]), exp_((acc - a[1]) * (T(4) * s_rcp(a[1]))) + T(1));
           break;
-        case AB_OP_PP_CAPPED_EXP: acc = min_(exp_(acc * (T(-4) * s_rcp(a[1]))), T(1)) * a[0]; break;
-        case AB_OP_PP_HARD_BIN:
+        case D_PP_CAPPED_EXP: acc = min_(exp_(acc * (T(-4) * s_rcp(a[1]))), T(1)) * a[0]; break;
+        case D_PP_HARD_BIN:
           acc = select_(le_(acc, a[0]), constant_like(acc, T(1)), constant_like(acc, T(0)));
           break;
-        case AB_OP_PP_LINEAR: acc = clamp_(T(1) - acc * s_rcp(a[1]), T(0), T(1)) * a[0]; break;
-        case AB_OP_PP_RELU: acc = max_(acc * s_rcp(a[0]), T(0)); break;
-        case AB_OP_PP_SMOOTH_RELU: {
+        case D_PP_LINEAR: acc = clamp_(T(1) - acc * s_rcp(a[1]), T(0), T(1)) * a[0]; break;
+        case D_PP_RELU: acc = max_(acc * s_rcp(a[0]), T(0)); break;
+        case D_PP_SMOOTH_RELU: {
           S v = acc * s_rcp(a[1]);
           acc = (v + sqrt_(fma_(v, v, constant_like(v, a[0])))) * T(0.5);
         } break;
-        case AB_OP_PP_SLOWSTART: {
+        case D_PP_SLOWSTART: {
           S v = max_(acc * s_rcp(a[0]), T(0));
           acc = sqrt_(fma_(v, v, constant_like(v, a[1]))) - a[2];
         } break;
-        case AB_OP_PP_GAUSS_BOUNDARY: {
+        case D_PP_GAUSS_BOUNDARY: {
           S v = acc * s_rcp(a[1]);
           acc = exp_(v * v * T(-4)) * a[0];
         } break;
-        case AB_OP_PP_GAUSS_FALLOFF: {
+        case D_PP_GAUSS_FALLOFF: {
           S v = max_(acc, T(0)) * s_rcp(a[1]);
           acc = exp_(v * v * T(-4)) * a[0];
         } break;
         // combine: acc = f(V[a], acc)
-        case AB_OP_C_UNION: acc = min_(SK::ld(vstack, sa, NT), acc); break;
-        case AB_OP_C_INTERSECT: acc = max_(SK::ld(vstack, sa, NT), acc); break;
-        case AB_OP_C_SUBTRACT: acc = max_(SK::ld(vstack, sa, NT), -acc); break;
-        case AB_OP_C_SUM: acc = SK::ld(vstack, sa, NT) + acc; break;
-        case AB_OP_C_DIFF: acc = SK::ld(vstack, sa, NT) - acc; break;
-        case AB_OP_C_SMIN2: acc = smin_poly2(SK::ld(vstack, sa, NT), acc, a[0]); break;
-        case AB_OP_C_SMIN3: acc = smin_poly3(SK::ld(vstack, sa, NT), acc, a[0]); break;
-        case AB_OP_C_SMAX3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), -acc, a[0]); break;
-        case AB_OP_C_SSUB3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), acc, a[0]); break;
-        case AB_OP_C_BOLTZ_INT: acc = smax_boltz(SK::ld(vstack, sa, NT), acc, a[0]); break;
-        case AB_OP_C_BOLTZ_SUB: acc = smax_boltz(SK::ld(vstack, sa, NT), -acc, a[0]); break;
+        case D_C_UNION: acc = min_(SK::ld(vstack, sa, NT), acc); break;
+        case D_C_INTERSECT: acc = max_(SK::ld(vstack, sa, NT), acc); break;
+        case D_C_SUBTRACT: acc = max_(SK::ld(vstack, sa, NT), -acc); break;
+        case D_C_SUM: acc = SK::ld(vstack, sa, NT) + acc; break;
+        case D_C_DIFF: acc = SK::ld(vstack, sa, NT) - acc; break;
+        case D_C_SMIN2: acc = smin_poly2(SK::ld(vstack, sa, NT), acc, a[0]); break;
+        case D_C_SMIN3: acc = smin_poly3(SK::ld(vstack, sa, NT), acc, a[0]); break;
+        case D_C_SMAX3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), -acc, a[0]); break;
+        case D_C_SSUB3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), acc, a[0]); break;
+        case D_C_BOLTZ_INT: acc = smax_boltz(SK::ld(vstack, sa, NT), acc, a[0]); break;
+        case D_C_BOLTZ_SUB: acc = smax_boltz(SK::ld(vstack, sa, NT), -acc, a[0]); break;
         // 3D primitives
-        case AB_OP_P_SPHERE: acc = prim_sphere(p, a); break;
-        case AB_OP_P_CYLINDER: acc = prim_cylinder(p, a); break;
-        case AB_OP_P_BOX: acc = prim_box(p, a); break;
-        case AB_OP_P_TORUS: acc = prim_torus(p, a); break;
-        case AB_OP_P_CHAINLINK: acc = prim_chainlink(p, a); break;
-        case AB_OP_P_BRAID: acc = prim_braid(p, a); break;
-        case AB_OP_P_ARC3D: acc = prim_arc3d(p, a); break;
-        case AB_OP_P_PLANE: acc = prim_plane(p, a); break;
-        case AB_OP_P_UPLANE: acc = prim_uplane(p, a); break;
-        case AB_OP_P_SEGMENT: acc = prim_segment(p, a); break;
-        case AB_OP_P_CONE: acc = prim_cone(p, a); break;
-        case AB_OP_P_OINF_CONE: acc = prim_inf_cone(p, a, true); break;
-        case AB_OP_P_INF_CONE: acc = prim_inf_cone(p, a, false); break;
-        case AB_OP_P_SOLID_ANGLE: acc = prim_solid_angle(p, a); break;
-        case AB_OP_P_TRIANGLE3D: acc = prim_triangle3d(p, a); break;
-        case AB_OP_P_QUAD3D: acc = prim_quad3d(p, a); break;
-        case AB_OP_P_SEGLINE: acc = prim_segline(p, a, 3); break;
-        case AB_OP_P_AXIS: acc = (sa == 0 ? p.x : (sa == 1 ? p.y : p.z)) - a[0]; break;
-        case AB_OP_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[op.b], kp.blob_count[op.b], sa); break;
+        case D_P_SPHERE: acc = prim_sphere(p, a); break;
+        case D_P_CYLINDER: acc = prim_cylinder(p, a); break;
+        case D_P_BOX: acc = prim_box(p, a); break;
+        case D_P_TORUS: acc = prim_torus(p, a); break;
+        case D_P_CHAINLINK: acc = prim_chainlink(p, a); break;
+        case D_P_BRAID: acc = prim_braid(p, a); break;
+        case D_P_ARC3D: acc = prim_arc3d(p, a); break;
+        case D_P_PLANE: acc = prim_plane(p, a); break;
+        case D_P_UPLANE: acc = prim_uplane(p, a); break;
+        case D_P_SEGMENT: acc = prim_segment(p, a); break;
+        case D_P_CONE: acc = prim_cone(p, a); break;
+        case D_P_OINF_CONE: acc = prim_inf_cone(p, a, true); break;
+        case D_P_INF_CONE: acc = prim_inf_cone(p, a, false); break;
+        case D_P_SOLID_ANGLE: acc = prim_solid_angle(p, a); break;
+        case D_P_TRIANGLE3D: acc = prim_triangle3d(p, a); break;
+        case D_P_QUAD3D: acc = prim_quad3d(p, a); break;
+        case D_P_SEGLINE: acc = prim_segline(p, a, 3); break;
+        case D_P_AXIS:
+          if (sa == 0) acc = p.x - a[0];
+          else if (sa == 1) acc = p.y - a[0];
+          else acc = p.z - a[0];
+          break;
+        case D_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[op.b], kp.blob_count[op.b], sa); break;
         // 2D primitives
-        case AB_OP_P_CIRCLE: acc = prim_circle(p, a); break;
-        case AB_OP_P_NEU_CIRCLE: acc = prim_neu_circle(p, a); break;
-        case AB_OP_P_BOX2D: acc = prim_box2d(p, a); break;
-        case AB_OP_P_SEGMENT2D: acc = prim_segment2d(p, a); break;
-        case AB_OP_P_RBOX2D: acc = prim_rbox2d(p, a); break;
-        case AB_OP_P_TRIANGLE2D: acc = prim_triangle2d(p, a); break;
-        case AB_OP_P_ARC: acc = prim_arc(p, a); break;
-        case AB_OP_P_SECTOR: acc = prim_sector(p, a); break;
-        case AB_OP_P_INF_SECTOR: acc = prim_inf_sector(p, a); break;
-        case AB_OP_P_NGON: acc = prim_ngon(p, a); break;
-        case AB_OP_P_SEGLINE2D: acc = prim_segline(p, a, 2); break;
+        case D_P_CIRCLE: acc = prim_circle(p, a); break;
+        case D_P_NEU_CIRCLE: acc = prim_neu_circle(p, a); break;
+        case D_P_BOX2D: acc = prim_box2d(p, a); break;
+        case D_P_SEGMENT2D: acc = prim_segment2d(p, a); break;
+        case D_P_RBOX2D: acc = prim_rbox2d(p, a); break;
+        case D_P_TRIANGLE2D: acc = prim_triangle2d(p, a); break;
+        case D_P_ARC: acc = prim_arc(p, a); break;
+        case D_P_SECTOR: acc = prim_sector(p, a); break;
+        case D_P_INF_SECTOR: acc = prim_inf_sector(p, a); break;
+        case D_P_NGON: acc = prim_ngon(p, a); break;
+        case D_P_SEGLINE2D: acc = prim_segline(p, a, 2); break;
         default: break;  // unknown opcodes are rejected on the host (AB_EUNSUPPORTED_OP)
       }
     }
@@ -456,6 +515,14 @@ cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream
   const uint64_t n_tiles = (kp.n + tile_pts - 1) / tile_pts;
   const uint64_t resident = (uint64_t)cfg.sms * occ;  // persistent CTAs: a whole number of resident waves
   const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+  KParams<T>& k = const_cast<KParams<T>&>(kp);
+  if (kp.grid_mode) {
+    const uint64_t d = (uint64_t)grid * tile_pts;
+    k.tile_stride[0] = (uint32_t)(d / kp.g.plane);
+    const uint64_t rem = d % kp.g.plane;
+    k.tile_stride[1] = (uint32_t)(rem / kp.g.n2);
+    k.tile_stride[2] = (uint32_t)(rem % kp.g.n2);
+  }
   kern<<<grid, nt, smem, st>>>(kp);
   return cudaGetLastError();
 }

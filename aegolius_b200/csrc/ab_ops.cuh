@@ -433,8 +433,13 @@ AB_DEV S prim_triangle2d(const Pt<S>& p, const T* g) {  // :60-82 ; args p0,p1,p
     S q0 = v0 - h * ex, q1 = v1 - h * ey;
     S dd = fma_(q0, q0, q1 * q1);
     S cr = (v0 * ey - v1 * ex) * g[15];
-    d0 = i ? min_(d0, dd) : dd;
-    d1 = i ? min_(d1, cr) : cr;
+    if (i == 0) {
+      d0 = dd;
+      d1 = cr;
+    } else {
+      d0 = min_(d0, dd);
+      d1 = min_(d1, cr);
+    }
   }
   return -mul_lane(sqrt_(d0), value_sign(d1));
 }

@@ -25,11 +25,7 @@ G3B = ((6.0, 6.0, 6.0), (20, 20, 20))    # -> 21^3
 G2 = ((8.0, 8.0), (64, 48))              # -> 65 x 49
 
 
-def spiral(t, radius, height, freq):  # Code/examples/scalar/3D/spiral_instancing_3D.py:16-22
-    x = radius * np.cos(2 * np.pi * freq * t)
-    y = radius * np.sin(2 * np.pi * freq * t)
-    z = height * t - height / 2
-    return np.asarray((x, y, z))
+from aegolius_b200.workloads import spiral, build_c1, build_c2, build_c3  # noqa: E402,F401
 
 
 def circle_curve(t, radius):
@@ -40,84 +36,10 @@ def circle_curve(t, radius):
 # BASELINE configs
 
 
-def build_c1(ns):
-    s = ns.Sphere(1.0)
-    s.move((0.5, 0, 0))
-    b = ns.Box(1.5, 1.0, 0.8)
-    b.rotate(np.pi / 5, (0, 0, 1))
-    b.move((-0.4, 0.2, 0.1))
-    return ns.CombineGeometry("SMOOTH_UNION2").combine_parametric(s, b, parameters=0.3)
-
-
 scenario("c1_sphere_box_smooth_union", *G3)(build_c1)
 
 
-def build_c2(ns):
-    rng = np.random.default_rng(0)
-
-    def shapes():
-        return [
-            lambda: ns.Circle(0.8), lambda: ns.Rectangle(1.4, 0.9),
-            lambda: ns.RoundedRectangle(1.5, 1.0, (0.1, 0.2, 0.3, 0.15)), lambda: ns.NGon(0.8, 5),
-            lambda: ns.Triangle((-0.6, -0.4), (0.7, -0.3), (0.1, 0.8)), lambda: ns.Sector(0.9, 0.3, 2.0),
-            lambda: _rounded(ns.Arc(0.7, 0.2, 2.4), 0.1),
-        ]
-
-    def _rounded(o, r):
-        o.rounding(r)
-        return o
-
-    makers = shapes()
-    counter = [0]
-
-    def fresh():
-        o = makers[counter[0] % len(makers)]()
-        counter[0] += 1
-        o.rotate(float(rng.uniform(0, 2 * np.pi)), (0, 0, 1))
-        o.rescale(float(rng.uniform(0.6, 1.6)))
-        t = rng.uniform(-2.5, 2.5, size=2)
-        o.move((float(t[0]), float(t[1]), 0.0))
-        return o
-
-    nonparam = ["UNION2", "UNION", "SUBTRACT2", "INTERSECT2", "INTERSECT", "SUM", "DIFFERENCE"]
-    param = ["SMOOTH_UNION2_2", "SMOOTH_UNION2", "SMOOTH_INTERSECT2", "SMOOTH_INTERSECT2_BOLTZMANN",
-             "SMOOTH_SUBTRACT2", "SMOOTH_SUBTRACT2_BOLTZMANN"]
-    acc = fresh()
-    for op in nonparam:
-        if op in ("UNION2", "UNION"):
-            acc = ns.CombineGeometry(op).combine(acc, fresh())
-        else:
-            side = ns.CombineGeometry(op).combine(fresh(), fresh())
-            acc = ns.CombineGeometry("UNION2").combine(acc, side)
-    for op in param:
-        w = float(rng.uniform(0.2, 0.5))
-        if op in ("SMOOTH_UNION2_2", "SMOOTH_UNION2"):
-            acc = ns.CombineGeometry(op).combine_parametric(acc, fresh(), parameters=w)
-        else:
-            side = ns.CombineGeometry(op).combine_parametric(fresh(), fresh(), parameters=w)
-            acc = ns.CombineGeometry("UNION2").combine(acc, side)
-    return acc
-
-
 scenario("c2_composite_2d_all13", *G2)(build_c2)
-
-
-def build_c3(ns):
-    t = ns.Torus(0.25, 0.2)
-    t.elongation((2, 0, 0))
-    t.rotate(np.pi / 2, (0, 1, 0))
-    g = ns.GenericGeometry(t.propagate, ())
-    g.twist(np.pi)
-    g.bend(2.0, 1.0)
-    g.rotational_symmetry(6, 1.5, 0.1)
-    g.fully_aligned_curve_instancing(spiral, (1, 2, 2), (0, 1, 21))
-    s = ns.Sphere(0.4)
-    s.move((0.2, 0, 0))
-    s.onion(0.05)
-    u = ns.CombineGeometry("SMOOTH_UNION2").combine_parametric(g, s, parameters=0.3)
-    u.rounding(0.01)
-    u.mirror((-1, 0, 0), (1, 0, 0))
-    return u
 
 
 scenario("c3_deep_tree", *G3B)(build_c3)

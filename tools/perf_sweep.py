@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Device-time sweep over the BASELINE configs (and the shallow-tree roofline probes). Prints one JSON line per case:
+Gpts/s, achieved GB/s of algorithmic output bytes and the fraction of the measured HBM peak. Used to steer kernel work;
+bench.py stays the contract benchmark."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import aegolius_b200 as ab
+    from aegolius_b200 import engine, workloads, cabi
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="sphere,c1,c3,c3g,c2,c1_64,c3_64,nn")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--nn-res", type=int, default=128)
+    args = ap.parse_args()
+    peak = 6452.8
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p))["hbm_gbs"])
+    dev = torch.device("cuda", 0)
+
+    sph = ab.Sphere(1.0)
+    sph.move((0.3, 0.1, -0.2))
+    cases = {
+        "sphere": (sph, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
+        "c1": (workloads.build_c1(), ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
+        "c1g": (workloads.build_c1(), ab.GridSpec((4, 4, 4), (768,) * 3), "f32", "spatial"),
+        "c3": (workloads.build_c3(), ab.GridSpec((6, 6, 6), (512,) * 3), "f32", None),
+        "c3g": (workloads.build_c3(), ab.GridSpec((6, 6, 6), (512,) * 3), "f32", "spatial"),
+        "c2": (workloads.build_c2(), ab.GridSpec((8, 8), (4096, 4096)), "f32", None),
+        "c1_64": (workloads.build_c1(), ab.GridSpec((4, 4, 4), (768,) * 3), "f64", None),
+        "c3_64": (workloads.build_c3(), ab.GridSpec((6, 6, 6), (384,) * 3), "f64", None),
+        "c3g_64": (workloads.build_c3(), ab.GridSpec((6, 6, 6), (256,) * 3), "f64", "spatial"),
+    }
+    for name in args.cases.split(","):
+        if name == "nn":
+            pts = workloads.c4_cloud(1_000_000)
+            spec = ab.GridSpec((2.5, 2.5, 1.5), (args.nn_res,) * 3)
+            import ctypes as C
+            lib = cabi.lib()
+            d_cloud = C.c_void_p()
+            cabi.check(lib.ab_cloud_upload(pts.ctypes.data, pts.shape[1], 3, pts.shape[1], cabi.AB_F32, 0, C.byref(d_cloud)))
+            out = torch.empty(spec.n_points, dtype=torch.float32, device=dev)
+            g = cabi.make_grid(spec.size, spec.res)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+            def run():
+                cabi.check(lib.ab_nn_grid(d_cloud, pts.shape[1], 3, C.byref(g), cabi.AB_F32, out.data_ptr(), 0, st))
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            pairs = spec.n_points * pts.shape[1]
+            print(json.dumps({"case": f"nn {spec.res} x 1M", "ms": ms, "Tpairs_per_s": pairs / ms / 1e9,
+                              "Mqueries_per_s": spec.n_points / ms / 1e3}), flush=True)
+            continue
+        obj, spec, dt, grad = cases[name]
+        prog = ab.flatten(obj)
+        tdt = torch.float32 if dt == "f32" else torch.float64
+        n = spec.n_points
+        field = torch.empty(n, dtype=tdt, device=dev)
+        gbuf = torch.empty((3, (n + 3) // 4 * 4), dtype=tdt, device=dev) if grad else None
+
+        def run():
+            engine.create_torch(prog, spec, dtype=dt, grad=grad, out=field, out_grad=gbuf)
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(args.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times))
+        bpp = (4 if dt == "f32" else 8) * (4 if grad else 1)
+        gbs = bpp * n / ms / 1e6
+        print(json.dumps({"case": name, "res": spec.res, "dtype": dt, "grad": bool(grad), "ops": prog.n_ops,
+                          "ms": round(ms, 4), "best_ms": round(min(times), 4), "Gpts_per_s": round(n / ms / 1e6, 2),
+                          "GBps": round(gbs, 1), "hbm_frac": round(gbs / peak, 4)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
