@@ -84,7 +84,7 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
     case AB_OP_C_SMIN2: case AB_OP_C_SMIN3: case AB_OP_C_SMAX3: case AB_OP_C_SSUB3: case AB_OP_C_BOLTZ_INT:
     case AB_OP_C_BOLTZ_SUB: case AB_OP_P_SPHERE: case AB_OP_P_AXIS: case AB_OP_P_CIRCLE:
       n = 1; break;
-    case AB_OP_ROTSYM: case AB_OP_PP_SIGMOID: case AB_OP_PP_POS_SIGMOID: case AB_OP_PP_CAPPED_EXP: case AB_OP_PP_LINEAR:
+    case AB_OP_PP_SIGMOID: case AB_OP_PP_POS_SIGMOID: case AB_OP_PP_CAPPED_EXP: case AB_OP_PP_LINEAR:
     case AB_OP_PP_SMOOTH_RELU: case AB_OP_PP_GAUSS_BOUNDARY: case AB_OP_PP_GAUSS_FALLOFF: case AB_OP_P_CYLINDER:
     case AB_OP_P_TORUS: case AB_OP_P_OINF_CONE: case AB_OP_P_INF_CONE: case AB_OP_P_NEU_CIRCLE: case AB_OP_P_BOX2D:
       n = 2; break;
@@ -102,6 +102,12 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
     case AB_OP_P_TRIANGLE2D: n = 16; break;
     case AB_OP_P_TRIANGLE3D: n = 34; break;
     case AB_OP_P_QUAD3D: n = 44; break;
+    case AB_OP_ROTSYM: {
+      if ((uint64_t)op.arg + 4 > n_args) return fail(AB_EINVAL, "ROTSYM header out of range");
+      double c = args[op.arg + 2];
+      if (!(c >= 1) || c > 1024 || c != (double)(int)c) return fail(AB_EINVAL, "bad ROTSYM sector count %g", c);
+      n = 4 + 2 * (int)c;
+    } break;
     case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: {
       if (op.arg >= n_args) return fail(AB_EINVAL, "op argument offset out of range");
       double c = args[op.arg];
@@ -278,11 +284,20 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   while (kp.n_ops > 0 && prog->ops[kp.n_ops - 1].opcode == AB_OP_END) kp.n_ops--;  // no dispatch spent on the terminator
   kp.n_pslots = prog->n_pslots ? prog->n_pslots : 1;
   kp.n_vslots = prog->n_vslots ? prog->n_vslots : 1;
-  for (uint32_t i = 0; i < prog->n_ops; i++) {
+  // repack: every op's arguments start on a 16-byte boundary of the kernel's pool (vector loads from shared memory)
+  uint32_t cursor = 0;
+  for (uint32_t i = 0; i < kp.n_ops; i++) {
     kp.ops[i] = prog->ops[i];
     kp.ops[i].opcode = (uint16_t)dense_opcode(prog->ops[i].opcode);  // validated above
+    int cnt = 0;
+    op_arg_count(prog->ops[i], prog->args, prog->n_args, &cnt);
+    if (cursor + (uint32_t)cnt + 4 > AB_MAX_ARGS)
+      return fail(AB_ETOOLARGE, "program arguments exceed %d after alignment", AB_MAX_ARGS);
+    kp.ops[i].arg = cursor;
+    for (int k = 0; k < cnt; k++) kp.args[cursor + k] = (T)prog->args[prog->ops[i].arg + k];
+    cursor = (cursor + (uint32_t)cnt + 3u) & ~3u;
   }
-  for (uint32_t i = 0; i < prog->n_args; i++) kp.args[i] = (T)prog->args[i];
+  kp.n_args = cursor;
 
   std::vector<void*> temp_blobs;
   for (uint32_t b = 0; b < AB_MAX_BLOBS; b++) {

@@ -88,7 +88,7 @@ struct KParams {
   int32_t grid_mode;
   GridK g;
   uint32_t tile_stride[3];  // (d0, d1, d2): decomposition of gridDim.x * tile points, filled in by the launcher
-  uint32_t n_ops, n_pslots, n_vslots;
+  uint32_t n_ops, n_args, n_pslots, n_vslots;
   const void* blob[AB_MAX_BLOBS];  // (x, y, z, 0) records of T
   uint32_t blob_count[AB_MAX_BLOBS];
   ab_op ops[AB_MAX_OPS];
@@ -251,6 +251,10 @@ AB_DEV S prim_point_cloud(const Pt<S>& p, const void* __restrict__ cloud_v, uint
   return norm2_(dx, dy);
 }
 
+__host__ __device__ inline size_t prog_ops_bytes(uint32_t n_ops) { return ((size_t)n_ops * sizeof(ab_op) + 15) & ~(size_t)15; }
+template <typename T>
+__host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((size_t)n_args * sizeof(T) + 15) & ~(size_t)15; }
+
 // ---- the interpreter -------------------------------------------------------------------------------------------------------
 template <typename S, typename T>
 __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
@@ -259,8 +263,15 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
   typedef Pack<T, W> P;
   typedef StackOf<S> SK;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  P* pstack = reinterpret_cast<P*>(smem_raw);                         // [n_pslots*3*cols][NT]
+  // shared memory: [ops][args][P stack][V stack]. The program is staged once per (persistent) CTA; afterwards every op
+  // fetch is one broadcast LDS.64 and its arguments come in with 128-bit broadcast loads.
+  ab_op* s_ops = reinterpret_cast<ab_op*>(smem_raw);
+  T* s_args = reinterpret_cast<T*>(smem_raw + prog_ops_bytes(kp.n_ops));
+  P* pstack = reinterpret_cast<P*>(smem_raw + prog_ops_bytes(kp.n_ops) + prog_args_bytes<T>(kp.n_args));
   P* vstack = pstack + (size_t)kp.n_pslots * 3 * SK::cols * NT;       // [n_vslots*cols][NT]
+  for (uint32_t i = threadIdx.x; i < kp.n_ops; i += NT) s_ops[i] = kp.ops[i];
+  for (uint32_t i = threadIdx.x; i < kp.n_args; i += NT) s_args[i] = kp.args[i];
+  __syncthreads();
 
   const uint32_t tile_pts = (uint32_t)NT * W;
   const uint32_t n32 = (uint32_t)kp.n;
@@ -341,11 +352,11 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
     S acc = constant_like(p.x, T(0));
 
     for (uint32_t pc = 0; pc < kp.n_ops; pc++) {
-      const ab_op op = kp.ops[pc];
-      const T* a = kp.args + op.arg;
+      const ab_op op = s_ops[pc];
+      const T* a = reinterpret_cast<const T*>(__builtin_assume_aligned(s_args + op.arg, 16));
       const int sa = op.a;
       switch (op.opcode) {
-        case D_END: pc = kp.n_ops; break;
+        case D_END: break;
         case D_SAVE_P:
           SK::st(pstack, sa * 3 + 0, NT, p.x);
           SK::st(pstack, sa * 3 + 1, NT, p.y);
@@ -489,11 +500,12 @@ cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream
   typedef StackOf<S> SK;
   *status = AB_OK;
   const size_t per_thread = (size_t)sizeof(typename SK::P) * SK::cols * ((size_t)kp.n_pslots * 3 + kp.n_vslots);
+  const size_t prog_bytes = prog_ops_bytes(kp.n_ops) + prog_args_bytes<T>(kp.n_args);
   // prefer 128 threads; shrink the CTA when the stacks would not leave room for >= 2 CTAs per SM
   int nt = 128;
-  if (per_thread * 128 > 96 * 1024) nt = 64;
-  if (per_thread * nt > cfg.smem_optin) nt = 32;
-  const size_t smem = per_thread * nt;
+  if (prog_bytes + per_thread * 128 > 96 * 1024) nt = 64;
+  if (prog_bytes + per_thread * nt > cfg.smem_optin) nt = 32;
+  const size_t smem = prog_bytes + per_thread * nt;
   if (smem > cfg.smem_optin) {
     *status = AB_ETOOLARGE;
     return cudaSuccess;

@@ -79,18 +79,34 @@ AB_DEV void op_bend(Pt<S>& p, const T* a) {
 // modifications.py:991-993
 template <typename S, typename T>
 AB_DEV void op_absx_sub(Pt<S>& p, const T* a) { p.x = abs_(p.x) - a[0]; }
-// modifications.py:1023-1029 (pre-rotation emitted as AFFINE); args angle, radius
+// modifications.py:1023-1029 (pre-rotation emitted as AFFINE); args angle, radius, n_sectors, pad, (cos, sin)[n_sectors].
+// The reference maps phi -> mod(phi, angle) - angle/2 and rebuilds (r cos, r sin); that is a rotation by
+// -theta_k, theta_k = k*angle + angle/2, k = floor(phi/angle): the sector comes from atan2, the rotation from the
+// host-computed table (fewer roundings than the polar round trip, no sqrt / sincos / mod).
 template <typename S, typename T>
 AB_DEV void op_rotsym(Pt<S>& p, const T* a) {
+  constexpr int W = S::width;
   const T ang = a[0], rad = a[1];
-  S phi = atan2_(p.y, p.x);
-  phi = select_(lt_(phi, T(0)), phi + T(6.283185307179586476925286766559), phi);
-  phi = mod_(phi, ang) - T(0.5) * ang;
-  S rr = norm2_(p.x, p.y);
-  S s, c;
-  sincos_(phi, s, c);
-  p.x = rr * c - rad;
-  p.y = rr * s;
+  const int nsec = (int)a[2];
+  const T inv = s_rcp(ang);
+  auto vx = value_of(p.x), vy = value_of(p.y);
+  Pack<T, W> c, s;
+#pragma unroll
+  for (int i = 0; i < W; i++) {
+    T phi = s_atan2(vy.v[i], vx.v[i]);
+    if (phi < T(0)) phi += T(6.283185307179586476925286766559);
+    int k = (int)(phi * inv);
+    k = k < 0 ? 0 : (k >= nsec ? nsec - 1 : k);
+    // one more exact step: phi*inv may round across an integer
+    if (phi < (T)k * ang && k > 0) k--;
+    else if (phi >= (T)(k + 1) * ang && k + 1 < nsec) k++;
+    c.v[i] = a[4 + 2 * k];
+    s.v[i] = a[5 + 2 * k];
+  }
+  S nx = mul_lane(p.x, c) + mul_lane(p.y, s) - rad;
+  S ny = mul_lane(p.y, c) - mul_lane(p.x, s);
+  p.x = nx;
+  p.y = ny;
 }
 // modifications.py:427-431
 template <typename S, typename T>
@@ -160,12 +176,12 @@ AB_DEV void op_curve_inst(Pt<S>& p, const T* a, int mode) {
   }
   for (int j = 0; j < n; j++) {
     const T cx = rec[j * stride], cy = rec[j * stride + 1], cz = rec[j * stride + 2];
+    const Pack<T, W> dx = vx - cx, dy = vy - cy, dz = vz - cz;  // packed f32x2 lanes
+    const Pack<T, W> d2 = fma_(dx, dx, fma_(dy, dy, dz * dz));
 #pragma unroll
     for (int i = 0; i < W; i++) {
-      T dx = vx.v[i] - cx, dy = vy.v[i] - cy, dz = vz.v[i] - cz;
-      T d2 = s_fma(dx, dx, s_fma(dy, dy, dz * dz));
-      if (d2 < best[i]) {
-        best[i] = d2;
+      if (d2.v[i] < best[i]) {
+        best[i] = d2.v[i];
         idx[i] = j;
       }
     }

@@ -291,7 +291,15 @@ class _Builder:
         elif name == "rotational_symmetry":
             angle = float(p["angle"])
             self.affine(_rot2(angle / 2 - p["phase"]), np.zeros(3))
-            self.emit(oc.ROTSYM, args=[angle, p["radius"]])
+            # args: angle, radius, number of sectors, pad, then (cos, sin) of every sector's centre direction
+            # theta_k = k*angle + angle/2: the kernel picks the sector from atan2 and rotates by the exact table entry
+            # instead of going through mod / cos / sin of the reduced angle (same map, fewer roundings)
+            nsec = int(np.ceil(2 * np.pi / abs(angle) - 1e-9))
+            if nsec < 1 or nsec > 1024 or not angle > 0:
+                raise FlattenError(f"rotational_symmetry order {2 * np.pi / angle:g} is outside [1, 1024]")
+            th = (np.arange(nsec) + 0.5) * angle
+            tab = np.stack([np.cos(th), np.sin(th)], axis=1).reshape(-1)
+            self.emit(oc.ROTSYM, args=[angle, p["radius"], float(nsec), 0.0] + list(tab))
         elif name == "linear_instancing":
             rot, c, l = _segment_frame(p["a"], p["b"], "linear_instancing")
             n = int(p["n"])
@@ -578,7 +586,9 @@ def _peephole(ops, args):
         n = oc.ARG_COUNT.get(code)
         if n is None:
             cnt = int(args[off])
-            if code == oc.CURVE_INST:
+            if code == oc.ROTSYM:
+                n = 4 + 2 * int(args[off + 2])
+            elif code == oc.CURVE_INST:
                 n = 1 + cnt * (12 if a == 1 else 3)
             elif code == oc.P_SEGLINE:
                 n = 1 + cnt * 3
