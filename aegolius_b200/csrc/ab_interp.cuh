@@ -10,6 +10,9 @@
 // Grid layout (generate_grid, helper_functions.py:23-93): flat k = (ix*ny + iy)*nz + iz, z fastest; the slab is a range
 // of ix planes, i.e. one contiguous range of k. Coordinates are regenerated from (ix,iy,iz): 0 bytes read per point.
 #pragma once
+#ifndef AB_TIER_FULL
+#define AB_TIER_FULL 1
+#endif
 #include "../../include/aegolius_b200.h"
 #include "ab_ops.cuh"
 
@@ -89,6 +92,7 @@ struct KParams {
   GridK g;
   uint32_t tile_stride[3];  // (d0, d1, d2): decomposition of gridDim.x * tile points, filled in by the launcher
   uint32_t n_ops, n_args, n_pslots, n_vslots;
+  int32_t tier;  // 0 = every op is in the lite set (host-side choice of kernel variant)
   const void* blob[AB_MAX_BLOBS];  // (x, y, z, 0) records of T
   uint32_t blob_count[AB_MAX_BLOBS];
   ab_op ops[AB_MAX_OPS];
@@ -256,8 +260,13 @@ template <typename T>
 __host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((size_t)n_args * sizeof(T) + 15) & ~(size_t)15; }
 
 // ---- the interpreter -------------------------------------------------------------------------------------------------------
-template <typename S, typename T>
+// TIER 0 ("lite") contains only the ops without transcendental functions or tables (stack, affine family, elongate,
+// mirror core, symmetry, revolve, infinite repetition, the value ops, the polynomial combines and the sqrt-only
+// primitives): 40 registers instead of ~120, so 3x the resident warps, and a 23 KB body instead of 170 KB. The host
+// picks the smallest tier that covers the program (is_lite_op below). TIER 1 is the full interpreter.
+template <typename S, typename T, int TIER>
 __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
+  static_assert(TIER == AB_TIER_FULL, "one tier per translation unit");
   constexpr int W = S::width;
   const int NT = blockDim.x;
   typedef Pack<T, W> P;
@@ -373,21 +382,35 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
         case D_TRANSLATE: op_translate(p, a); break;
         case D_SCALE_P: op_scale_p(p, a); break;
         case D_ELONGATE: op_elongate(p, a); break;
+#if AB_TIER_FULL
         case D_TWIST: op_twist(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_BEND: op_bend(p, a); break;
+#endif
         case D_ABSX_SUB: op_absx_sub(p, a); break;
         case D_SYMMETRY:
           if (sa == 0) p.x = abs_(p.x);
           else if (sa == 1) p.y = abs_(p.y);
           else p.z = abs_(p.z);
           break;
+#if AB_TIER_FULL
         case D_ROTSYM: op_rotsym(p, a); break;
+#endif
         case D_REVOLVE: op_revolve(p, a); break;
+#if AB_TIER_FULL
         case D_AXIS_REVOLVE: op_axis_revolve(p, a); break;
+#endif
         case D_REP_INF: op_rep_inf(p, a); break;
+#if AB_TIER_FULL
         case D_REP_FIN: op_rep_fin(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_LIN_INST: op_lin_inst(p, a, sa); break;
+#endif
+#if AB_TIER_FULL
         case D_CURVE_INST: op_curve_inst(p, a, sa); break;
+#endif
         case D_ZERO_Z: p.z = constant_like(p.z, T(0)); break;
         // value ops
         case D_ROUND: acc = acc - a[0]; break;
@@ -403,32 +426,52 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
           break;
         case D_EXTRUDE_END: acc = op_extrude_end<S, T>(acc, SK::ld(vstack, sa, NT)); break;
         // post-processing (post_processing.py:380-560)
+#if AB_TIER_FULL
         case D_PP_SIGMOID: acc = div_(constant_like(acc, a[0]), exp_(acc * (T(4) * s_rcp(a[1]))) + T(1)); break;
+#endif
+#if AB_TIER_FULL
         case D_PP_POS_SIGMOID:
           acc = div_(constant_like(acc, a[0]), exp_((acc - a[1]) * (T(4) * s_rcp(a[1]))) + T(1));
           break;
+#endif
+#if AB_TIER_FULL
         case D_PP_CAPPED_EXP: acc = min_(exp_(acc * (T(-4) * s_rcp(a[1]))), T(1)) * a[0]; break;
+#endif
+#if AB_TIER_FULL
         case D_PP_HARD_BIN:
           acc = select_(le_(acc, a[0]), constant_like(acc, T(1)), constant_like(acc, T(0)));
           break;
+#endif
+#if AB_TIER_FULL
         case D_PP_LINEAR: acc = clamp_(T(1) - acc * s_rcp(a[1]), T(0), T(1)) * a[0]; break;
+#endif
+#if AB_TIER_FULL
         case D_PP_RELU: acc = max_(acc * s_rcp(a[0]), T(0)); break;
+#endif
+#if AB_TIER_FULL
         case D_PP_SMOOTH_RELU: {
           S v = acc * s_rcp(a[1]);
           acc = (v + sqrt_(fma_(v, v, constant_like(v, a[0])))) * T(0.5);
         } break;
+#endif
+#if AB_TIER_FULL
         case D_PP_SLOWSTART: {
           S v = max_(acc * s_rcp(a[0]), T(0));
           acc = sqrt_(fma_(v, v, constant_like(v, a[1]))) - a[2];
         } break;
+#endif
+#if AB_TIER_FULL
         case D_PP_GAUSS_BOUNDARY: {
           S v = acc * s_rcp(a[1]);
           acc = exp_(v * v * T(-4)) * a[0];
         } break;
+#endif
+#if AB_TIER_FULL
         case D_PP_GAUSS_FALLOFF: {
           S v = max_(acc, T(0)) * s_rcp(a[1]);
           acc = exp_(v * v * T(-4)) * a[0];
         } break;
+#endif
         // combine: acc = f(V[a], acc)
         case D_C_UNION: acc = min_(SK::ld(vstack, sa, NT), acc); break;
         case D_C_INTERSECT: acc = max_(SK::ld(vstack, sa, NT), acc); break;
@@ -439,44 +482,84 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
         case D_C_SMIN3: acc = smin_poly3(SK::ld(vstack, sa, NT), acc, a[0]); break;
         case D_C_SMAX3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), -acc, a[0]); break;
         case D_C_SSUB3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), acc, a[0]); break;
+#if AB_TIER_FULL
         case D_C_BOLTZ_INT: acc = smax_boltz(SK::ld(vstack, sa, NT), acc, a[0]); break;
+#endif
+#if AB_TIER_FULL
         case D_C_BOLTZ_SUB: acc = smax_boltz(SK::ld(vstack, sa, NT), -acc, a[0]); break;
+#endif
         // 3D primitives
         case D_P_SPHERE: acc = prim_sphere(p, a); break;
         case D_P_CYLINDER: acc = prim_cylinder(p, a); break;
         case D_P_BOX: acc = prim_box(p, a); break;
         case D_P_TORUS: acc = prim_torus(p, a); break;
         case D_P_CHAINLINK: acc = prim_chainlink(p, a); break;
+#if AB_TIER_FULL
         case D_P_BRAID: acc = prim_braid(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_ARC3D: acc = prim_arc3d(p, a); break;
+#endif
         case D_P_PLANE: acc = prim_plane(p, a); break;
         case D_P_UPLANE: acc = prim_uplane(p, a); break;
         case D_P_SEGMENT: acc = prim_segment(p, a); break;
+#if AB_TIER_FULL
         case D_P_CONE: acc = prim_cone(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_OINF_CONE: acc = prim_inf_cone(p, a, true); break;
+#endif
+#if AB_TIER_FULL
         case D_P_INF_CONE: acc = prim_inf_cone(p, a, false); break;
+#endif
+#if AB_TIER_FULL
         case D_P_SOLID_ANGLE: acc = prim_solid_angle(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_TRIANGLE3D: acc = prim_triangle3d(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_QUAD3D: acc = prim_quad3d(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_SEGLINE: acc = prim_segline(p, a, 3); break;
+#endif
         case D_P_AXIS:
           if (sa == 0) acc = p.x - a[0];
           else if (sa == 1) acc = p.y - a[0];
           else acc = p.z - a[0];
           break;
+#if AB_TIER_FULL
         case D_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[op.b], kp.blob_count[op.b], sa); break;
+#endif
         // 2D primitives
         case D_P_CIRCLE: acc = prim_circle(p, a); break;
+#if AB_TIER_FULL
         case D_P_NEU_CIRCLE: acc = prim_neu_circle(p, a); break;
+#endif
         case D_P_BOX2D: acc = prim_box2d(p, a); break;
         case D_P_SEGMENT2D: acc = prim_segment2d(p, a); break;
+#if AB_TIER_FULL
         case D_P_RBOX2D: acc = prim_rbox2d(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_TRIANGLE2D: acc = prim_triangle2d(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_ARC: acc = prim_arc(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_SECTOR: acc = prim_sector(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_INF_SECTOR: acc = prim_inf_sector(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_NGON: acc = prim_ngon(p, a); break;
+#endif
+#if AB_TIER_FULL
         case D_P_SEGLINE2D: acc = prim_segline(p, a, 2); break;
+#endif
         default: break;  // unknown opcodes are rejected on the host (AB_EUNSUPPORTED_OP)
       }
     }
@@ -491,11 +574,27 @@ struct LaunchCfg {
   size_t smem_optin;
 };
 // returns cudaSuccess or the CUDA error; *status is AB_OK / AB_ETOOLARGE
-template <typename S, typename T>
+template <typename S, typename T, int TIER>
 cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream_t st, int* status);
 
+inline bool is_lite_op(int ab_opcode) {
+  switch (ab_opcode) {
+    case AB_OP_END: case AB_OP_SAVE_P: case AB_OP_LOAD_P: case AB_OP_PUSH_V: case AB_OP_AFFINE: case AB_OP_TRANSLATE:
+    case AB_OP_SCALE_P: case AB_OP_ELONGATE: case AB_OP_ABSX_SUB: case AB_OP_SYMMETRY: case AB_OP_REVOLVE:
+    case AB_OP_REP_INF: case AB_OP_ZERO_Z: case AB_OP_ROUND: case AB_OP_ABS: case AB_OP_NEG: case AB_OP_SIGN:
+    case AB_OP_ONION: case AB_OP_CONCENTRIC: case AB_OP_SCALE_V: case AB_OP_EXTRUDE_BEGIN: case AB_OP_EXTRUDE_END:
+    case AB_OP_C_UNION: case AB_OP_C_INTERSECT: case AB_OP_C_SUBTRACT: case AB_OP_C_SUM: case AB_OP_C_DIFF:
+    case AB_OP_C_SMIN2: case AB_OP_C_SMIN3: case AB_OP_C_SMAX3: case AB_OP_C_SSUB3: case AB_OP_P_SPHERE:
+    case AB_OP_P_CYLINDER: case AB_OP_P_BOX: case AB_OP_P_TORUS: case AB_OP_P_CHAINLINK: case AB_OP_P_PLANE:
+    case AB_OP_P_UPLANE: case AB_OP_P_SEGMENT: case AB_OP_P_AXIS: case AB_OP_P_CIRCLE: case AB_OP_P_BOX2D:
+    case AB_OP_P_SEGMENT2D:
+      return true;
+    default: return false;
+  }
+}
+
 #ifdef AB_INTERP_INSTANTIATE
-template <typename S, typename T>
+template <typename S, typename T, int TIER>
 cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream_t st, int* status) {
   typedef StackOf<S> SK;
   *status = AB_OK;
@@ -510,7 +609,7 @@ cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream
     *status = AB_ETOOLARGE;
     return cudaSuccess;
   }
-  auto kern = ab_interp_kernel<S, T>;
+  auto kern = ab_interp_kernel<S, T, TIER>;
   cudaError_t e;
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,8 +1,9 @@
-// ab_interp_f32.cu — one instantiation of the SDF interpreter (kept in its own translation unit so the four
-// variants compile in parallel): S = Pack<float, 4>, argument pool of float.
+// ab_interp_f32.cu — one instantiation of the SDF interpreter (each variant sits in its own translation unit so
+// that they compile in parallel): S = Pack<float, 4>, argument pool of float, tier 1 (full op set).
 #define AB_INTERP_INSTANTIATE 1
+#define AB_TIER_FULL 1
 #include "ab_interp.cuh"
 
 namespace ab {
-template cudaError_t launch_interp<Pack<float, 4>, float>(const KParams<float>&, const LaunchCfg&, cudaStream_t, int*);
+template cudaError_t launch_interp<Pack<float, 4>, float, 1>(const KParams<float>&, const LaunchCfg&, cudaStream_t, int*);
 }
