@@ -251,7 +251,12 @@ static int dispatch_nt(const KParams<T>& kp, int device, cudaStream_t st) {
   if (rc) return rc;
   LaunchCfg cfg{di.sms, di.smem_optin};
   int status = AB_OK;
-  cudaError_t e = kp.tier == 0 ? launch_interp<S, T, 0>(kp, cfg, st, &status) : launch_interp<S, T, 1>(kp, cfg, st, &status);
+  cudaError_t e;
+  if (kp.tier == 0) e = launch_interp<S, T, 0>(kp, cfg, st, &status);
+  else if (kp.tier == 1) {
+    if constexpr (sizeof(T) == 4) e = launch_interp<S, T, 1>(kp, cfg, st, &status);
+    else e = launch_interp<S, T, 2>(kp, cfg, st, &status);  // fp64 has no mid-tier build
+  } else e = launch_interp<S, T, 2>(kp, cfg, st, &status);
   if (e != cudaSuccess) return fail(AB_ECUDA, "interpreter launch: %s", cudaGetErrorString(e));
   if (status != AB_OK) return fail(status, "interpreter stacks (%u P, %u V slots) do not fit in shared memory", kp.n_pslots, kp.n_vslots);
   g_launches++;
@@ -285,8 +290,10 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   kp.n_pslots = prog->n_pslots ? prog->n_pslots : 1;
   kp.n_vslots = prog->n_vslots ? prog->n_vslots : 1;
   kp.tier = 0;
-  for (uint32_t i = 0; i < kp.n_ops; i++)
-    if (!is_lite_op(prog->ops[i].opcode)) kp.tier = 1;
+  for (uint32_t i = 0; i < kp.n_ops; i++) {
+    const int t = op_tier(prog->ops[i].opcode);
+    if (t > kp.tier) kp.tier = t;
+  }
   // repack: every op's arguments start on a 16-byte boundary of the kernel's pool (vector loads from shared memory)
   uint32_t cursor = 0;
   for (uint32_t i = 0; i < kp.n_ops; i++) {

@@ -11,7 +11,7 @@
 // of ix planes, i.e. one contiguous range of k. Coordinates are regenerated from (ix,iy,iz): 0 bytes read per point.
 #pragma once
 #ifndef AB_TIER_FULL
-#define AB_TIER_FULL 1
+#define AB_TIER_FULL 2
 #endif
 #include "../../include/aegolius_b200.h"
 #include "ab_ops.cuh"
@@ -263,7 +263,9 @@ __host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((si
 // TIER 0 ("lite") contains only the ops without transcendental functions or tables (stack, affine family, elongate,
 // mirror core, symmetry, revolve, infinite repetition, the value ops, the polynomial combines and the sqrt-only
 // primitives): 40 registers instead of ~120, so 3x the resident warps, and a 23 KB body instead of 170 KB. The host
-// picks the smallest tier that covers the program (is_lite_op below). TIER 1 is the full interpreter.
+// picks the smallest tier that covers the program (op_tier below). TIER 1 adds every op with one transcendental or a
+// small table (twist, bend, rotational symmetry, instancing, Boltzmann combines, post-processing maps, cones, arcs,
+// n-gons ...) at 90 registers; TIER 2 adds the widest primitives (triangles, quads, sectors, polylines, point clouds).
 template <typename S, typename T, int TIER>
 __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
   static_assert(TIER == AB_TIER_FULL, "one tier per translation unit");
@@ -512,16 +514,16 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
 #if AB_TIER_FULL
         case D_P_INF_CONE: acc = prim_inf_cone(p, a, false); break;
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
         case D_P_SOLID_ANGLE: acc = prim_solid_angle(p, a); break;
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
         case D_P_TRIANGLE3D: acc = prim_triangle3d(p, a); break;
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
         case D_P_QUAD3D: acc = prim_quad3d(p, a); break;
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
         case D_P_SEGLINE: acc = prim_segline(p, a, 3); break;
 #endif
         case D_P_AXIS:
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
           else if (sa == 1) acc = p.y - a[0];
           else acc = p.z - a[0];
           break;
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
         case D_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[op.b], kp.blob_count[op.b], sa); break;
 #endif
         // 2D primitives
@@ -542,13 +544,13 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
 #if AB_TIER_FULL
         case D_P_RBOX2D: acc = prim_rbox2d(p, a); break;
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
         case D_P_TRIANGLE2D: acc = prim_triangle2d(p, a); break;
 #endif
 #if AB_TIER_FULL
         case D_P_ARC: acc = prim_arc(p, a); break;
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
         case D_P_SECTOR: acc = prim_sector(p, a); break;
 #endif
 #if AB_TIER_FULL
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(128) ab_interp_kernel(const __grid_constant__ 
 #if AB_TIER_FULL
         case D_P_NGON: acc = prim_ngon(p, a); break;
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
         case D_P_SEGLINE2D: acc = prim_segline(p, a, 2); break;
 #endif
         default: break;  // unknown opcodes are rejected on the host (AB_EUNSUPPORTED_OP)
@@ -577,6 +579,7 @@ struct LaunchCfg {
 template <typename S, typename T, int TIER>
 cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream_t st, int* status);
 
+inline int op_tier(int ab_opcode);
 inline bool is_lite_op(int ab_opcode) {
   switch (ab_opcode) {
     case AB_OP_END: case AB_OP_SAVE_P: case AB_OP_LOAD_P: case AB_OP_PUSH_V: case AB_OP_AFFINE: case AB_OP_TRANSLATE:
@@ -590,6 +593,16 @@ inline bool is_lite_op(int ab_opcode) {
     case AB_OP_P_SEGMENT2D:
       return true;
     default: return false;
+  }
+}
+
+inline int op_tier(int ab_opcode) {
+  if (is_lite_op(ab_opcode)) return 0;
+  switch (ab_opcode) {
+    case AB_OP_P_SOLID_ANGLE: case AB_OP_P_SECTOR: case AB_OP_P_TRIANGLE3D: case AB_OP_P_QUAD3D: case AB_OP_P_SEGLINE:
+    case AB_OP_P_SEGLINE2D: case AB_OP_P_POINT_CLOUD: case AB_OP_P_TRIANGLE2D:
+      return 2;
+    default: return 1;
   }
 }
 

@@ -1,0 +1,9 @@
+// ab_interp_f32_mid.cu — one instantiation of the SDF interpreter (each variant sits in its own translation unit so
+// that they compile in parallel): S = Pack<float, 4>, argument pool of float, tier 1 (mid op set: everything but the widest primitives).
+#define AB_INTERP_INSTANTIATE 1
+#define AB_TIER_FULL 1
+#include "ab_interp.cuh"
+
+namespace ab {
+template cudaError_t launch_interp<Pack<float, 4>, float, 1>(const KParams<float>&, const LaunchCfg&, cudaStream_t, int*);
+}
