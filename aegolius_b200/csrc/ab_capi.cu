@@ -113,7 +113,7 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
       double c = args[op.arg];
       if (!(c >= 0) || c > 1e6) return fail(AB_EINVAL, "bad element count %g", c);
       int per = op.opcode == AB_OP_CURVE_INST ? (op.a ? 12 : 3) : (op.opcode == AB_OP_P_SEGLINE ? 3 : 2);
-      n = 1 + (int)c * per;
+      n = (op.opcode == AB_OP_CURVE_INST ? 4 : 1) + (int)c * per;
     } break;
     default: return fail(AB_EUNSUPPORTED_OP, "opcode %u is not supported by this build", (unsigned)op.opcode);
   }

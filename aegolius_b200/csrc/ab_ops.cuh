@@ -90,10 +90,11 @@ AB_DEV void op_rotsym(Pt<S>& p, const T* a) {
   const int nsec = (int)a[2];
   const T inv = s_rcp(ang);
   auto vx = value_of(p.x), vy = value_of(p.y);
+  const Pack<T, W> ph = atan2_(vy, vx);
   Pack<T, W> c, s;
 #pragma unroll
   for (int i = 0; i < W; i++) {
-    T phi = s_atan2(vy.v[i], vx.v[i]);
+    T phi = ph.v[i];
     if (phi < T(0)) phi += T(6.283185307179586476925286766559);
     int k = (int)(phi * inv);
     k = k < 0 ? 0 : (k >= nsec ? nsec - 1 : k);
@@ -158,35 +159,77 @@ AB_DEV void op_lin_inst(Pt<S>& p, const T* a, int inner_on) {
   }
   p.x = v;
 }
-// modifications.py:1120-1127 / 1183-1191 / 1253-1261: nearest instance (exhaustive argmin replaces the KD-tree), then
+// modifications.py:1120-1127 / 1183-1191 / 1253-1261: nearest instance by position (the reference asks a KD-tree), then
 // subtract its position and, for the aligned variants, rotate into its frame. Record = pos(3) [+ rows dx,dy,dz (9)].
+//
+// Warp-cooperative exact search. A warp's 32*W points are spatially close (consecutive grid points), so the few instances
+// that can be nearest for ANY of them are found once per warp: lane l measures instance l (32 per round) from a warp
+// reference point C; with R = max distance of the warp's points from C, instance j can only win if
+// d(C, j) <= min_j d(C, j) + 2R (triangle inequality). Every thread then scans just that candidate list for its W points.
+// Cost ~ n/32 + (#candidates) per point instead of n; scattered point sets degrade gracefully to the full scan.
 template <typename S, typename T>
 AB_DEV void op_curve_inst(Pt<S>& p, const T* a, int mode) {
   const int n = (int)a[0];
   const int stride = mode ? 12 : 3;
-  const T* rec = a + 1;
+  const T* rec = a + 4;  // records start on a 16-byte boundary
   constexpr int W = S::width;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   auto vx = value_of(p.x), vy = value_of(p.y), vz = value_of(p.z);
-  T best[W];
+  const T Cx = __shfl_sync(FULL, vx.v[0], 0), Cy = __shfl_sync(FULL, vy.v[0], 0), Cz = __shfl_sync(FULL, vz.v[0], 0);
+  T r2 = T(0);
+#pragma unroll
+  for (int i = 0; i < W; i++) {
+    const T dx = vx.v[i] - Cx, dy = vy.v[i] - Cy, dz = vz.v[i] - Cz;
+    r2 = s_max(r2, s_fma(dx, dx, s_fma(dy, dy, dz * dz)));
+  }
+  T dmin = T(3.0e38);
+  for (int base = 0; base < n; base += 32) {
+    const int j = base + lane;
+    if (j < n) {
+      const T dx = Cx - rec[j * stride], dy = Cy - rec[j * stride + 1], dz = Cz - rec[j * stride + 2];
+      dmin = s_min(dmin, s_fma(dx, dx, s_fma(dy, dy, dz * dz)));
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    r2 = s_max(r2, __shfl_xor_sync(FULL, r2, off));
+    dmin = s_min(dmin, __shfl_xor_sync(FULL, dmin, off));
+  }
+  // widened a little against rounding: it only admits extra candidates, never drops the true nearest
+  const T reach = s_sqrt(dmin) * T(1.00001) + T(2.0001) * s_sqrt(r2) + T(1e-30);
+  const T cut = reach * reach;
+  T bst[W];
   int idx[W];
 #pragma unroll
   for (int i = 0; i < W; i++) {
-    best[i] = T(3.0e38);
+    bst[i] = T(3.0e38);
     idx[i] = 0;
   }
-  for (int j = 0; j < n; j++) {
-    const T cx = rec[j * stride], cy = rec[j * stride + 1], cz = rec[j * stride + 2];
-    const Pack<T, W> dx = vx - cx, dy = vy - cy, dz = vz - cz;  // packed f32x2 lanes
-    const Pack<T, W> d2 = fma_(dx, dx, fma_(dy, dy, dz * dz));
+  for (int base = 0; base < n; base += 32) {
+    const int jl = base + lane;
+    bool in = false;
+    if (jl < n) {
+      const T dx = Cx - rec[jl * stride], dy = Cy - rec[jl * stride + 1], dz = Cz - rec[jl * stride + 2];
+      in = s_fma(dx, dx, s_fma(dy, dy, dz * dz)) <= cut;
+    }
+    unsigned m = __ballot_sync(FULL, in);
+    while (m) {  // warp-uniform loop over the candidates, in index order (ties resolve to the lowest index)
+      const int j = base + __ffs(m) - 1;
+      m &= m - 1;
+      const T qx = rec[j * stride], qy = rec[j * stride + 1], qz = rec[j * stride + 2];
+      const Pack<T, W> dx = vx - qx, dy = vy - qy, dz = vz - qz;  // packed f32x2 lanes
+      const Pack<T, W> d2 = fma_(dx, dx, fma_(dy, dy, dz * dz));
 #pragma unroll
-    for (int i = 0; i < W; i++) {
-      if (d2.v[i] < best[i]) {
-        best[i] = d2.v[i];
-        idx[i] = j;
+      for (int i = 0; i < W; i++) {
+        if (d2.v[i] < bst[i]) {
+          bst[i] = d2.v[i];
+          idx[i] = j;
+        }
       }
     }
   }
-  // gather the chosen record per lane (divergent constant reads: a handful per point, off the critical path)
+  // gather the chosen record per lane
   Pack<T, W> r[12];
 #pragma unroll
   for (int i = 0; i < W; i++) {

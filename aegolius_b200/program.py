@@ -407,7 +407,7 @@ class _Builder:
             mode = 1
         if not np.all(np.isfinite(rec)):
             raise ValueError(f"{name}: the curve frame contains NaN/inf (degenerate tangent or normal)")
-        self.emit(oc.CURVE_INST, a=mode, args=[float(n)] + list(rec))
+        self.emit(oc.CURVE_INST, a=mode, args=[float(n), 0.0, 0.0, 0.0] + list(rec))  # 4-entry header: 16-byte aligned records
 
     # ---- leaves --------------------------------------------------------------------------------------------
     def leaf(self, name, params):
@@ -589,7 +589,7 @@ def _peephole(ops, args):
             if code == oc.ROTSYM:
                 n = 4 + 2 * int(args[off + 2])
             elif code == oc.CURVE_INST:
-                n = 1 + cnt * (12 if a == 1 else 3)
+                n = 4 + cnt * (12 if a == 1 else 3)
             elif code == oc.P_SEGLINE:
                 n = 1 + cnt * 3
             elif code == oc.P_SEGLINE2D:

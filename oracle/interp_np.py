@@ -202,7 +202,7 @@ def run(prog, co, return_state=False, return_margin=False):
             elif code == CURVE_INST:  # modifications.py:1120-1127, 1183-1191, 1253-1261 (nearest instance)
                 n = int(A[o])
                 stride = 12 if a == 1 else 3
-                rec = A[o + 1:o + 1 + n * stride].reshape(n, stride)
+                rec = A[o + 4:o + 4 + n * stride].reshape(n, stride)
                 best = np.full(x.shape, np.inf)
                 second = np.full(x.shape, np.inf)
                 idx = np.zeros(x.shape, dtype=np.int64)
