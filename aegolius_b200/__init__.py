@@ -10,6 +10,7 @@ from .frontend import *  # noqa: F401,F403
 from .frontend import LEAVES, LeafSDF, GenericGeometry, CombineGeometry  # noqa: F401
 from .program import Program, flatten, FlattenError  # noqa: F401
 from .introspect import to_frontend  # noqa: F401
+from . import workloads  # noqa: F401
 
 
 def __getattr__(name):

@@ -437,6 +437,30 @@ static int scratch(int device, int which, size_t bytes, void** out) {
 
 static int grad_rows(int grad_mode) { return grad_mode == AB_GRAD_SPATIAL ? 3 : (grad_mode == AB_GRAD_PARAM ? 1 : 0); }
 
+// Pipelined host variant: the slab is cut into chunks of whole planes; chunk i+1 is evaluated on the compute stream
+// while chunk i travels device->host on the copy stream (double-buffered scratch, events in both directions), so the
+// PCIe copy, which dominates end to end, is the only thing left on the critical path.
+struct Pipe {
+  cudaStream_t comp = nullptr, copy = nullptr;
+  cudaEvent_t done[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+static Pipe g_pipe[64];
+static int pipe_for(int device, Pipe** out) {
+  Pipe& p = g_pipe[device];
+  if (!p.ok) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.comp, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CUDA_TRY(cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&p.freed[i], cudaEventDisableTiming));
+    }
+    p.ok = true;
+  }
+  *out = &p;
+  return AB_OK;
+}
+
 extern "C" int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out_host,
                                  void* out_grad_host, uint64_t grad_stride, int device) {
   int rc = use_device(device);
@@ -451,21 +475,51 @@ extern "C" int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, in
   const size_t es = dtype == AB_F32 ? 4 : 8;
   const int rows = grad_rows(grad_mode);
   if (rows && (!out_grad_host || grad_stride < n)) return fail(AB_EINVAL, "gradient output missing or grad_stride < n");
-  const uint64_t dstride = (n + 3) & ~3ull;
-  void *d_out = nullptr, *d_grad = nullptr;
-  rc = scratch(device, 0, n * es, &d_out);
+  Pipe* pp = nullptr;
+  rc = pipe_for(device, &pp);
   if (rc) return rc;
-  if (rows) {
-    rc = scratch(device, 1, dstride * rows * es, &d_grad);
-    if (rc) return rc;
+  // chunk = whole planes, about 128 MB of output each (at least one plane, at most the slab)
+  const uint64_t plane = g.plane;
+  const uint64_t bytes_per_plane = plane * es * (1 + rows);
+  uint64_t planes_per_chunk = (128ull << 20) / (bytes_per_plane ? bytes_per_plane : 1);
+  if (planes_per_chunk < 1) planes_per_chunk = 1;
+  const uint64_t total_planes = grid->slab_end - grid->slab_begin;
+  if (planes_per_chunk > total_planes) planes_per_chunk = total_planes;
+  const uint64_t chunk_pts = planes_per_chunk * plane;
+  const uint64_t dstride = (chunk_pts + 3) & ~3ull;
+  void* d_out[2] = {nullptr, nullptr};
+  void* d_grad[2] = {nullptr, nullptr};
+  void* base = nullptr;
+  const size_t per_buf = (size_t)dstride * es * (1 + rows);
+  rc = scratch(device, 0, per_buf * 2, &base);
+  if (rc) return rc;
+  for (int b = 0; b < 2; b++) {
+    d_out[b] = (char*)base + b * per_buf;
+    d_grad[b] = rows ? (char*)d_out[b] + (size_t)dstride * es : nullptr;
   }
-  rc = ab_eval_grid(prog, grid, dtype, grad_mode, d_out, d_grad, dstride, device, nullptr);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(out_host, d_out, n * es, cudaMemcpyDeviceToHost, 0));
-  for (int r = 0; r < rows; r++)
-    CUDA_TRY(cudaMemcpyAsync((char*)out_grad_host + (size_t)r * grad_stride * es, (char*)d_grad + (size_t)r * dstride * es,
-                             n * es, cudaMemcpyDeviceToHost, 0));
-  CUDA_TRY(cudaStreamSynchronize(0));
+  uint64_t done_planes = 0;
+  int c = 0;
+  while (done_planes < total_planes) {
+    const uint64_t np = (total_planes - done_planes < planes_per_chunk) ? total_planes - done_planes : planes_per_chunk;
+    const uint64_t pts = np * plane, off = done_planes * plane;
+    const int b = c & 1;
+    ab_grid sub = *grid;
+    sub.slab_begin = grid->slab_begin + (uint32_t)done_planes;
+    sub.slab_end = sub.slab_begin + (uint32_t)np;
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(pp->comp, pp->freed[b], 0));
+    rc = ab_eval_grid(prog, &sub, dtype, grad_mode, d_out[b], d_grad[b], dstride, device, pp->comp);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(pp->done[b], pp->comp));
+    CUDA_TRY(cudaStreamWaitEvent(pp->copy, pp->done[b], 0));
+    CUDA_TRY(cudaMemcpyAsync((char*)out_host + off * es, d_out[b], pts * es, cudaMemcpyDeviceToHost, pp->copy));
+    for (int r = 0; r < rows; r++)
+      CUDA_TRY(cudaMemcpyAsync((char*)out_grad_host + ((size_t)r * grad_stride + off) * es,
+                               (char*)d_grad[b] + (size_t)r * dstride * es, pts * es, cudaMemcpyDeviceToHost, pp->copy));
+    CUDA_TRY(cudaEventRecord(pp->freed[b], pp->copy));
+    done_planes += np;
+    c++;
+  }
+  CUDA_TRY(cudaStreamSynchronize(pp->copy));
   return AB_OK;
 }
 

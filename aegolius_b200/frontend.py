@@ -58,6 +58,16 @@ def rotation_matrix_from_rotvec(rotvec) -> np.ndarray:
     return np.eye(3) + np.sin(theta) * K + (1.0 - np.cos(theta)) * (K @ K)
 
 
+def _rotvec_matrix(rotvec):
+    """The reference calls scipy's Rotation.from_rotvec (transformations.py:160); use the same routine when scipy is
+    importable so that rotation matrices are bit-identical to SPOMSO's, else the Rodrigues form (<= 2e-16 apart)."""
+    try:
+        from scipy.spatial.transform import Rotation
+        return Rotation.from_rotvec(np.asarray(rotvec, dtype=np.float64)).as_matrix()
+    except ImportError:  # pragma: no cover
+        return rotation_matrix_from_rotvec(rotvec)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Euclidean state (transformations.py:12-264)
 
@@ -125,7 +135,7 @@ class EuclideanTransform:
             raise SyntaxError(f"Array {axis} is of incorrect size!")
         if not isinstance(angle, (float, int)):
             raise TypeError("Rotation angle must be a float or an int")
-        return rotation_matrix_from_rotvec(angle * axis_), angle, axis_
+        return _rotvec_matrix(angle * axis_), angle, axis_
 
     def set_rotation(self, angle, axis):
         # NB: like transformations.py:163-173 the axis is NOT normalised here
@@ -426,14 +436,16 @@ class CombineGeometry:
 
     def combine(self, *combined_objects):
         if self.operation_type not in self.OPERATIONS:
-            raise SyntaxError(f"{self.operation_type} is not an implemented non-parametric operation.",
+            # the reference builds SyntaxError(msg, str) (combine.py:125-127), which CPython >= 3.10 turns into a
+            # TypeError about the malformed details tuple; the intended SyntaxError is raised here
+            raise SyntaxError(f"{self.operation_type} is not an implemented non-parametric operation. "
                               f"Possible operations are {self.OPERATIONS}")
         self._combined_geometry = _CombineDescriptor(self.operation_type, combined_objects, None)
         return GenericGeometry(self._combined_geometry, ())
 
     def combine_parametric(self, *combined_objects, parameters):
         if self.operation_type not in self.PARAMETRIC_OPERATIONS:
-            raise SyntaxError(f"{self.operation_type} is not an implemented parametric operation.",
+            raise SyntaxError(f"{self.operation_type} is not an implemented parametric operation. "
                               f"Possible parametric operations are {self.PARAMETRIC_OPERATIONS}")
         self._combined_geometry = _CombineDescriptor(self.operation_type, combined_objects, parameters)
         return GenericGeometry(self._combined_geometry, ())

@@ -1,0 +1,165 @@
+"""Host logic without a GPU: the SPOMSO-mirroring front end, the flattener and grid helpers."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import aegolius_b200 as ab
+from aegolius_b200 import opcodes as oc
+from oracle import interp_np
+from scenarios import SCENARIOS, make_namespace
+
+REF = os.path.isdir("/root/reference/Code/spomso")
+if REF and "/root/reference/Code/spomso" not in sys.path:
+    sys.path.insert(0, "/root/reference/Code/spomso")
+
+
+def test_rodrigues_matches_scipy_rotation():
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        v = rng.normal(size=3) * rng.uniform(0, 3)
+        assert np.allclose(ab.frontend.rotation_matrix_from_rotvec(v), Rotation.from_rotvec(v).as_matrix(), atol=1e-15)
+    assert np.array_equal(ab.frontend.rotation_matrix_from_rotvec(np.zeros(3)), np.eye(3))
+
+
+def test_transform_state_follows_the_reference_rules():
+    s = ab.Sphere(1.0)
+    s.move((1, 2, 3))
+    s.move((1, 0, 0))
+    assert np.array_equal(s.center, (2, 2, 3))
+    s.move(0.5)  # scalar broadcasts, as `self._center += vector` does in transformations.py:104
+    assert np.array_equal(s.center, (2.5, 2.5, 3.5))
+    with pytest.raises(ValueError):
+        s.move((1, 2))  # a 2-vector cannot be added to the 3-vector (same failure as the reference)
+    s.set_location((7, 8))
+    assert np.array_equal(s.center, (7, 8, 3.5))
+    s.rescale(2)
+    s.rescale(1.5)
+    assert s.scale == 3.0
+    with pytest.raises(TypeError):
+        s.rescale("2")
+    with pytest.raises(SyntaxError):
+        s.move((1, 2, 3, 4))
+    s.rotate(np.pi / 2, (0, 0, 2))   # rotate() normalises the axis ...
+    r1 = s.rotation_matrix.copy()
+    s.set_rotation(np.pi / 2, (0, 0, 2))  # ... set_rotation() does not (transformations.py:163-173): angle * |axis|
+    assert np.allclose(r1 @ np.array([1, 0, 0]), (0, 1, 0))
+    assert np.allclose(s.rotation_matrix @ np.array([1, 0, 0]), (-1, 0, 0))
+    with pytest.raises(ValueError):
+        s.rotate(0.3, (0, 0, 0))
+    a = ab.Box(1, 1, 1)
+    a.rotate(0.3, (1, 0, 0))
+    a.rotate(0.4, (0, 1, 0))  # accumulates by LEFT multiplication
+    ra = ab.frontend.rotation_matrix_from_rotvec
+    assert np.allclose(a.rotation_matrix, ra((0, 0.4, 0)) @ ra((0.3, 0, 0)))
+
+
+def test_combine_api_errors_match_the_reference():
+    with pytest.raises(SyntaxError):
+        ab.CombineGeometry("NOPE").combine(ab.Sphere(1), ab.Sphere(2))
+    with pytest.raises(SyntaxError):
+        ab.CombineGeometry("UNION2").combine_parametric(ab.Sphere(1), ab.Sphere(2), parameters=0.1)
+    with pytest.raises(TypeError):  # the reference's 2-argument lambda raises TypeError at create()
+        ab.flatten(ab.CombineGeometry("UNION2").combine(ab.Sphere(1), ab.Sphere(2), ab.Sphere(3)))
+    u = ab.CombineGeometry("UNION").combine(ab.Sphere(1), ab.Sphere(2), ab.Sphere(3))
+    assert [int(o["opcode"]) for o in ab.flatten(u).ops].count(oc.C_UNION) == 2
+
+
+def test_unflattenable_trees_raise_not_implemented_naming_the_culprit():
+    s = ab.Sphere(1.0)
+    for name in ("custom_modification", "displacement", "define_volume", "signed", "conv_averaging"):
+        with pytest.raises(NotImplementedError, match=name):
+            getattr(s, name)(lambda *a: 0, ())
+    with pytest.raises(NotImplementedError):
+        ab.GenericGeometry(lambda co: co[0])
+
+
+def test_late_binding_of_children_like_the_reference_closures():
+    a, b = ab.Sphere(0.5), ab.Box(1, 1, 1)
+    u = ab.CombineGeometry("UNION2").combine(a, b)
+    p0 = ab.flatten(u)
+    a.move((1, 0, 0))  # mutated AFTER combine(): seen at create() time (combine.py:129-135 is late-bound)
+    p1 = ab.flatten(u)
+    assert not np.array_equal(p0.args, p1.args)
+
+
+def test_program_evaluation_order_and_slot_sharing():
+    u = ab.workloads.build_c1()
+    names = [oc.NAMES[int(o["opcode"])] for o in ab.flatten(u).ops]
+    assert names == ["SAVE_P", "TRANSLATE", "P_SPHERE", "PUSH_V", "LOAD_P", "AFFINE", "P_BOX", "C_SMIN3", "END"]
+    # last-called modification is the outermost wrapper: coordinate parts run in reverse call order
+    b = ab.Box(1, 1, 1)
+    b.rounding(0.1)
+    b.elongation((0.2, 0, 0))
+    b.twist(1.0)
+    names = [oc.NAMES[int(o["opcode"])] for o in ab.flatten(b).ops]
+    assert names == ["TWIST", "ELONGATE", "P_BOX", "ROUND", "END"]
+    # a left-deep chain of identity-transform combines shares ONE saved-coordinate slot
+    c2 = ab.flatten(ab.workloads.build_c2())
+    assert c2.n_pslots == 1 and c2.n_ops > 100
+
+
+def test_peephole_composes_affine_runs():
+    s = ab.Sphere(1.0)
+    s.move_sdf((1, 0, 0))
+    s.rotate_sdf(ab.frontend.rotation_matrix_from_rotvec((0, 0, 0.3)))
+    s.shear_xz(0.2)
+    s.rotate(0.5, (0, 1, 0))
+    s.rescale(1.5)
+    s.move((0.1, 0.2, 0.3))
+    raw = ab.flatten(s, optimize=False)
+    opt = ab.flatten(s, optimize=True)
+    assert raw.n_ops > opt.n_ops and [oc.NAMES[int(o["opcode"])] for o in opt.ops] == ["AFFINE", "P_SPHERE", "SCALE_V", "END"]
+    co = np.random.default_rng(3).uniform(-2, 2, size=(3, 500))
+    assert np.max(np.abs(interp_np.run(raw, co) - interp_np.run(opt, co))) < 1e-13
+
+
+def test_generate_grid_matches_reference_layout_and_detection():
+    co, res = ab.generate_grid((4, 2, 6), (8, 5, 6))
+    assert res == (9, 5, 7) and co.shape == (3, 9 * 5 * 7) and co.dtype == np.float64
+    assert np.array_equal(co[2, :7], np.linspace(-3, 3, 7))           # z is the fastest axis
+    assert np.array_equal(co[0, ::5 * 7], np.linspace(-2, 2, 9))      # x the slowest
+    spec = ab.detect_grid(np.array(co))
+    assert spec is not None and spec.res == (9, 5, 7) and spec.size == (4.0, 2.0, 6.0)
+    co2, res2 = ab.generate_grid((8, 8), (16, 12))
+    assert res2 == (17, 13, 17) and co2.shape == (3, 17 * 13) and not co2[2].any()
+    spec2 = ab.detect_grid(np.array(co2))
+    assert spec2 is not None and spec2.res == (17, 13, 1) and spec2.dims == 2
+    assert ab.detect_grid(np.random.default_rng(0).normal(size=(3, 100))) is None
+    assert ab.detect_grid(np.array(co)[:, ::-1].copy()) is None
+    assert ab.smarter_reshape(np.zeros(9 * 5 * 7), (8, 5, 6)).shape == (9, 5, 7)
+    with pytest.raises(IndexError):
+        ab.generate_grid((4,), (8,))
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_introspected_spomso_objects_flatten_like_the_mirror_front_end(name):
+    """The same construction code run against real SPOMSO classes (flattened by closure introspection) and against the
+    mirror front end must give the identical program."""
+    sc = SCENARIOS[name]
+    p_ref = ab.flatten(sc["build"](make_namespace("reference")))
+    p_own = ab.flatten(sc["build"](make_namespace("frontend")))
+    assert np.array_equal(p_ref.ops, p_own.ops)
+    assert np.array_equal(p_ref.args, p_own.args)
+    assert (p_ref.n_pslots, p_ref.n_vslots) == (p_own.n_pslots, p_own.n_vslots)
+
+
+@pytest.mark.reference
+def test_generate_grid_is_bit_identical_to_spomso():
+    from spomso.cores.helper_functions import generate_grid
+    for size, res in (((4, 4, 4), (16, 12, 20)), ((8, 8), (64, 48)), ((2.5, 2.5, 1.5), (7, 9, 5))):
+        a, ra = ab.generate_grid(size, res)
+        b, rb = generate_grid(size, res)
+        assert ra == rb and np.array_equal(np.asarray(a), b)
+
+
+@pytest.mark.reference
+def test_introspection_rejects_custom_closures_by_name():
+    ns = make_namespace("reference")
+    s = ns.Sphere(1.0)
+    s.custom_modification(lambda f, co, p, mp: f(co, *p), (), "wobble")
+    with pytest.raises(NotImplementedError, match="custom_modification"):
+        ab.flatten(s)
