@@ -73,14 +73,50 @@ AB_DEV float s_abs(float a) { return fabsf(a); }
 AB_DEV double s_abs(double a) { return fabs(a); }
 AB_DEV float s_floor(float a) { return floorf(a); }
 AB_DEV double s_floor(double a) { return floor(a); }
-AB_DEV void s_sincos(float a, float& s, float& c) { sincosf(a, &s, &c); }
-AB_DEV void s_sincos(double a, double& s, double& c) { sincos(a, &s, &c); }
-AB_DEV float s_atan2(float y, float x) { return atan2f(y, x); }
-AB_DEV double s_atan2(double y, double x) { return atan2(y, x); }
-AB_DEV float s_exp(float a) { return expf(a); }
-AB_DEV double s_exp(double a) { return exp(a); }
-AB_DEV float s_pow(float a, float b) { return powf(a, b); }
-AB_DEV double s_pow(double a, double b) { return pow(a, b); }
+// The big libm bodies (sincos with its Payne-Hanek slow path, atan2, exp, pow) are deliberately NOT inlined: inlined
+// W times at every call site they made the executed path of a deep tree larger than the instruction cache
+// ("no_instructions" was the top stall of the C5 kernel, profiles/r01_c5_dual_kernel_ncu_summary.json). One shared copy
+// per kernel, results returned in registers.
+#ifndef AB_OUTLINE_LIBM
+#define AB_OUTLINE_LIBM 1
+#endif
+#if AB_OUTLINE_LIBM
+#define AB_LIBM static __device__ __noinline__
+#else
+#define AB_LIBM static __device__ __forceinline__
+#endif
+AB_LIBM float2 ab_sincosf(float a) {
+  float2 r;
+  sincosf(a, &r.x, &r.y);
+  return r;
+}
+AB_LIBM double2 ab_sincos(double a) {
+  double2 r;
+  sincos(a, &r.x, &r.y);
+  return r;
+}
+AB_LIBM float ab_atan2f(float y, float x) { return atan2f(y, x); }
+AB_LIBM double ab_atan2(double y, double x) { return atan2(y, x); }
+AB_LIBM float ab_expf(float a) { return expf(a); }
+AB_LIBM double ab_exp(double a) { return exp(a); }
+AB_LIBM float ab_powf(float a, float b) { return powf(a, b); }
+AB_LIBM double ab_pow(double a, double b) { return pow(a, b); }
+AB_DEV void s_sincos(float a, float& s, float& c) {
+  const float2 r = ab_sincosf(a);
+  s = r.x;
+  c = r.y;
+}
+AB_DEV void s_sincos(double a, double& s, double& c) {
+  const double2 r = ab_sincos(a);
+  s = r.x;
+  c = r.y;
+}
+AB_DEV float s_atan2(float y, float x) { return ab_atan2f(y, x); }
+AB_DEV double s_atan2(double y, double x) { return ab_atan2(y, x); }
+AB_DEV float s_exp(float a) { return ab_expf(a); }
+AB_DEV double s_exp(double a) { return ab_exp(a); }
+AB_DEV float s_pow(float a, float b) { return ab_powf(a, b); }
+AB_DEV double s_pow(double a, double b) { return ab_pow(a, b); }
 AB_DEV float s_log(float a) { return logf(a); }
 AB_DEV double s_log(double a) { return log(a); }
 
@@ -270,7 +306,7 @@ template <int W>
 AB_DEV Pack<double, W> atan2_(const Pack<double, W>& y, const Pack<double, W>& x) {
   Pack<double, W> r;
 #pragma unroll
-  AB_PACK_LOOP r.v[i] = atan2(y.v[i], x.v[i]);
+  AB_PACK_LOOP r.v[i] = s_atan2(y.v[i], x.v[i]);
   return r;
 }
 template <int W>
@@ -303,7 +339,7 @@ AB_DEV Pack<float, W> atan2_(const Pack<float, W>& y, const Pack<float, W>& x) {
 #else
   Pack<float, W> r;
 #pragma unroll
-  AB_PACK_LOOP r.v[i] = atan2f(y.v[i], x.v[i]);
+  AB_PACK_LOOP r.v[i] = s_atan2(y.v[i], x.v[i]);
   return r;
 #endif
 }
