@@ -297,13 +297,12 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   // repack: every op's arguments start on a 16-byte boundary of the kernel's pool (vector loads from shared memory)
   uint32_t cursor = 0;
   for (uint32_t i = 0; i < kp.n_ops; i++) {
-    kp.ops[i] = prog->ops[i];
-    kp.ops[i].opcode = (uint16_t)dense_opcode(prog->ops[i].opcode);  // validated above
+    const uint32_t dense = (uint32_t)dense_opcode(prog->ops[i].opcode);  // validated above
     int cnt = 0;
     op_arg_count(prog->ops[i], prog->args, prog->n_args, &cnt);
     if (cursor + (uint32_t)cnt + 4 > AB_MAX_ARGS)
       return fail(AB_ETOOLARGE, "program arguments exceed %d after alignment", AB_MAX_ARGS);
-    kp.ops[i].arg = cursor;
+    kp.ops[i] = make_uint2(dense, cursor | ((uint32_t)prog->ops[i].a << 16) | ((uint32_t)prog->ops[i].b << 24));
     for (int k = 0; k < cnt; k++) kp.args[cursor + k] = (T)prog->args[prog->ops[i].arg + k];
     cursor = (cursor + (uint32_t)cnt + 3u) & ~3u;
   }

@@ -13,6 +13,9 @@
 #ifndef AB_TIER_FULL
 #define AB_TIER_FULL 2
 #endif
+#ifndef AB_DISPATCH_BRX
+#define AB_DISPATCH_BRX 0 /* 1 = indexed-branch dispatch, 0 = uniform compare tree (faster on B200, see the dispatch comment) */
+#endif
 #include "../../include/aegolius_b200.h"
 #include "ab_ops.cuh"
 
@@ -92,10 +95,11 @@ struct KParams {
   GridK g;
   uint32_t tile_stride[3];  // (d0, d1, d2): decomposition of gridDim.x * tile points, filled in by the launcher
   uint32_t n_ops, n_args, n_pslots, n_vslots;
+  uint32_t off_args, off_pstack, off_vstack;  // byte offsets inside dynamic shared memory (filled in by the launcher)
   int32_t tier;  // 0 = every op is in the lite set (host-side choice of kernel variant)
   const void* blob[AB_MAX_BLOBS];  // (x, y, z, 0) records of T
   uint32_t blob_count[AB_MAX_BLOBS];
-  ab_op ops[AB_MAX_OPS];
+  uint2 ops[AB_MAX_OPS];  // kernel-side encoding: x = dense opcode (a full word), y = argument offset | a << 16 | b << 24
   T args[AB_MAX_ARGS];
 };
 
@@ -255,7 +259,7 @@ AB_DEV S prim_point_cloud(const Pt<S>& p, const void* __restrict__ cloud_v, uint
   return norm2_(dx, dy);
 }
 
-__host__ __device__ inline size_t prog_ops_bytes(uint32_t n_ops) { return ((size_t)n_ops * sizeof(ab_op) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t prog_ops_bytes(uint32_t n_ops) { return ((size_t)n_ops * sizeof(uint2) + 15) & ~(size_t)15; }
 template <typename T>
 __host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((size_t)n_args * sizeof(T) + 15) & ~(size_t)15; }
 
@@ -277,10 +281,10 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_i
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // shared memory: [ops][args][P stack][V stack]. The program is staged once per (persistent) CTA; afterwards every op
   // fetch is one broadcast LDS.64 and its arguments come in with 128-bit broadcast loads.
-  ab_op* s_ops = reinterpret_cast<ab_op*>(smem_raw);
-  T* s_args = reinterpret_cast<T*>(smem_raw + prog_ops_bytes(kp.n_ops));
-  P* pstack = reinterpret_cast<P*>(smem_raw + prog_ops_bytes(kp.n_ops) + prog_args_bytes<T>(kp.n_args));
-  P* vstack = pstack + (size_t)kp.n_pslots * 3 * SK::cols * NT;       // [n_vslots*cols][NT]
+  uint2* s_ops = reinterpret_cast<uint2*>(smem_raw);
+  T* s_args = reinterpret_cast<T*>(smem_raw + kp.off_args);
+  P* pstack = reinterpret_cast<P*>(smem_raw + kp.off_pstack);  // [n_pslots*3*cols][NT]
+  P* vstack = reinterpret_cast<P*>(smem_raw + kp.off_vstack);  // [n_vslots*cols][NT]
   for (uint32_t i = threadIdx.x; i < kp.n_ops; i += NT) s_ops[i] = kp.ops[i];
   for (uint32_t i = threadIdx.x; i < kp.n_args; i += NT) s_args[i] = kp.args[i];
   __syncthreads();
@@ -364,10 +368,15 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_i
     S acc = constant_like(p.x, T(0));
 
     for (uint32_t pc = 0; pc < kp.n_ops; pc++) {
-      const ab_op op = s_ops[pc];
-      const T* a = reinterpret_cast<const T*>(__builtin_assume_aligned(s_args + op.arg, 16));
-      const int sa = op.a;
-      switch (op.opcode) {
+      // one 64-bit broadcast load per op. Dispatch: with an unmasked 32-bit switch variable nvcc emits one indexed
+      // branch (LDC of the table entry + BRX); with a value it can narrow to 8/16 bits it emits a ~7-level tree of
+      // uniform compares and branches. Measured on B200 (profiles/r01_sweeps.md) the tree is FASTER here (C1: 254 vs
+      // 228 Gpts/s): the indexed branch waits on a dependent constant load and resolves late, the uniform tree does not.
+      const uint2 w = s_ops[pc];
+      const uint32_t code = AB_DISPATCH_BRX ? w.x : (w.x & 0xffu);
+      const int sa = (int)((w.y >> 16) & 0xffu), sb = (int)(w.y >> 24);
+      const T* a = reinterpret_cast<const T*>(__builtin_assume_aligned(s_args + (w.y & 0xffffu), 16));
+      switch (code) {
         case D_END: break;
         case D_SAVE_P:
           SK::st(pstack, sa * 3 + 0, NT, p.x);
@@ -533,7 +542,7 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_i
           else acc = p.z - a[0];
           break;
 #if AB_TIER_FULL >= 2
-        case D_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[op.b], kp.blob_count[op.b], sa); break;
+        case D_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[sb], kp.blob_count[sb], sa); break;
 #endif
         // 2D primitives
         case D_P_CIRCLE: acc = prim_circle(p, a); break;
@@ -641,6 +650,9 @@ cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream
   const uint64_t resident = (uint64_t)cfg.sms * occ;  // persistent CTAs: a whole number of resident waves
   const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
   KParams<T>& k = const_cast<KParams<T>&>(kp);
+  k.off_args = (uint32_t)prog_ops_bytes(kp.n_ops);
+  k.off_pstack = (uint32_t)prog_bytes;
+  k.off_vstack = (uint32_t)(prog_bytes + (size_t)sizeof(typename SK::P) * SK::cols * kp.n_pslots * 3 * nt);
   if (kp.grid_mode) {
     const uint64_t d = (uint64_t)grid * tile_pts;
     k.tile_stride[0] = (uint32_t)(d / kp.g.plane);
