@@ -564,7 +564,9 @@ static int launch_nn(const NNParams<T>& kp, int device, cudaStream_t st) {
   int rc = dev_info(device, di);
   if (rc) return rc;
   constexpr int NT = 256;
-  auto kern = ab_nn_kernel<T, Q, NT, TILE>;
+  void (*kern)(NNParams<T>);
+  if constexpr (sizeof(T) == 4) kern = ab_nn_kernel_f32x2<Q, NT, TILE>;
+  else kern = ab_nn_kernel<T, Q, NT, TILE>;
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, 0));
   if (occ < 1) occ = 1;
@@ -596,7 +598,7 @@ static int nn_t(const void* cloud, uint64_t m, int dim, int grid_mode, const Gri
   kp.co = co;
   kp.co_stride = co_stride;
   kp.co_is_f64 = co_dtype == AB_F64;
-  if constexpr (sizeof(T) == 4) return launch_nn<T, 8, 1024>(kp, device, st);
+  if constexpr (sizeof(T) == 4) return launch_nn<T, 8, 512>(kp, device, st);
   else return launch_nn<T, 4, 512>(kp, device, st);
 }
 

@@ -107,6 +107,114 @@ __global__ void __launch_bounds__(NT) ab_nn_kernel(const __grid_constant__ NNPar
   }
 }
 
+// fp32 fast path. Two queries share every FADD2/FMUL2/FFMA2 (f32x2) and two cloud points share every FMNMX3, so one
+// (query, point) pair costs 3.5 issue slots instead of 7: (3 FADD2 + FMUL2 + 2 FFMA2) per point per query pair, plus one
+// 3-input min per query per two points. Tiles are staged already negated and duplicated, (-x,-x,-y,-y) + (-z,-z), so the
+// packed adds take them straight from a broadcast LDS.128 + LDS.64 with no register shuffling.
+AB_DEV float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+template <int Q, int NT, int NN_TILE>
+__global__ void __launch_bounds__(NT) ab_nn_kernel_f32x2(const __grid_constant__ NNParams<float> kp) {
+  static_assert(Q % 2 == 0 && NN_TILE % 2 == 0, "pairs");
+  __shared__ float4 sxy[2][NN_TILE];
+  __shared__ float2 sz[2][NN_TILE];
+  const uint64_t tile_pts = (uint64_t)NT * Q;
+  const uint64_t n_tiles = (kp.n + tile_pts - 1) / tile_pts;
+  for (uint64_t qt = blockIdx.x; qt < n_tiles; qt += gridDim.x) {
+    const uint64_t idx = qt * tile_pts + (uint64_t)threadIdx.x * Q;
+    float2 qx[Q / 2], qy[Q / 2], qz[Q / 2];
+    float best[Q];
+    {
+      float x[Q], y[Q], z[Q];
+      if (kp.grid_mode) {
+        uint64_t k = idx < kp.n ? idx : (kp.n - 1);
+        uint32_t i0 = (uint32_t)(k / kp.g.plane);
+        uint32_t rem = (uint32_t)(k - (uint64_t)i0 * kp.g.plane);
+        uint32_t i1 = rem / kp.g.n2, i2 = rem - i1 * kp.g.n2;
+        i0 += kp.g.i0_begin;
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+          x[j] = grid_coord(kp.g, 0, i0, 0.0f);
+          y[j] = grid_coord(kp.g, 1, i1, 0.0f);
+          z[j] = kp.dim == 3 ? grid_coord(kp.g, 2, i2, 0.0f) : 0.0f;
+          if (++i2 == kp.g.n2) {
+            i2 = 0;
+            if (++i1 == kp.g.n1) {
+              i1 = 0;
+              ++i0;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+          const uint64_t k = idx + j < kp.n ? idx + j : kp.n - 1;
+          if (kp.co_is_f64) {
+            const double* c = (const double*)kp.co;
+            x[j] = (float)c[k];
+            y[j] = (float)c[kp.co_stride + k];
+            z[j] = kp.dim == 3 ? (float)c[2 * kp.co_stride + k] : 0.0f;
+          } else {
+            const float* c = (const float*)kp.co;
+            x[j] = c[k];
+            y[j] = c[kp.co_stride + k];
+            z[j] = kp.dim == 3 ? c[2 * kp.co_stride + k] : 0.0f;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < Q / 2; j++) {
+        qx[j] = make_float2(x[2 * j], x[2 * j + 1]);
+        qy[j] = make_float2(y[2 * j], y[2 * j + 1]);
+        qz[j] = make_float2(z[2 * j], z[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < Q; j++) best[j] = 3.0e38f;
+
+    const uint32_t n_ct = (kp.m + NN_TILE - 1) / NN_TILE;
+    auto stage = [&](int buf, uint32_t base) {
+      for (int i = threadIdx.x; i < NN_TILE; i += NT) {
+        float4 c = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.0f);  // padding: farther than any real point
+        if (base + i < kp.m) c = kp.cloud[base + i];
+        sxy[buf][i] = make_float4(-c.x, -c.x, -c.y, -c.y);
+        sz[buf][i] = make_float2(-c.z, -c.z);
+      }
+    };
+    __syncthreads();  // the previous query tile may still be reading the buffers
+    stage(0, 0);
+    __syncthreads();
+    for (uint32_t ct = 0; ct < n_ct; ct++) {
+      const int cur = ct & 1;
+      if (ct + 1 < n_ct) stage(cur ^ 1, (ct + 1) * NN_TILE);  // overlaps with the scan of the current tile
+#pragma unroll 2
+      for (int i = 0; i < NN_TILE; i += 2) {
+        const float4 a = sxy[cur][i], b = sxy[cur][i + 1];
+        const float2 az = sz[cur][i], bz = sz[cur][i + 1];
+#pragma unroll
+        for (int j = 0; j < Q / 2; j++) {
+          float2 dxa = __fadd2_rn(qx[j], make_float2(a.x, a.y)), dya = __fadd2_rn(qy[j], make_float2(a.z, a.w));
+          float2 dza = __fadd2_rn(qz[j], az);
+          float2 da = __ffma2_rn(dza, dza, __ffma2_rn(dya, dya, __fmul2_rn(dxa, dxa)));
+          float2 dxb = __fadd2_rn(qx[j], make_float2(b.x, b.y)), dyb = __fadd2_rn(qy[j], make_float2(b.z, b.w));
+          float2 dzb = __fadd2_rn(qz[j], bz);
+          float2 db = __ffma2_rn(dzb, dzb, __ffma2_rn(dyb, dyb, __fmul2_rn(dxb, dxb)));
+          best[2 * j] = fmin3(best[2 * j], da.x, db.x);
+          best[2 * j + 1] = fmin3(best[2 * j + 1], da.y, db.y);
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < Q; j++)
+      if (idx + j < kp.n) __stcs(kp.out + idx + j, s_sqrt(best[j]));
+  }
+}
+
 // ---- from_sdf -----------------------------------------------------------------------------------------------------------
 template <typename T>
 struct FDParams {

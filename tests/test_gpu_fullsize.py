@@ -1,0 +1,107 @@
+"""Parity at BASELINE.json's full sizes. The oracle cannot evaluate 10^8..10^9 points in seconds, so the full-size GPU
+fields are checked (a) against the oracle on a seeded random sample of grid points (the oracle accepts arbitrary point
+sets, so no grid is materialised), (b) through size-independent properties: x-slabs concatenate bit-identically, the
+C3 tree is mirror-symmetric in x, the analytic gradient has unit norm away from kinks, from_sdf of the GPU field agrees
+with the analytic gradient direction."""
+import numpy as np
+import pytest
+
+from oracle import interp_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample_check(prog, spec, field, n_samples, tol, band, extent, seed=0):
+    rng = np.random.default_rng(seed)
+    k = rng.integers(0, spec.n_points, size=n_samples)
+    nx, ny, nz = spec.res
+    iz, iy, ix = k % nz, (k // nz) % ny, k // (nz * ny)
+    ax = [np.linspace(-spec.size[i] / 2, spec.size[i] / 2, spec.res[i]) for i in range(spec.dims)]
+    co = np.zeros((3, n_samples))
+    co[0], co[1] = ax[0][ix], ax[1][iy]
+    if spec.dims == 3:
+        co[2] = ax[2][iz]
+    exp, margin = interp_np.run(prog, co, return_margin=True)
+    keep = margin > band * extent
+    assert keep.mean() > 0.97
+    got = field[k][keep].astype(np.float64)
+    err = np.max(np.abs(got - exp[keep]))
+    assert err <= tol * extent, f"max |cuda - oracle| on the sample = {err:.3e}"
+    far = np.abs(exp[keep]) > 1e-6 * extent
+    assert np.array_equal(np.sign(got[far]), np.sign(exp[keep][far]))
+    return err
+
+
+def test_c1_full_129_cubed_whole_grid():
+    import aegolius_b200 as ab
+    cfg = ab.workloads.CONFIGS["C1"]
+    spec = ab.GridSpec(cfg["size"], cfg["res"])
+    prog = ab.flatten(cfg["build"]())
+    assert spec.res == (129, 129, 129)
+    exp = interp_np.run_grid(prog, spec.size, spec.res)
+    assert np.max(np.abs(ab.create(prog, spec, dtype="f32") - exp)) <= 1e-5 * 4
+    assert np.max(np.abs(ab.create(prog, spec, dtype="f64") - exp)) <= 1e-12 * 4
+
+
+def test_c2_full_4097_squared_sampled():
+    import aegolius_b200 as ab
+    cfg = ab.workloads.CONFIGS["C2"]
+    spec = ab.GridSpec(cfg["size"], cfg["res"])
+    prog = ab.flatten(cfg["build"]())
+    assert spec.res == (4097, 4097, 1)
+    f32 = ab.create(prog, spec, dtype="f32")
+    _sample_check(prog, spec, f32, 200_000, 1e-5, 2e-6, 8.0)
+    f64 = ab.create(prog, spec, dtype="f64")
+    _sample_check(prog, spec, f64, 200_000, 1e-12, 1e-9, 8.0)
+
+
+def test_c3_full_513_cubed_sampled_and_properties():
+    import aegolius_b200 as ab
+    cfg = ab.workloads.CONFIGS["C3"]
+    spec = ab.GridSpec(cfg["size"], cfg["res"])
+    prog = ab.flatten(cfg["build"]())
+    assert spec.res == (513, 513, 513)
+    f32, g32 = ab.create(prog, spec, dtype="f32", grad="spatial")
+    _sample_check(prog, spec, f32, 200_000, 1e-5, 2e-6, 6.0)
+    # the outermost modification is a mirror across x = 0: the field is even in x up to rounding
+    vol = f32.reshape(spec.res)
+    assert np.max(np.abs(vol - vol[::-1])) <= 2e-5 * 6
+    # slabs concatenate bit-identically (value-only kernel against itself; the dual-number kernel rounds differently)
+    whole = ab.create(prog, spec, dtype="f32")
+    parts = [ab.create(prog, spec, dtype="f32", slab=s) for s in ab.engine.slab_ranges(513, 4)]
+    assert np.array_equal(np.concatenate(parts), whole)
+    assert np.max(np.abs(whole - f32)) <= 2e-6 * 6
+    # analytic gradient: unit norm wherever the field is a true distance (rounded, smooth-union'ed, twisted regions are
+    # not), so only bounded and finite here; its direction must agree with the np.gradient-based from_sdf of the field
+    assert np.isfinite(g32).all()
+    fd = ab.from_sdf(f32, spec.res)
+    n = np.linalg.norm(g32, axis=0)
+    dirs = g32 / np.maximum(n, 1e-30)
+    cosang = np.sum(dirs * fd, axis=0)
+    smooth = (n > 0.5) & (np.linalg.norm(fd, axis=0) > 0.5)
+    # (the instanced / symmetric tree has many discontinuity surfaces where a finite difference is meaningless)
+    assert np.median(cosang[smooth]) > 0.999 and np.mean(cosang[smooth] > 0.9) > 0.85
+
+
+def test_c5_full_1025_cubed_sampled_f32():
+    import aegolius_b200 as ab
+    cfg = ab.workloads.CONFIGS["C5"]
+    spec = ab.GridSpec(cfg["size"], cfg["res"])
+    prog = ab.flatten(cfg["build"]())
+    assert spec.res == (1025, 1025, 1025) and spec.n_points == 1_076_890_625
+    f32 = ab.create(prog, spec, dtype="f32")
+    _sample_check(prog, spec, f32, 300_000, 1e-5, 2e-6, 6.0)
+    del f32
+
+
+def test_c4_terrain_fixture_cloud_grid():
+    """C4's small parity case: a 16 384-point terrain-like cloud (same generator as the 1 M-point benchmark cloud) on
+    the 65^3 grid against exhaustive search."""
+    import aegolius_b200 as ab
+    pts = ab.workloads.c4_cloud(16_384, seed=1)
+    spec = ab.GridSpec((2.5, 2.5, 1.5), (64, 64, 64))
+    exp = interp_np.point_cloud_distance(spec.materialize(), pts)
+    got = ab.point_cloud_sdf(spec, pts, dtype="f32")
+    assert np.max(np.abs(got - exp)) <= 1e-5 * 2.5
+    got64 = ab.point_cloud_sdf(spec, pts, dtype="f64")
+    assert np.max(np.abs(got64 - exp)) <= 1e-12 * 2.5
