@@ -108,7 +108,7 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
       if (!(c >= 1) || c > 1024 || c != (double)(int)c) return fail(AB_EINVAL, "bad ROTSYM sector count %g", c);
       n = 4 + 2 * (int)c;
     } break;
-    case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: {
+    case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D: {
       if (op.arg >= n_args) return fail(AB_EINVAL, "op argument offset out of range");
       double c = args[op.arg];
       if (!(c >= 0) || c > 1e6) return fail(AB_EINVAL, "bad element count %g", c);

@@ -54,7 +54,8 @@ AB_DEV void divmod_small(uint32_t t, uint32_t n, uint32_t magic, uint32_t& q, ui
   X(C_SMIN3) X(C_SMAX3) X(C_SSUB3) X(C_BOLTZ_INT) X(C_BOLTZ_SUB) X(P_SPHERE) X(P_CYLINDER) X(P_BOX) X(P_TORUS)         \
   X(P_CHAINLINK) X(P_BRAID) X(P_ARC3D) X(P_PLANE) X(P_UPLANE) X(P_SEGMENT) X(P_CONE) X(P_OINF_CONE) X(P_INF_CONE)      \
   X(P_SOLID_ANGLE) X(P_TRIANGLE3D) X(P_QUAD3D) X(P_SEGLINE) X(P_AXIS) X(P_POINT_CLOUD) X(P_CIRCLE) X(P_NEU_CIRCLE)     \
-  X(P_BOX2D) X(P_SEGMENT2D) X(P_RBOX2D) X(P_TRIANGLE2D) X(P_ARC) X(P_SECTOR) X(P_INF_SECTOR) X(P_NGON) X(P_SEGLINE2D)
+  X(P_BOX2D) X(P_SEGMENT2D) X(P_RBOX2D) X(P_TRIANGLE2D) X(P_ARC) X(P_SECTOR) X(P_INF_SECTOR) X(P_NGON) X(P_SEGLINE2D) \
+  X(P_POLYGON2D)
 enum DenseOp : uint16_t {
 #define AB_X(name) D_##name,
   AB_OPLIST(AB_X)
@@ -572,6 +573,9 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_i
 #if AB_TIER_FULL >= 2
         case D_P_SEGLINE2D: acc = prim_segline(p, a, 2); break;
 #endif
+#if AB_TIER_FULL >= 2
+        case D_P_POLYGON2D: acc = prim_polygon2d(p, a); break;
+#endif
         default: break;  // unknown opcodes are rejected on the host (AB_EUNSUPPORTED_OP)
       }
     }
@@ -610,7 +614,7 @@ inline int op_tier(int ab_opcode) {
   if (is_lite_op(ab_opcode)) return 0;
   switch (ab_opcode) {
     case AB_OP_P_SOLID_ANGLE: case AB_OP_P_SECTOR: case AB_OP_P_TRIANGLE3D: case AB_OP_P_QUAD3D: case AB_OP_P_SEGLINE:
-    case AB_OP_P_SEGLINE2D: case AB_OP_P_POINT_CLOUD: case AB_OP_P_TRIANGLE2D:
+    case AB_OP_P_SEGLINE2D: case AB_OP_P_POINT_CLOUD: case AB_OP_P_TRIANGLE2D: case AB_OP_P_POLYGON2D:
       return 2;
     default: return 1;
   }

@@ -537,4 +537,40 @@ AB_DEV S prim_ngon(const Pt<S>& p, const T* a) {  // :153-177 ; args radius, alp
   return mul_lane(len, value_sign(fma_(q0, a[4], q1 * a[5])));
 }
 
+// sdf_polygon_2d (sdf_2D.py:201-218) for simple polygons: unsigned distance = min over the closed edge loop, interior
+// by the crossing-number rule (equals the union of the reference's ear-clipping triangles,
+// triangulation_functions.py:390-430). args: n, then n (x, y) vertices.
+template <typename S, typename T>
+AB_DEV S prim_polygon2d(const Pt<S>& p, const T* a) {
+  constexpr int W = S::width;
+  const int n = (int)a[0];
+  const T* pts = a + 1;
+  auto vx = value_of(p.x), vy = value_of(p.y);
+  S best = constant_like(p.x, T(1e32));
+  bool inside[W];
+#pragma unroll
+  for (int i = 0; i < W; i++) inside[i] = false;
+  for (int i = 0; i < n; i++) {
+    const int k = (i + 1 == n) ? 0 : i + 1;
+    const T ax = pts[2 * i], ay = pts[2 * i + 1], bx = pts[2 * k] - ax, by = pts[2 * k + 1] - ay;
+    const T bb = s_fma(bx, bx, by * by);
+    S px = p.x - ax, py = p.y - ay;
+    S h = clamp_(fma_(px, bx, py * by) * s_rcp(bb), T(0), T(1));
+    S t0 = px - h * bx, t1 = py - h * by;
+    best = min_(best, fma_(t0, t0, t1 * t1));
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+      const bool ca = ay > vy.v[j], cb = (ay + by) > vy.v[j];
+      if (ca != cb) {
+        const T xi = bx * (vy.v[j] - ay) / by + ax;
+        inside[j] = inside[j] != (vx.v[j] < xi);
+      }
+    }
+  }
+  Pack<T, W> sg;
+#pragma unroll
+  for (int j = 0; j < W; j++) sg.v[j] = inside[j] ? T(-1) : T(1);
+  return mul_lane(sqrt_(best), sg);
+}
+
 }  // namespace ab

@@ -41,7 +41,9 @@ _LEAF_NAMES = [
     "sdf_infinite_cone", "sdf_solid_angle", "sdf_triangle_3d", "sdf_quad_3d", "sdf_segmented_line_3d",
     "sdf_point_cloud_3d", "sdf_circle", "sdf_neu_circle", "sdf_box_2d", "sdf_segment_2d", "sdf_rounded_box_2d",
     "sdf_triangle_2d", "sdf_arc", "sdf_sector", "sdf_inf_sector", "sdf_ngon", "sdf_segmented_line_2d",
-    "sdf_point_cloud_2d", "sdf_closed_segmented_line_2d", "sdf_closed_segmented_line_3d",
+    "sdf_point_cloud_2d", "sdf_closed_segmented_line_2d", "sdf_closed_segmented_line_3d", "sdf_polygon_2d",
+    "sdf_parametric_curve_2d", "sdf_parametric_curve_3d", "sdf_closed_parametric_curve_2d",
+    "sdf_closed_parametric_curve_3d",
 ]
 LEAVES = {n: LeafSDF(n) for n in _LEAF_NAMES}
 globals().update(LEAVES)
@@ -583,6 +585,24 @@ class SegmentedLine3D(GenericGeometry):
         return self._closed
 
 
+class ParametricCurve3D(GenericGeometry):
+    """geom_3d.py:577-648: distance to the nearest sample of f(t), t = linspace(*t_range) (+ closing segment)."""
+
+    def __init__(self, parametric_curve, parametric_curve_parameters, t_range, closed=False):
+        self._curve, self._c_params, self._t_range, self._closed = parametric_curve, parametric_curve_parameters, \
+            t_range, closed
+        GenericGeometry.__init__(self, _leaf("sdf_closed_parametric_curve_3d" if closed else "sdf_parametric_curve_3d"),
+                                 parametric_curve, parametric_curve_parameters, self.ts)
+
+    @property
+    def ts(self):
+        return np.linspace(*self._t_range)
+
+    @property
+    def closed(self):
+        return self._closed
+
+
 class PointCloud3D(GenericGeometry):
     def __init__(self, points):
         self._points = _as_rows(points)
@@ -645,6 +665,44 @@ class InfiniteSector(GenericGeometry):
 class Arc(GenericGeometry):
     def __init__(self, radius, start_angle, end_angle):
         GenericGeometry.__init__(self, _leaf("sdf_arc"), radius, start_angle, end_angle)
+
+
+class Polygon(GenericGeometry):
+    """geom_2d.py:102-125 (simple polygons; vertices (3, N) or (N, 3))."""
+
+    def __init__(self, vertices):
+        GenericGeometry.__init__(self, _leaf("sdf_polygon_2d"), vertices)
+        vertices = np.array(vertices)
+        if not (vertices.shape[1] >= 3 and vertices.shape[0] >= 3):
+            raise ValueError("There must be at least 3 vertices defined by their coordinates in 3D space.")
+        if 3 not in vertices.shape:
+            raise ValueError("The coordinates of vertices should be defined in 3D space.")
+        if not (vertices.shape[0] == 3):
+            vertices = vertices.T
+        self._vertices = vertices
+        self._n_sides = vertices.shape[1]
+
+    @property
+    def n_sides(self):
+        return self._n_sides
+
+
+class ParametricCurve(GenericGeometry):
+    """geom_2d.py:340-457 (without .shape(), which needs a grid-wide test)."""
+
+    def __init__(self, parametric_curve, parametric_curve_parameters, t_range, closed=False):
+        self._curve, self._c_params, self._t_range, self._closed = parametric_curve, parametric_curve_parameters, \
+            t_range, closed
+        GenericGeometry.__init__(self, _leaf("sdf_closed_parametric_curve_2d" if closed else "sdf_parametric_curve_2d"),
+                                 parametric_curve, parametric_curve_parameters, self.ts)
+
+    @property
+    def ts(self):
+        return np.linspace(*self._t_range)
+
+    @property
+    def closed(self):
+        return self._closed
 
 
 class SegmentedLine(GenericGeometry):

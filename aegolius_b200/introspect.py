@@ -90,6 +90,12 @@ def to_frontend(obj, _stack=()):
             node.leaf = "sdf_closed_segmented_line_2d" if qn.startswith("SegmentedLine.") else \
                 "sdf_closed_segmented_line_3d"
             node._geo_parameters = tuple(getattr(obj, "_geo_parameters", ()))
+        elif qn in ("ParametricCurve.sdf_closed_curve.<locals>.new_geo_object",
+                    "ParametricCurve3D.sdf_closed_curve.<locals>.new_geo_object"):
+            node = _blank("leaf")
+            node.leaf = "sdf_closed_parametric_curve_2d" if qn.startswith("ParametricCurve.") else \
+                "sdf_closed_parametric_curve_3d"
+            node._geo_parameters = tuple(getattr(obj, "_geo_parameters", ()))
         elif inspect.isfunction(fn) and fn.__name__ in fe.LEAVES and "<locals>" not in qn:
             node = _blank("leaf")
             node.leaf = fn.__name__

@@ -186,6 +186,7 @@ class _Builder:
             posts.append(post)
 
         if n.kind == "leaf":
+            self.cur_vd = vd  # first free V slot, for leaves that need a temporary
             self.leaf(n.leaf, n._geo_parameters)
         elif n.kind == "nested":
             self.node(n.inner, pd, vd, stack)
@@ -487,6 +488,40 @@ class _Builder:
             if name.startswith("sdf_closed"):
                 pts = np.concatenate([pts, pts[:, :1]], axis=1)
             e(oc.P_SEGLINE2D, args=[float(pts.shape[1])] + list(pts.T.reshape(-1)))
+        elif name == "sdf_polygon_2d":
+            pts = np.asarray(params[0], dtype=np.float64)
+            if pts.ndim != 2 or 3 not in pts.shape:
+                raise ValueError("The coordinates of vertices should be defined in 3D space.")
+            if pts.shape[0] != 3:
+                pts = pts.T
+            pts = pts[:2]
+            if pts.shape[1] < 3:
+                raise ValueError("There must be at least 3 vertices defined by their coordinates in 3D space.")
+            if _polygon_self_intersects(pts):
+                raise FlattenError("self-intersecting polygons (split into loops by the reference, "
+                                   "triangulation_functions.py:413-419) are not supported on the GPU path")
+            e(oc.P_POLYGON2D, args=[float(pts.shape[1])] + list(pts.T.reshape(-1)))
+        elif name in ("sdf_parametric_curve_2d", "sdf_parametric_curve_3d", "sdf_closed_parametric_curve_2d",
+                      "sdf_closed_parametric_curve_3d"):
+            # nearest SAMPLE of the curve (a KD-tree over f(t) in the reference, sdf_2D.py:215-218, sdf_3D.py:274-280):
+            # the user's callable is evaluated here on the host and the samples become a point cloud blob
+            f, fp, ts = params
+            dim = 3 if name.endswith("3d") else 2
+            fval = np.asarray(f(np.asarray(ts), *fp), dtype=np.float64)
+            if fval.ndim != 2 or fval.shape[0] < dim:
+                raise ValueError(f"parametric curve must return an array of shape ({dim}, len(t))")
+            self.leaf(f"sdf_point_cloud_{dim}d", (fval[:dim],))
+            if name.startswith("sdf_closed"):  # min(f1, segment(p0, p1)), geom_2d.py:377-383 / geom_3d.py:606-612
+                p0 = np.asarray(f(ts[0], *fp), dtype=np.float64).reshape(-1)
+                p1 = np.asarray(f(ts[-1], *fp), dtype=np.float64).reshape(-1)
+                slot = self.cur_vd
+                self.use_v(slot)
+                e(oc.PUSH_V, a=slot)
+                if dim == 3:
+                    self.leaf("sdf_segment_3d", (p0[:3], p1[:3]))
+                else:
+                    self.leaf("sdf_segment_2d", (p0[:2], p1[:2]))
+                e(oc.C_UNION, a=slot)
         elif name in ("sdf_point_cloud_3d", "sdf_point_cloud_2d"):
             pts = np.asarray(params[0], dtype=np.float64)
             dim = 3 if name.endswith("3d") else 2
@@ -537,6 +572,24 @@ class _Builder:
             e(oc.P_NGON, args=[radius, alpha, -c, s, s, c, 2 * radius * np.sin(alpha / 2)])
         else:
             raise FlattenError(f"primitive '{name}' cannot enter the GPU op list")
+
+
+def _polygon_self_intersects(pts):
+    """True if two non-adjacent edges of the closed polygon properly intersect (O(n^2), host side)."""
+    n = pts.shape[1]
+
+    def orient(a, b, c):
+        return np.sign((b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]))
+
+    for i in range(n):
+        a, b = pts[:, i], pts[:, (i + 1) % n]
+        for j in range(i + 1, n):
+            if j == i or (j + 1) % n == i or (i + 1) % n == j:
+                continue
+            c, d = pts[:, j], pts[:, (j + 1) % n]
+            if orient(a, b, c) * orient(a, b, d) < 0 and orient(c, d, a) * orient(c, d, b) < 0:
+                return True
+    return False
 
 
 def _is_identity(M):
@@ -592,7 +645,7 @@ def _peephole(ops, args):
                 n = 4 + cnt * (12 if a == 1 else 3)
             elif code == oc.P_SEGLINE:
                 n = 1 + cnt * 3
-            elif code == oc.P_SEGLINE2D:
+            elif code in (oc.P_SEGLINE2D, oc.P_POLYGON2D):
                 n = 1 + cnt * 2
         put(code, a, b, args[off:off + n])
     flush()

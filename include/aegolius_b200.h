@@ -119,6 +119,7 @@ typedef enum ab_opcode {
   AB_OP_P_CIRCLE = 128, AB_OP_P_NEU_CIRCLE = 129, AB_OP_P_BOX2D = 130, AB_OP_P_SEGMENT2D = 131,
   AB_OP_P_RBOX2D = 132, AB_OP_P_TRIANGLE2D = 133, AB_OP_P_ARC = 134, AB_OP_P_SECTOR = 135,
   AB_OP_P_INF_SECTOR = 136, AB_OP_P_NGON = 137, AB_OP_P_SEGLINE2D = 138,
+  AB_OP_P_POLYGON2D = 139, /* simple polygon: min edge distance, sign by crossing number (sdf_2D.py:201-218) */
   AB_OP__COUNT = 160
 } ab_opcode;
 

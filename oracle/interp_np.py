@@ -28,7 +28,7 @@ import numpy as np
 (P_SPHERE, P_CYLINDER, P_BOX, P_TORUS, P_CHAINLINK, P_BRAID, P_ARC3D, P_PLANE, P_UPLANE, P_SEGMENT, P_CONE,
  P_OINF_CONE, P_INF_CONE, P_SOLID_ANGLE, P_TRIANGLE3D, P_QUAD3D, P_SEGLINE, P_AXIS, P_POINT_CLOUD) = range(96, 115)
 (P_CIRCLE, P_NEU_CIRCLE, P_BOX2D, P_SEGMENT2D, P_RBOX2D, P_TRIANGLE2D, P_ARC, P_SECTOR, P_INF_SECTOR, P_NGON,
- P_SEGLINE2D) = range(128, 139)
+ P_SEGLINE2D, P_POLYGON2D) = range(128, 140)
 
 
 def _norm(*c):
@@ -450,6 +450,22 @@ def run(prog, co, return_state=False, return_margin=False):
                     ba = pts[i + 1] - pts[i]
                     out = np.minimum(out, _segment((x - pts[i, 0], y - pts[i, 1]), ba, np.dot(ba, ba)))
                 acc = out
+            elif code == P_POLYGON2D:  # sdf_2D.py:201-218; interior of a SIMPLE polygon (triangulation_functions.py:390-430
+                # builds it as the union of the ear-clipping triangles, boundary included) == crossing-number rule
+                n = int(A[o])
+                pts = A[o + 1:o + 1 + 2 * n].reshape(n, 2)
+                out = np.ones(x.shape) * 1e16
+                inside = np.zeros(x.shape, dtype=bool)
+                for i in range(n):
+                    pa, pb = pts[i], pts[(i + 1) % n]
+                    ba = pb - pa
+                    out = np.minimum(out, _segment((x - pa[0], y - pa[1]), ba, np.dot(ba, ba)))
+                    cond = (pa[1] > y) != (pb[1] > y)
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        xi = (pb[0] - pa[0]) * (y - pa[1]) / (pb[1] - pa[1]) + pa[0]
+                    inside ^= cond & (x < xi)
+                    margin = np.minimum(margin, np.where(cond, np.abs(x - xi), np.inf))
+                acc = np.where(inside, -out, out)
             else:
                 raise ValueError(f"oracle: unknown opcode {code}")
     if return_state:

@@ -106,6 +106,26 @@ PRIMS2 = {
     "segmented_line_closed": lambda ns: ns.SegmentedLine(
         np.array([[-2.0, -0.5, 0.7, 2.1], [-1.0, 1.2, -0.9, 0.8]]), closed=True),
 }
+def lissajous(t, a, b):
+    return np.asarray((a * np.sin(2 * np.pi * t), b * np.sin(4 * np.pi * t + 0.3)))
+
+
+def helix(t, r, h):
+    return np.asarray((r * np.cos(4 * np.pi * t), r * np.sin(4 * np.pi * t), h * (t - 0.5)))
+
+
+PRIMS2.update({
+    "polygon_convex": lambda ns: ns.Polygon(np.array([[-1.5, 0.2, 1.6, 0.9, -0.8], [-1.0, -1.4, 0.1, 1.5, 1.2],
+                                                      [0.0, 0.0, 0.0, 0.0, 0.0]])),
+    "polygon_concave": lambda ns: ns.Polygon(np.array([[-1.6, 0.0, 1.7, 1.2, 0.1, -1.1], [-1.2, -0.3, -1.3, 1.4, 0.4, 1.5],
+                                                       [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]])),
+    "parametric_curve": lambda ns: ns.ParametricCurve(lissajous, (1.6, 1.1), (0, 1, 57)),
+    "parametric_curve_closed": lambda ns: ns.ParametricCurve(lissajous, (1.6, 1.1), (0, 0.8, 41), closed=True),
+})
+PRIMS3["parametric_curve3d"] = lambda ns: ns.ParametricCurve3D(helix, (0.8, 1.6), (0, 1, 49))
+PRIMS3["parametric_curve3d_closed"] = lambda ns: ns.ParametricCurve3D(helix, (0.8, 1.6), (0, 1, 33), closed=True)
+scenario("prim3_parametric_curve3d", *G3)(lambda ns: _xf(PRIMS3["parametric_curve3d"](ns), 1))
+scenario("prim3_parametric_curve3d_closed", *G3)(lambda ns: _xf(PRIMS3["parametric_curve3d_closed"](ns), 2))
 for _i, (_n, _b) in enumerate(PRIMS2.items()):
     scenario("prim2_" + _n, *G2)(lambda ns, _b=_b, _i=_i: _xf2(_b(ns), _i % 4))
 
