@@ -136,6 +136,33 @@ def create_with_gradient(obj, co, **kw):
     return create(obj, co, grad="spatial", **kw)
 
 
+# ---- parameter sensitivities (stand-in for jacfwd(geometry, argnums=k), Code/examples/autodiff/gradient_map_3D.py:84) ----
+
+
+def jacfwd(geometry, argnums=0, *, rel_step=1e-6, device=0):
+    """Returns g(co, *params) -> d field / d params[argnums] for a builder `geometry(*params) -> geometry object`.
+
+    The reference obtains this map with JAX forward mode through its jnp twin of the NumPy functions. Here the builder
+    is flattened at params[k] +- h and both programs are evaluated in fp64 on the GPU; the map is their central
+    difference (truncation O(h^2), rounding ~1e-16/h: ~1e-9 relative with the default step). This is a numerical
+    derivative: dual-number ARGUMENT tangents inside the interpreter (AB_GRAD_PARAM) are not built yet, the spatial
+    gradient (grad="spatial") is true forward mode. Every op is supported, including host-folded parameters."""
+
+    def grad_map(co, *params):
+        params = list(params)
+        theta = float(params[argnums])
+        h = rel_step * max(1.0, abs(theta))
+        lo, hi = list(params), list(params)
+        lo[argnums], hi[argnums] = theta - h, theta + h
+        f_hi = create(geometry(*hi), co, dtype="f64", device=device)
+        f_lo = create(geometry(*lo), co, dtype="f64", device=device)
+        f_hi -= f_lo
+        f_hi *= 1.0 / (2.0 * h)
+        return f_hi
+
+    return grad_map
+
+
 # ---- device-resident evaluation (torch owns the memory and the stream) ------------------------------------------------------
 
 

@@ -98,3 +98,38 @@ def test_launch_counter_counts_kernels():
     n0 = cabi.launch_count()
     ab.create(ab.flatten(ab.Sphere(1.0)), ab.GridSpec((2, 2, 2), (8, 8, 8)))
     assert cabi.launch_count() == n0 + 1
+
+
+def test_parameter_gradient_map_matches_oracle_differences():
+    """The gradient_map_3D.py:55-84 geometry (arc, concentric, elongation, two rotated copies, union, smooth union, onion)
+    differentiated with respect to each of its four parameters."""
+    import aegolius_b200 as ab
+
+    def geometry(r, a, w, s):
+        def part(sign):
+            arc = ab.Arc3D(r, 0.0, np.pi * 5 / 6, -np.pi * 5 / 6)
+            arc.concentric(w)
+            arc.elongation((0.0, 0.0, 0.75 / 2))
+            if sign:
+                arc.rotate(float(np.deg2rad(sign * a)), (0, 0, 1))
+                arc.rescale(1.2)
+                arc.move((0, 0, 1.5 * sign))
+            return arc
+        u = ab.CombineGeometry("UNION2").combine(part(+1), part(-1))
+        v = ab.CombineGeometry("SMOOTH_UNION2").combine_parametric(u, part(0), parameters=s)
+        v.onion(0.1)
+        return v
+
+    p = (2.0, 30.0, 0.5, 1.8)
+    rng = np.random.default_rng(4)
+    co = rng.uniform(-3, 3, size=(3, 5003))
+    for k in range(4):
+        got = ab.jacfwd(geometry, argnums=k)(co, *p)
+        h = 1e-5
+        lo, hi = list(p), list(p)
+        lo[k] -= h
+        hi[k] += h
+        exp = (interp_np.run(ab.flatten(geometry(*hi)), co) - interp_np.run(ab.flatten(geometry(*lo)), co)) / (2 * h)
+        kink = np.abs(exp - got) > 1e-3  # points whose active branch flips inside the stencil
+        assert kink.mean() < 0.02
+        assert np.max(np.abs(exp - got)[~kink]) < 1e-5
