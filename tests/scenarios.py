@@ -326,6 +326,125 @@ def build_2d_mirror_symmetry(ns):  # Code/examples/scalar/2D/mirror_symmetry_2D.
 scenario("struct_2d_mirror_rotsym", *G2)(build_2d_mirror_symmetry)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# geometry-building portions of the reference's example scripts (Code/examples/scalar/**, plotting stripped)
+
+
+def ex_pawn(ns):  # 3D/pawn_3D.py:30-71
+    torso = ns.Cone(1.8, np.pi / 10)
+    torso.move((0, 0, -0.55))
+    torso.rounding_cs(0.1, 0.4)
+    base = ns.Cylinder(0.4, 0.07)
+    base.rounding(0.1)
+    base.move((0, 0, -0.95))
+    head = ns.Sphere(0.25)
+    head.move((0, 0, 0.6))
+    collar = ns.Cylinder(0.3, 0.05)
+    collar.move((0, 0, 0.25))
+    union = ns.CombineGeometry("UNION2")
+    statue = union.combine(union.combine(base, torso), head)
+    pawn = ns.CombineGeometry("SMOOTH_UNION2_2").combine_parametric(statue, collar, parameters=0.2)
+    pawn.move((0, 0, 0.2))
+    return pawn
+
+
+def ex_rod(ns):  # 3D/rod_3D.py
+    box = ns.Box(3, 1, 0.5)
+    hexagon = ns.NGon(0.3, 6)
+    hexagon.boundary()
+    hexagon.concentric(0.2)
+    hexagon.rounding(0.05)
+    hexagon.extrusion(2)
+    hexagon.move((0.5, 0, 0))
+    cy = ns.Cylinder(0.4, 1)
+    cy.move((-0.5, 0, 0))
+    cy.rotate(np.pi / 6, (0, 1, 0))
+    arc = ns.Arc3D(1, 0.2, np.pi / 4, 7 * np.pi / 4)
+    cya = ns.Cylinder(1.2, 1)
+    union = ns.CombineGeometry("UNION")
+    s1 = union.combine(box, arc)
+    s2 = union.combine(hexagon, cy)
+    s3 = ns.CombineGeometry("SUBTRACT2").combine(s1, s2)
+    return ns.CombineGeometry("INTERSECT2").combine(s3, cya)
+
+
+def ex_braid(ns):  # 3D/braid_3D.py
+    torus = ns.Torus(0.25, 0.2)
+    torus.elongation((2., 0., 0.0))
+    torus.rotate(np.pi / 2, (0, 1, 0))
+    braid = ns.GenericGeometry(torus.propagate, ())
+    braid.twist(np.pi)
+    return braid
+
+
+def ex_candy_cane(ns):  # 3D/candy_cane_3D.py
+    seg = ns.Line((-5, 0, 0), (1.5, 0, 0))
+    seg.rounding(0.15)
+    seg.bend(0.5, np.pi)
+    seg.rotate(-np.pi / 2, (1, 0, 0))
+    seg.rotate(-np.pi / 2, (0, 0, 1))
+    seg.move((0.013, 0.007, 2.5))  # (0, 0, 2.5) in the example; nudged so the bend cut misses the grid's centre plane
+    return seg
+
+
+def ex_chip(ns):  # 3D/chip_3D.py without the user displacement callable
+    cy = ns.Cylinder(1, 0.05)
+    cy.rotate(np.pi / 2, (1, 0, 0))
+    s1 = ns.GenericGeometry(cy.propagate, ())
+    s1.bend(1.75, np.pi)
+    s1.rotate(np.pi / 2, (0, 1, 0))
+    s2 = ns.GenericGeometry(s1.propagate, ())
+    s2.bend(1.75, np.pi)
+    s2.rotate(np.pi / 2, (1, 0, 0))
+    return ns.GenericGeometry(s2.propagate, ())
+
+
+def ex_lamp_shade(ns):  # 3D/lamp_shade_3D.py
+    shade = ns.Arc(1, np.pi, np.pi + 0.7 * np.pi / 2)
+    shade.axis_revolution(1 + 0.2, -np.pi / 10)
+    shade.rounding(0.02)
+    shade.rotate(np.pi / 10, (0, 0, 1))
+    shade.rotate(np.pi / 2, (1, 0, 0))
+    shade.move((0, 0, 0.3))
+    return shade
+
+
+def ex_olympic_rings(ns):  # 2D/olympic_rings_2D.py
+    radius, thickness, x_sep, y_sep = 0.5, 0.05, 1.2, 0.5
+    rings = []
+    for cx, cy in ((-x_sep, y_sep / 2), (0, y_sep / 2), (x_sep, y_sep / 2), (-x_sep / 2, -y_sep / 2),
+                   (x_sep / 2, -y_sep / 2)):
+        c = ns.Circle(radius)
+        c.onion(thickness)
+        c.move((cx, cy, 0))
+        rings.append(c)
+    return ns.CombineGeometry("UNION").combine(*rings)
+
+
+def ex_water_molecule(ns):  # 2D/water_molecule_2D.py
+    angle, d, h_size = 104.5, 0.0957, 0.075
+    o_size = h_size * 1.3
+    x_sep = 10 * d * np.cos(np.deg2rad((180 - angle) / 2))
+    y_sep = 10 * d * np.sin(np.deg2rad((180 - angle) / 2))
+    h = ns.Circle(10 * h_size / 2)
+    h.linear_instancing(2, (-x_sep, 0, 0), (x_sep, 0, 0))
+    h.move((0, -y_sep, 0))
+    o = ns.Circle(10 * o_size / 2)
+    combine = ns.CombineGeometry("")
+    combine.operation_type = "SMOOTH_UNION2"  # the example sets the type after construction
+    return combine.combine_parametric(h, o, parameters=0.45)
+
+
+scenario("ex_pawn_3D", (3.0, 3.0, 3.0), (20, 20, 20))(ex_pawn)
+scenario("ex_rod_3D", (4.0, 4.0, 2.0), (24, 20, 12))(ex_rod)
+scenario("ex_braid_3D", (3.0, 3.0, 3.0), (20, 20, 20))(ex_braid)
+scenario("ex_candy_cane_3D", (6.0, 6.0, 8.0), (16, 16, 24))(ex_candy_cane)
+scenario("ex_chip_3D", (4.0, 4.0, 4.0), (20, 20, 20))(ex_chip)
+scenario("ex_lamp_shade_3D", (4.0, 4.0, 4.0), (20, 20, 20))(ex_lamp_shade)
+scenario("ex_olympic_rings_2D", (4.0, 2.0), (96, 48))(ex_olympic_rings)
+scenario("ex_water_molecule_2D", (3.0, 3.0), (64, 64))(ex_water_molecule)
+
+
 def make_namespace(kind):
     """kind = 'reference' (needs /root/reference or an installed spomso) or 'frontend'."""
     import types
