@@ -77,6 +77,7 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
   switch (op.opcode) {
     case AB_OP_END: case AB_OP_SAVE_P: case AB_OP_LOAD_P: case AB_OP_PUSH_V: case AB_OP_SYMMETRY: case AB_OP_ZERO_Z:
     case AB_OP_ABS: case AB_OP_NEG: case AB_OP_SIGN: case AB_OP_EXTRUDE_END: case AB_OP_C_UNION: case AB_OP_C_INTERSECT:
+    case AB_OP_NEXT_LOAD:
     case AB_OP_C_SUBTRACT: case AB_OP_C_SUM: case AB_OP_C_DIFF: case AB_OP_P_POINT_CLOUD:
       n = 0; break;
     case AB_OP_SCALE_P: case AB_OP_TWIST: case AB_OP_ABSX_SUB: case AB_OP_REVOLVE: case AB_OP_ROUND: case AB_OP_ONION:
@@ -88,7 +89,7 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
     case AB_OP_PP_SMOOTH_RELU: case AB_OP_PP_GAUSS_BOUNDARY: case AB_OP_PP_GAUSS_FALLOFF: case AB_OP_P_CYLINDER:
     case AB_OP_P_TORUS: case AB_OP_P_OINF_CONE: case AB_OP_P_INF_CONE: case AB_OP_P_NEU_CIRCLE: case AB_OP_P_BOX2D:
       n = 2; break;
-    case AB_OP_TRANSLATE: case AB_OP_AXIS_REVOLVE: case AB_OP_PP_SLOWSTART: case AB_OP_P_BOX: case AB_OP_P_CHAINLINK:
+    case AB_OP_TRANSLATE: case AB_OP_NEXT_TRANSLATE: case AB_OP_AXIS_REVOLVE: case AB_OP_PP_SLOWSTART: case AB_OP_P_BOX: case AB_OP_P_CHAINLINK:
       n = 3; break;
     case AB_OP_P_BRAID: case AB_OP_P_PLANE: case AB_OP_P_UPLANE: case AB_OP_P_CONE: case AB_OP_P_ARC:
       n = 4; break;
@@ -98,7 +99,7 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
       n = 6; break;
     case AB_OP_P_SEGMENT: case AB_OP_P_NGON: n = 7; break;
     case AB_OP_BEND: n = 8; break;
-    case AB_OP_AFFINE: case AB_OP_REP_FIN: n = 12; break;
+    case AB_OP_AFFINE: case AB_OP_NEXT_AFFINE: case AB_OP_REP_FIN: n = 12; break;
     case AB_OP_P_TRIANGLE2D: n = 16; break;
     case AB_OP_P_TRIANGLE3D: n = 34; break;
     case AB_OP_P_QUAD3D: n = 44; break;
@@ -141,6 +142,10 @@ static int validate(const ab_program* prog) {
       case AB_OP_SAVE_P: case AB_OP_LOAD_P:
         if (op.a >= prog->n_pslots) return fail(AB_EINVAL, "op %u: P slot %u >= n_pslots %u", i, op.a, prog->n_pslots);
         break;
+      case AB_OP_NEXT_AFFINE: case AB_OP_NEXT_TRANSLATE: case AB_OP_NEXT_LOAD:
+        if (op.a >= prog->n_pslots) return fail(AB_EINVAL, "op %u: P slot %u >= n_pslots %u", i, op.a, prog->n_pslots);
+        if (op.b > prog->n_vslots) return fail(AB_EINVAL, "op %u: fused V slot %u > n_vslots %u", i, op.b, prog->n_vslots);
+        break;
       case AB_OP_PUSH_V: case AB_OP_EXTRUDE_BEGIN: case AB_OP_EXTRUDE_END:
         if (op.a >= prog->n_vslots) return fail(AB_EINVAL, "op %u: V slot %u >= n_vslots %u", i, op.a, prog->n_vslots);
         break;
@@ -154,8 +159,9 @@ static int validate(const ab_program* prog) {
         if (op.a > 2) return fail(AB_EINVAL, "op %u: axis %u", i, op.a);
         break;
       default:
-        if (op.opcode >= AB_OP_C_UNION && op.opcode <= AB_OP_C_BOLTZ_SUB && op.a >= prog->n_vslots)
-          return fail(AB_EINVAL, "op %u: V slot %u >= n_vslots %u", i, op.a, prog->n_vslots);
+        if (op.opcode >= AB_OP_C_UNION && op.opcode <= AB_OP_C_BOLTZ_SUB &&
+            (op.a >= prog->n_vslots || op.b > prog->n_vslots))
+          return fail(AB_EINVAL, "op %u: V slot out of range (a %u, b %u, n_vslots %u)", i, op.a, op.b, prog->n_vslots);
     }
     if (op.opcode >= AB_OP_P_SPHERE) have_value = true;
     if (op.opcode == AB_OP_END) break;

@@ -46,7 +46,7 @@ AB_DEV void divmod_small(uint32_t t, uint32_t n, uint32_t magic, uint32_t& q, ui
 // dense opcode numbering used inside the kernel (the host remaps ab_opcode -> DenseOp so that the dispatch switch
 // compiles to one indexed branch instead of a compare tree)
 #define AB_OPLIST(X)                                                                                                   \
-  X(END) X(SAVE_P) X(LOAD_P) X(PUSH_V) X(AFFINE) X(TRANSLATE) X(SCALE_P) X(ELONGATE) X(TWIST) X(BEND) X(ABSX_SUB)        \
+  X(END) X(SAVE_P) X(LOAD_P) X(PUSH_V) X(NEXT_AFFINE) X(NEXT_TRANSLATE) X(NEXT_LOAD) X(AFFINE) X(TRANSLATE) X(SCALE_P) X(ELONGATE) X(TWIST) X(BEND) X(ABSX_SUB)        \
   X(SYMMETRY) X(ROTSYM) X(REVOLVE) X(AXIS_REVOLVE) X(REP_INF) X(REP_FIN) X(LIN_INST) X(CURVE_INST) X(ZERO_Z) X(ROUND)  \
   X(ABS) X(NEG) X(SIGN) X(ONION) X(CONCENTRIC) X(SCALE_V) X(EXTRUDE_BEGIN) X(EXTRUDE_END) X(PP_SIGMOID)                \
   X(PP_POS_SIGMOID) X(PP_CAPPED_EXP) X(PP_HARD_BIN) X(PP_LINEAR) X(PP_RELU) X(PP_SMOOTH_RELU) X(PP_SLOWSTART)          \
@@ -264,6 +264,12 @@ __host__ __device__ inline size_t prog_ops_bytes(uint32_t n_ops) { return ((size
 template <typename T>
 __host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((size_t)n_args * sizeof(T) + 15) & ~(size_t)15; }
 
+// fused PUSH_V after a combine op (b = V slot + 1, 0 = none)
+#define AB_CPUSH                                  \
+  do {                                            \
+    if (sb) SK::st(vstack, sb - 1, NT, acc);      \
+  } while (0)
+
 // ---- the interpreter -------------------------------------------------------------------------------------------------------
 // TIER 0 ("lite") contains only the ops without transcendental functions or tables (stack, affine family, elongate,
 // mirror core, symmetry, revolve, infinite repetition, the value ops, the polynomial combines and the sqrt-only
@@ -390,6 +396,17 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_i
           p.z = SK::ld(pstack, sa * 3 + 2, NT);
           break;
         case D_PUSH_V: SK::st(vstack, sa, NT, acc); break;
+        // fused [PUSH_V] + LOAD_P + transform (program.py::_fuse): one dispatch per child of a combine chain
+        case D_NEXT_AFFINE:
+        case D_NEXT_TRANSLATE:
+        case D_NEXT_LOAD:
+          if (sb) SK::st(vstack, sb - 1, NT, acc);
+          p.x = SK::ld(pstack, sa * 3 + 0, NT);
+          p.y = SK::ld(pstack, sa * 3 + 1, NT);
+          p.z = SK::ld(pstack, sa * 3 + 2, NT);
+          if (code == D_NEXT_AFFINE) op_affine(p, a);
+          else if (code == D_NEXT_TRANSLATE) op_translate(p, a);
+          break;
         // coordinate ops
         case D_AFFINE: op_affine(p, a); break;
         case D_TRANSLATE: op_translate(p, a); break;
@@ -486,20 +503,20 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_i
         } break;
 #endif
         // combine: acc = f(V[a], acc)
-        case D_C_UNION: acc = min_(SK::ld(vstack, sa, NT), acc); break;
-        case D_C_INTERSECT: acc = max_(SK::ld(vstack, sa, NT), acc); break;
-        case D_C_SUBTRACT: acc = max_(SK::ld(vstack, sa, NT), -acc); break;
-        case D_C_SUM: acc = SK::ld(vstack, sa, NT) + acc; break;
-        case D_C_DIFF: acc = SK::ld(vstack, sa, NT) - acc; break;
-        case D_C_SMIN2: acc = smin_poly2(SK::ld(vstack, sa, NT), acc, a[0]); break;
-        case D_C_SMIN3: acc = smin_poly3(SK::ld(vstack, sa, NT), acc, a[0]); break;
-        case D_C_SMAX3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), -acc, a[0]); break;
-        case D_C_SSUB3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), acc, a[0]); break;
+        case D_C_UNION: acc = min_(SK::ld(vstack, sa, NT), acc); AB_CPUSH; break;
+        case D_C_INTERSECT: acc = max_(SK::ld(vstack, sa, NT), acc); AB_CPUSH; break;
+        case D_C_SUBTRACT: acc = max_(SK::ld(vstack, sa, NT), -acc); AB_CPUSH; break;
+        case D_C_SUM: acc = SK::ld(vstack, sa, NT) + acc; AB_CPUSH; break;
+        case D_C_DIFF: acc = SK::ld(vstack, sa, NT) - acc; AB_CPUSH; break;
+        case D_C_SMIN2: acc = smin_poly2(SK::ld(vstack, sa, NT), acc, a[0]); AB_CPUSH; break;
+        case D_C_SMIN3: acc = smin_poly3(SK::ld(vstack, sa, NT), acc, a[0]); AB_CPUSH; break;
+        case D_C_SMAX3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), -acc, a[0]); AB_CPUSH; break;
+        case D_C_SSUB3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), acc, a[0]); AB_CPUSH; break;
 #if AB_TIER_FULL
-        case D_C_BOLTZ_INT: acc = smax_boltz(SK::ld(vstack, sa, NT), acc, a[0]); break;
+        case D_C_BOLTZ_INT: acc = smax_boltz(SK::ld(vstack, sa, NT), acc, a[0]); AB_CPUSH; break;
 #endif
 #if AB_TIER_FULL
-        case D_C_BOLTZ_SUB: acc = smax_boltz(SK::ld(vstack, sa, NT), -acc, a[0]); break;
+        case D_C_BOLTZ_SUB: acc = smax_boltz(SK::ld(vstack, sa, NT), -acc, a[0]); AB_CPUSH; break;
 #endif
         // 3D primitives
         case D_P_SPHERE: acc = prim_sphere(p, a); break;
@@ -597,6 +614,7 @@ inline int op_tier(int ab_opcode);
 inline bool is_lite_op(int ab_opcode) {
   switch (ab_opcode) {
     case AB_OP_END: case AB_OP_SAVE_P: case AB_OP_LOAD_P: case AB_OP_PUSH_V: case AB_OP_AFFINE: case AB_OP_TRANSLATE:
+    case AB_OP_NEXT_AFFINE: case AB_OP_NEXT_TRANSLATE: case AB_OP_NEXT_LOAD:
     case AB_OP_SCALE_P: case AB_OP_ELONGATE: case AB_OP_ABSX_SUB: case AB_OP_SYMMETRY: case AB_OP_REVOLVE:
     case AB_OP_REP_INF: case AB_OP_ZERO_Z: case AB_OP_ROUND: case AB_OP_ABS: case AB_OP_NEG: case AB_OP_SIGN:
     case AB_OP_ONION: case AB_OP_CONCENTRIC: case AB_OP_SCALE_V: case AB_OP_EXTRUDE_BEGIN: case AB_OP_EXTRUDE_END:

@@ -652,6 +652,43 @@ def _peephole(ops, args):
     return out_ops, out_args
 
 
+_COMBINES = (oc.C_UNION, oc.C_INTERSECT, oc.C_SUBTRACT, oc.C_SUM, oc.C_DIFF, oc.C_SMIN2, oc.C_SMIN3, oc.C_SMAX3,
+             oc.C_SSUB3, oc.C_BOLTZ_INT, oc.C_BOLTZ_SUB)
+
+
+def _fuse(ops):
+    """Superinstructions: every dispatch costs the interpreter ~20 issue slots per thread, so the recurring sequences of
+    a combine chain are folded into one op each:
+        [PUSH_V v] LOAD_P s, AFFINE|TRANSLATE   ->  NEXT_AFFINE|NEXT_TRANSLATE (a = s, b = v + 1 or 0)
+        [PUSH_V v] LOAD_P s                     ->  NEXT_LOAD
+        C_xxx (a = v), PUSH_V w                 ->  C_xxx (a = v, b = w + 1)
+    Argument offsets are untouched (the fused op keeps the transform's arguments)."""
+    out, i = [], 0
+    while i < len(ops):
+        code, a, b, off = ops[i]
+        nxt = ops[i + 1] if i + 1 < len(ops) else None
+        nn = ops[i + 2] if i + 2 < len(ops) else None
+        if code == oc.PUSH_V and nxt is not None and nxt[0] == oc.LOAD_P:
+            if nn is not None and nn[0] in (oc.AFFINE, oc.TRANSLATE):
+                out.append((oc.NEXT_AFFINE if nn[0] == oc.AFFINE else oc.NEXT_TRANSLATE, nxt[1], a + 1, nn[3]))
+                i += 3
+            else:
+                out.append((oc.NEXT_LOAD, nxt[1], a + 1, 0))
+                i += 2
+            continue
+        if code == oc.LOAD_P and nxt is not None and nxt[0] in (oc.AFFINE, oc.TRANSLATE):
+            out.append((oc.NEXT_AFFINE if nxt[0] == oc.AFFINE else oc.NEXT_TRANSLATE, a, 0, nxt[3]))
+            i += 2
+            continue
+        if code in _COMBINES and b == 0 and nxt is not None and nxt[0] == oc.PUSH_V:
+            out.append((code, a, nxt[1] + 1, off))
+            i += 2
+            continue
+        out.append(ops[i])
+        i += 1
+    return out
+
+
 def flatten(obj, optimize=True) -> Program:
     """Flattens a frontend.GenericGeometry tree (or a SPOMSO object, via introspect.to_frontend)."""
     from .frontend import GenericGeometry
@@ -663,6 +700,7 @@ def flatten(obj, optimize=True) -> Program:
     ops, args = b.ops, b.args
     if optimize:
         ops, args = _peephole(ops, args)
+        ops = _fuse(ops)
     ops.append((oc.END, 0, 0, 0))
     if len(ops) > oc.MAX_OPS or len(args) > oc.MAX_ARGS:
         raise FlattenError(f"program too large: {len(ops)} ops / {len(args)} args "

@@ -87,6 +87,11 @@ typedef enum ab_opcode {
   AB_OP_CURVE_INST = 22, /* a = mode (0 positions only, 1 positions + 3x3 frames); args: n, then n records
                             (curve_instancing :1090-1132, aligned :1134-1196, fully aligned :1198-1266) */
   AB_OP_ZERO_Z = 23,     /* z = 0 */
+  /* fused forms emitted by the flattener's peephole pass (one dispatch instead of two or three):
+     optional PUSH_V (b = V slot + 1, 0 = none), then p = f(P[a]) */
+  AB_OP_NEXT_AFFINE = 24,    /* [V[b-1] = acc;] p = M P[a] + t   (PUSH_V + LOAD_P + AFFINE) */
+  AB_OP_NEXT_TRANSLATE = 25, /* [V[b-1] = acc;] p = P[a] + t     (PUSH_V + LOAD_P + TRANSLATE) */
+  AB_OP_NEXT_LOAD = 26,      /* [V[b-1] = acc;] p = P[a]         (PUSH_V + LOAD_P) */
   /* --- value ops --- */
   AB_OP_ROUND = 32,      /* acc -= r (rounding :100) */
   AB_OP_ABS = 33,        /* boundary :146 */
@@ -101,7 +106,8 @@ typedef enum ab_opcode {
   AB_OP_PP_SIGMOID = 48, AB_OP_PP_POS_SIGMOID = 49, AB_OP_PP_CAPPED_EXP = 50, AB_OP_PP_HARD_BIN = 51,
   AB_OP_PP_LINEAR = 52, AB_OP_PP_RELU = 53, AB_OP_PP_SMOOTH_RELU = 54, AB_OP_PP_SLOWSTART = 55,
   AB_OP_PP_GAUSS_BOUNDARY = 56, AB_OP_PP_GAUSS_FALLOFF = 57,
-  /* --- combine ops: acc = f(V[a], acc)  (combine.py:51-78) --- */
+  /* --- combine ops: acc = f(V[a], acc)  (combine.py:51-78); if b != 0 the result is also stored to V[b-1]
+     (fused PUSH_V of a left-deep combine chain) --- */
   AB_OP_C_UNION = 64, AB_OP_C_INTERSECT = 65, AB_OP_C_SUBTRACT = 66, AB_OP_C_SUM = 67, AB_OP_C_DIFF = 68,
   AB_OP_C_SMIN2 = 69,     /* smoothmin_poly2, 1 arg w (combine.py:12-18) */
   AB_OP_C_SMIN3 = 70,     /* smoothmin_poly3 (combine.py:20-26) */

@@ -20,6 +20,7 @@ import numpy as np
 (END, SAVE_P, LOAD_P, PUSH_V) = (0, 1, 2, 3)
 (AFFINE, TRANSLATE, SCALE_P, ELONGATE, TWIST, BEND, ABSX_SUB, SYMMETRY, ROTSYM, REVOLVE, AXIS_REVOLVE, REP_INF,
  REP_FIN, LIN_INST, CURVE_INST, ZERO_Z) = range(8, 24)
+(NEXT_AFFINE, NEXT_TRANSLATE, NEXT_LOAD) = (24, 25, 26)  # fused PUSH_V + LOAD_P + transform (program.py peephole)
 (ROUND, ABS, NEG, SIGN, ONION, CONCENTRIC, SCALE_V, EXTRUDE_BEGIN, EXTRUDE_END) = range(32, 41)
 (PP_SIGMOID, PP_POS_SIGMOID, PP_CAPPED_EXP, PP_HARD_BIN, PP_LINEAR, PP_RELU, PP_SMOOTH_RELU, PP_SLOWSTART,
  PP_GAUSS_BOUNDARY, PP_GAUSS_FALLOFF) = range(48, 58)
@@ -110,6 +111,16 @@ def run(prog, co, return_state=False, return_margin=False):
                 x, y, z = P[a]
             elif code == PUSH_V:
                 V[a] = acc
+            elif code in (NEXT_AFFINE, NEXT_TRANSLATE, NEXT_LOAD):
+                if b:
+                    V[b - 1] = acc
+                x, y, z = P[a]
+                if code == NEXT_AFFINE:
+                    m = A[o:o + 12]
+                    x, y, z = (m[0] * x + m[1] * y + m[2] * z + m[9], m[3] * x + m[4] * y + m[5] * z + m[10],
+                               m[6] * x + m[7] * y + m[8] * z + m[11])
+                elif code == NEXT_TRANSLATE:
+                    x, y, z = x + A[o], y + A[o + 1], z + A[o + 2]
             # ---- coordinate ops ----
             elif code == AFFINE:  # transformations.py:238-240 folded: M = R^T/s, b = -R^T t
                 m = A[o:o + 12]
@@ -468,6 +479,8 @@ def run(prog, co, return_state=False, return_margin=False):
                 acc = np.where(inside, -out, out)
             else:
                 raise ValueError(f"oracle: unknown opcode {code}")
+            if C_UNION <= code <= C_BOLTZ_SUB and b:
+                V[b - 1] = acc  # fused PUSH_V of a left-deep combine chain
     if return_state:
         return acc, (x, y, z)
     if return_margin:
