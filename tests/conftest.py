@@ -15,6 +15,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the SPOMSO sources under /root/reference (build container only)")
 
 
+def pytest_sessionstart(session):
+    """The library is a build artefact (git-ignored): build it once if a fresh checkout has none (nvcc cross-compiles
+    without a GPU; ~2 min). Tests that need it fail loudly if this fails."""
+    from aegolius_b200 import cabi
+    if not os.path.exists(cabi.LIB_PATH):
+        try:
+            from aegolius_b200 import build
+            build.build(verbose=False)
+        except Exception as e:  # pragma: no cover
+            print(f"[conftest] could not build libaegolius_b200.so: {e}")
+
+
 def has_cuda():
     try:
         from aegolius_b200 import cabi
