@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "ab_kernels_aux.cuh"
@@ -258,11 +259,28 @@ static int dispatch_nt(const KParams<T>& kp, int device, cudaStream_t st) {
   LaunchCfg cfg{di.sms, di.smem_optin};
   int status = AB_OK;
   cudaError_t e;
-  if (kp.tier == 0) e = launch_interp<S, T, 0>(kp, cfg, st, &status);
-  else if (kp.tier == 1) {
+  if (kp.tier == 0 && !std::is_same<S, Pack<float, 4>>::value) {
+    // (fp32 value-only lite programs never get here: run_program sends them to the 8-wide lite kernel)
+    if constexpr (!std::is_same<S, Pack<float, 4>>::value) e = launch_interp<S, T, 0>(kp, cfg, st, &status);
+    else e = cudaErrorInvalidValue;
+  } else if (kp.tier <= 1) {
     if constexpr (sizeof(T) == 4) e = launch_interp<S, T, 1>(kp, cfg, st, &status);
     else e = launch_interp<S, T, 2>(kp, cfg, st, &status);  // fp64 has no mid-tier build
   } else e = launch_interp<S, T, 2>(kp, cfg, st, &status);
+  if (e != cudaSuccess) return fail(AB_ECUDA, "interpreter launch: %s", cudaGetErrorString(e));
+  if (status != AB_OK) return fail(status, "interpreter stacks (%u P, %u V slots) do not fit in shared memory", kp.n_pslots, kp.n_vslots);
+  g_launches++;
+  return AB_OK;
+}
+
+template <typename S, typename T, int TIER>
+static int dispatch_fixed(const KParams<T>& kp, int device, cudaStream_t st) {
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  LaunchCfg cfg{di.sms, di.smem_optin};
+  int status = AB_OK;
+  cudaError_t e = launch_interp<S, T, TIER>(kp, cfg, st, &status);
   if (e != cudaSuccess) return fail(AB_ECUDA, "interpreter launch: %s", cudaGetErrorString(e));
   if (status != AB_OK) return fail(status, "interpreter stacks (%u P, %u V slots) do not fit in shared memory", kp.n_pslots, kp.n_vslots);
   g_launches++;
@@ -360,7 +378,14 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
     } else {
       kp.co = (const char*)tg.co + done * (tg.co_is_f64 ? 8 : 4);
     }
-    if (grad_mode == AB_GRAD_NONE) rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
+    if (grad_mode == AB_GRAD_NONE) {
+      if constexpr (sizeof(T) == 4) {
+        // lite programs are cheap per op, so 8 points per thread (two 128-bit stores) halve the per-point dispatch and
+        // index overhead at still < 100 registers
+        if (kp.tier == 0) rc = dispatch_fixed<Pack<T, 8>, T, 0>(kp, device, st);
+        else rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
+      } else rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
+    }
     else rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
     done += chunk;
   }

@@ -114,11 +114,43 @@ AB_DEV double grid_coord(const GridK& g, int c, uint32_t i, double) {
   return (i == g.last[c]) ? g.stop[c] : __dadd_rn(__dmul_rn((double)i, g.step[c]), g.start[c]);
 }
 
+// W consecutive samples of one axis starting at index i: k_j = (i - centre) + j is exact in fp32, then the same one-rounding
+// product as grid_coord, issued as packed f32x2 (3 packed instructions per 2 samples instead of 4 scalar per sample)
+template <int W>
+AB_DEV void grid_coord_run(const GridK& g, int c, uint32_t i, Pack<float, W>& out) {
+  const float k0 = (float)i - g.centre[c];
+  Pack<float, W> k;
+#pragma unroll
+  for (int j = 0; j < W; j++) k.v[j] = (float)j;
+  k = k + k0;
+  out = fma_(k, g.hi[c], k * g.lo[c]);
+}
+template <int W>
+AB_DEV void grid_coord_run(const GridK& g, int c, uint32_t i, Pack<double, W>& out) {
+#pragma unroll
+  for (int j = 0; j < W; j++) out.v[j] = grid_coord(g, c, i + j, 0.0);
+}
+
 // ---- stack in shared memory: element [slot][tid] is one 16-byte Pack column --------------------------------------------
 template <typename P>
 AB_DEV void st_pack(P* base, int slot, int nt, const P& v) { base[slot * nt + threadIdx.x] = v; }
 template <typename P>
 AB_DEV P ld_pack(const P* base, int slot, int nt) { return base[slot * nt + threadIdx.x]; }
+
+// 32-byte packs are stored as two 16-byte columns so that consecutive threads stay on consecutive banks
+AB_DEV void st_pack(Pack<float, 8>* base, int slot, int nt, const Pack<float, 8>& v) {
+  float4* b = reinterpret_cast<float4*>(base);
+  b[(slot * 2 + 0) * nt + threadIdx.x] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+  b[(slot * 2 + 1) * nt + threadIdx.x] = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+AB_DEV Pack<float, 8> ld_pack(const Pack<float, 8>* base, int slot, int nt) {
+  const float4* b = reinterpret_cast<const float4*>(base);
+  const float4 lo = b[(slot * 2 + 0) * nt + threadIdx.x], hi = b[(slot * 2 + 1) * nt + threadIdx.x];
+  Pack<float, 8> r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
 
 template <typename T, int W>
 struct StackIO {
@@ -161,6 +193,16 @@ AB_DEV void store_pack(float* dst, const Pack<float, 4>& v, uint64_t idx, uint64
   } else {
 #pragma unroll
     for (int i = 0; i < 4; i++)
+      if (idx + i < n) __stcs(dst + idx + i, v.v[i]);
+  }
+}
+AB_DEV void store_pack(float* dst, const Pack<float, 8>& v, uint64_t idx, uint64_t n, bool aligned) {
+  if (aligned && idx + 8 <= n) {
+    __stcs(reinterpret_cast<float4*>(dst + idx), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+    __stcs(reinterpret_cast<float4*>(dst + idx) + 1, make_float4(v.v[4], v.v[5], v.v[6], v.v[7]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
       if (idx + i < n) __stcs(dst + idx + i, v.v[i]);
   }
 }
@@ -318,13 +360,9 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_i
       divmod_small(b1 + q, kp.g.n1, kp.g.m1, q, i1);
       i0 = b0 + q + kp.g.i0_begin;
       if (i2 + W <= kp.g.n2) {  // the W points share one (ix, iy) row: the common case
-        const T c0 = grid_coord(kp.g, 0, i0, T()), c1 = grid_coord(kp.g, 1, i1, T());
-#pragma unroll
-        for (int j = 0; j < W; j++) {
-          cx.v[j] = c0;
-          cy.v[j] = c1;
-          cz.v[j] = grid_coord(kp.g, 2, i2 + j, T());
-        }
+        cx = P(grid_coord(kp.g, 0, i0, T()));
+        cy = P(grid_coord(kp.g, 1, i1, T()));
+        grid_coord_run(kp.g, 2, i2, cz);
       } else {  // a row boundary falls inside this thread's run
 #pragma unroll
         for (int j = 0; j < W; j++) {
