@@ -178,28 +178,38 @@ static int make_gridk(const ab_grid* grid, GridK& g, uint64_t* n_points) {
     if (grid->res[c] == 0) return fail(AB_EINVAL, "grid resolution of 0");
   if (grid->slab_begin >= grid->slab_end || grid->slab_end > grid->res[0])
     return fail(AB_EINVAL, "bad slab [%u, %u) for res0 %u", grid->slab_begin, grid->slab_end, grid->res[0]);
-  uint64_t plane = (uint64_t)grid->res[1] * grid->res[2];
-  if (plane > 0x7fffffffull) return fail(AB_ETOOLARGE, "ny*nz does not fit 31 bits");
-  g.n1 = grid->res[1];
-  g.n2 = grid->res[2];
+  // 2D grids (res[2] == 1) are remapped to index axes (1, nx, ny) so that the fast index axis is y and a thread's run
+  // of consecutive points stays inside one row; parameter sets 1 and 2 then describe x and y, z is +0
+  const bool is2d = grid->res[2] == 1 && grid->res[1] > 1 && grid->size[2] == 0.0;
+  const uint32_t n1 = is2d ? grid->res[0] : grid->res[1];
+  const uint32_t n2 = is2d ? grid->res[1] : grid->res[2];
+  const uint64_t plane = (uint64_t)n1 * n2;  // 2D: the whole grid is one "plane" of index axis 0
+  if (plane > 0x7fffffffull) return fail(AB_ETOOLARGE, "one grid plane has more than 2^31 points");
+  g.n1 = n1;
+  g.n2 = n2;
   g.plane = (uint32_t)plane;
-  g.i0_begin = grid->slab_begin;
-  g.m1 = (uint32_t)(0x100000000ull / grid->res[1] > 0xffffffffull ? 0xffffffffull : 0x100000000ull / grid->res[1]);
-  g.m2 = (uint32_t)(0x100000000ull / grid->res[2] > 0xffffffffull ? 0xffffffffull : 0x100000000ull / grid->res[2]);
+  g.is2d = is2d ? 1u : 0u;
+  g.i0_begin = is2d ? 0u : grid->slab_begin;
+  g.i1_begin = is2d ? grid->slab_begin : 0u;
+  g.m1 = (uint32_t)(0x100000000ull / n1 > 0xffffffffull ? 0xffffffffull : 0x100000000ull / n1);
+  g.m2 = (uint32_t)(0x100000000ull / n2 > 0xffffffffull ? 0xffffffffull : 0x100000000ull / n2);
   for (int c = 0; c < 3; c++) {
-    uint32_t n = grid->res[c];
-    double start = -grid->size[c] / 2, stop = grid->size[c] / 2;
+    // parameter set c describes index axis c: (x, y, z) in 3D, (unused, x, y) in 2D
+    int src = is2d ? c - 1 : c;
+    uint32_t n = src >= 0 ? grid->res[src] : 1;
+    double sz = src >= 0 ? grid->size[src] : 0.0;
+    double start = -sz / 2, stop = sz / 2;
     double step = n > 1 ? (stop - start) / (double)(n - 1) : 0.0;  // np.linspace: delta / div
     g.last[c] = n - 1;
     g.start[c] = start;
     g.stop[c] = n > 1 ? stop : start + 0.0;
-    if (n == 1) g.stop[c] = (grid->size[c] == 0.0) ? 0.0 : start;  // linspace(a, b, 1) == [a]; 2D grids: z = +0
+    if (n == 1) g.stop[c] = (sz == 0.0) ? 0.0 : start;  // linspace(a, b, 1) == [a]; 2D grids: z = +0
     g.step[c] = step;
     g.hi[c] = (float)step;
     g.lo[c] = (float)(step - (double)g.hi[c]);
     g.centre[c] = (float)((double)(n - 1) * 0.5);
   }
-  *n_points = (uint64_t)(grid->slab_end - grid->slab_begin) * plane;
+  *n_points = (uint64_t)(grid->slab_end - grid->slab_begin) * (is2d ? (uint64_t)n2 : plane);
   return AB_OK;
 }
 
@@ -363,9 +373,10 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
     if (chunk > kMax) {
       chunk = kMax;
       if (tg.grid_mode) {
-        uint64_t planes = kMax / tg.g.plane;
+        const uint64_t unit = tg.g.is2d ? tg.g.n2 : tg.g.plane;  // whole ix planes (rows of y in 2D)
+        uint64_t planes = kMax / unit;
         if (planes == 0) return fail(AB_ETOOLARGE, "one grid plane has more than 2^31 points");
-        chunk = planes * tg.g.plane;
+        chunk = planes * unit;
       } else {
         chunk &= ~3ull;
       }
@@ -374,7 +385,8 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
     kp.out = tg.out + done;
     kp.grad = tg.grad ? tg.grad + done : nullptr;
     if (tg.grid_mode) {
-      kp.g.i0_begin = tg.g.i0_begin + (uint32_t)(done / tg.g.plane);
+      if (tg.g.is2d) kp.g.i1_begin = tg.g.i1_begin + (uint32_t)(done / tg.g.n2);
+      else kp.g.i0_begin = tg.g.i0_begin + (uint32_t)(done / tg.g.plane);
     } else {
       kp.co = (const char*)tg.co + done * (tg.co_is_f64 ? 8 : 4);
     }
@@ -509,7 +521,7 @@ extern "C" int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, in
   rc = pipe_for(device, &pp);
   if (rc) return rc;
   // chunk = whole planes, about 128 MB of output each (at least one plane, at most the slab)
-  const uint64_t plane = g.plane;
+  const uint64_t plane = g.is2d ? g.n2 : g.plane;  // one ix plane (a row of y in 2D)
   const uint64_t bytes_per_plane = plane * es * (1 + rows);
   uint64_t planes_per_chunk = (128ull << 20) / (bytes_per_plane ? bytes_per_plane : 1);
   if (planes_per_chunk < 1) planes_per_chunk = 1;

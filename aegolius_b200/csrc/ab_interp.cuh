@@ -25,7 +25,9 @@ struct GridK {
   // index axes (ix, iy, iz), iz fastest. 2D grids are (nx, ny, 1) with size_z = 0, so z == 0.
   uint32_t n1, n2;          // ny, nz
   uint32_t plane;           // ny * nz
-  uint32_t i0_begin;        // first ix plane of the slab
+  uint32_t i0_begin;        // first ix plane of the slab (3D)
+  uint32_t i1_begin;        // 2D grids are remapped to index axes (1, nx, ny): the slab offset then applies to axis 1
+  uint32_t is2d;            // 1: x = axis-1 sample, y = axis-2 sample, z = +0 (parameter sets 1 and 2 hold x and y)
   uint32_t last[3];         // res-1 per axis (for the exact linspace end point)
   double start[3], step[3], stop[3];  // linspace parameters per axis (fp64 path: bit-identical to numpy)
   float hi[3], lo[3], centre[3];      // fp32 path: x = (i - centre) * (hi + lo), one rounding
@@ -117,7 +119,7 @@ AB_DEV double grid_coord(const GridK& g, int c, uint32_t i, double) {
 // W consecutive samples of one axis starting at index i: k_j = (i - centre) + j is exact in fp32, then the same one-rounding
 // product as grid_coord, issued as packed f32x2 (3 packed instructions per 2 samples instead of 4 scalar per sample)
 template <int W>
-AB_DEV void grid_coord_run(const GridK& g, int c, uint32_t i, Pack<float, W>& out) {
+AB_DEV void grid_coord_run(const GridK& g, int c, int32_t i, Pack<float, W>& out) {
   const float k0 = (float)i - g.centre[c];
   Pack<float, W> k;
 #pragma unroll
@@ -126,9 +128,9 @@ AB_DEV void grid_coord_run(const GridK& g, int c, uint32_t i, Pack<float, W>& ou
   out = fma_(k, g.hi[c], k * g.lo[c]);
 }
 template <int W>
-AB_DEV void grid_coord_run(const GridK& g, int c, uint32_t i, Pack<double, W>& out) {
+AB_DEV void grid_coord_run(const GridK& g, int c, int32_t i, Pack<double, W>& out) {
 #pragma unroll
-  for (int j = 0; j < W; j++) out.v[j] = grid_coord(g, c, i + j, 0.0);
+  for (int j = 0; j < W; j++) out.v[j] = (i + j >= 0) ? grid_coord(g, c, (uint32_t)(i + j), 0.0) : 0.0;
 }
 
 // ---- stack in shared memory: element [slot][tid] is one 16-byte Pack column --------------------------------------------
@@ -359,24 +361,57 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_i
       divmod_small(b2 + threadIdx.x * W, kp.g.n2, kp.g.m2, q, i2);
       divmod_small(b1 + q, kp.g.n1, kp.g.m1, q, i1);
       i0 = b0 + q + kp.g.i0_begin;
-      if (i2 + W <= kp.g.n2) {  // the W points share one (ix, iy) row: the common case
-        cx = P(grid_coord(kp.g, 0, i0, T()));
-        cy = P(grid_coord(kp.g, 1, i1, T()));
-        grid_coord_run(kp.g, 2, i2, cz);
-      } else {  // a row boundary falls inside this thread's run
+      i1 += kp.g.i1_begin;
+      const int ca = kp.g.is2d ? 1 : 0, cb = kp.g.is2d ? 2 : 1;  // parameter sets of the two slow coordinates
+      P ua, ub, uc;  // samples along index axes (slow, middle, fast)
+      if (i2 + W <= kp.g.n2) {  // the W points share one row: the common case
+        ua = P(grid_coord(kp.g, 0, i0, T()));
+        ub = P(grid_coord(kp.g, 1, i1, T()));
+        grid_coord_run(kp.g, 2, (int32_t)i2, uc);
+      } else if (kp.g.n2 >= (uint32_t)W) {  // exactly one row boundary inside the run: points j >= s sit on the next row
+        const int s = (int)(kp.g.n2 - i2);
+        uint32_t j1 = i1 + 1, j0 = i0;
+        if (j1 == kp.g.n1 + kp.g.i1_begin) {
+          j1 = kp.g.i1_begin;
+          ++j0;
+        }
+        const T a0 = grid_coord(kp.g, 0, i0, T()), a1 = grid_coord(kp.g, 1, i1, T());
+        const T n0 = grid_coord(kp.g, 0, j0, T()), n1 = grid_coord(kp.g, 1, j1, T());
+        P ra, rb;
+        grid_coord_run(kp.g, 2, (int32_t)i2, ra);
+        grid_coord_run(kp.g, 2, -s, rb);
 #pragma unroll
         for (int j = 0; j < W; j++) {
-          cx.v[j] = grid_coord(kp.g, 0, i0, T());
-          cy.v[j] = grid_coord(kp.g, 1, i1, T());
-          cz.v[j] = grid_coord(kp.g, 2, i2, T());
+          const bool first = j < s;
+          ua.v[j] = first ? a0 : n0;
+          ub.v[j] = first ? a1 : n1;
+          uc.v[j] = first ? ra.v[j] : rb.v[j];
+        }
+      } else {  // rows shorter than the run (tiny grids): walk point by point
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+          ua.v[j] = grid_coord(kp.g, 0, i0, T());
+          ub.v[j] = grid_coord(kp.g, 1, i1, T());
+          uc.v[j] = grid_coord(kp.g, 2, i2, T());
           if (++i2 == kp.g.n2) {
             i2 = 0;
-            if (++i1 == kp.g.n1) {
-              i1 = 0;
+            if (++i1 == kp.g.n1 + kp.g.i1_begin) {
+              i1 = kp.g.i1_begin;
               ++i0;
             }
           }
         }
+      }
+      (void)ca;
+      (void)cb;
+      if (kp.g.is2d) {
+        cx = ub;
+        cy = uc;
+        cz = P(T(0));
+      } else {
+        cx = ua;
+        cy = ub;
+        cz = uc;
       }
       // advance the tile origin by gridDim.x tiles
       b2 += kp.tile_stride[2];

@@ -41,15 +41,22 @@ __global__ void __launch_bounds__(NT) ab_nn_kernel(const __grid_constant__ NNPar
       uint32_t rem = (uint32_t)(k - (uint64_t)i0 * kp.g.plane);
       uint32_t i1 = rem / kp.g.n2, i2 = rem - i1 * kp.g.n2;
       i0 += kp.g.i0_begin;
+      i1 += kp.g.i1_begin;
 #pragma unroll
       for (int j = 0; j < Q; j++) {
-        qx[j] = grid_coord(kp.g, 0, i0, T());
-        qy[j] = grid_coord(kp.g, 1, i1, T());
-        qz[j] = kp.dim == 3 ? grid_coord(kp.g, 2, i2, T()) : T(0);
+        if (kp.g.is2d) {  // index axes (1, nx, ny): parameter sets 1 and 2 are x and y
+          qx[j] = grid_coord(kp.g, 1, i1, T());
+          qy[j] = grid_coord(kp.g, 2, i2, T());
+          qz[j] = T(0);
+        } else {
+          qx[j] = grid_coord(kp.g, 0, i0, T());
+          qy[j] = grid_coord(kp.g, 1, i1, T());
+          qz[j] = kp.dim == 3 ? grid_coord(kp.g, 2, i2, T()) : T(0);
+        }
         if (++i2 == kp.g.n2) {
           i2 = 0;
-          if (++i1 == kp.g.n1) {
-            i1 = 0;
+          if (++i1 == kp.g.n1 + kp.g.i1_begin) {
+            i1 = kp.g.i1_begin;
             ++i0;
           }
         }
@@ -136,15 +143,22 @@ __global__ void __launch_bounds__(NT) ab_nn_kernel_f32x2(const __grid_constant__
         uint32_t rem = (uint32_t)(k - (uint64_t)i0 * kp.g.plane);
         uint32_t i1 = rem / kp.g.n2, i2 = rem - i1 * kp.g.n2;
         i0 += kp.g.i0_begin;
+        i1 += kp.g.i1_begin;
 #pragma unroll
         for (int j = 0; j < Q; j++) {
-          x[j] = grid_coord(kp.g, 0, i0, 0.0f);
-          y[j] = grid_coord(kp.g, 1, i1, 0.0f);
-          z[j] = kp.dim == 3 ? grid_coord(kp.g, 2, i2, 0.0f) : 0.0f;
+          if (kp.g.is2d) {
+            x[j] = grid_coord(kp.g, 1, i1, 0.0f);
+            y[j] = grid_coord(kp.g, 2, i2, 0.0f);
+            z[j] = 0.0f;
+          } else {
+            x[j] = grid_coord(kp.g, 0, i0, 0.0f);
+            y[j] = grid_coord(kp.g, 1, i1, 0.0f);
+            z[j] = kp.dim == 3 ? grid_coord(kp.g, 2, i2, 0.0f) : 0.0f;
+          }
           if (++i2 == kp.g.n2) {
             i2 = 0;
-            if (++i1 == kp.g.n1) {
-              i1 = 0;
+            if (++i1 == kp.g.n1 + kp.g.i1_begin) {
+              i1 = kp.g.i1_begin;
               ++i0;
             }
           }
