@@ -641,7 +641,35 @@ static int nn_t(const void* cloud, uint64_t m, int dim, int grid_mode, const Gri
   kp.co = co;
   kp.co_stride = co_stride;
   kp.co_is_f64 = co_dtype == AB_F64;
-  if constexpr (sizeof(T) == 4) return launch_nn<T, 8, 512>(kp, device, st);
+  if constexpr (sizeof(T) == 4) {
+    // few queries: split the cloud across lanes / warps / CTAs (warp-shuffle min + atomic min), else one query per lane
+    DevInfo di;
+    int rc = dev_info(device, di);
+    if (rc) return rc;
+    if (n < (uint64_t)di.sms * 2 * 2048 && m >= 4096) {
+      constexpr int QW = 16, NT = 128;
+      const uint64_t groups = (n + QW - 1) / QW;
+      // aim for ~8 waves of warps over the machine, slices of at least 1024 points
+      uint64_t want_slices = ((uint64_t)di.sms * 64 * 8 + groups - 1) / groups;
+      uint64_t max_slices = (m + 1023) / 1024;
+      if (want_slices > max_slices) want_slices = max_slices;
+      if (want_slices < 1) want_slices = 1;
+      uint32_t slice = (uint32_t)((m + want_slices - 1) / want_slices);
+      slice = (slice + 31) & ~31u;
+      const uint32_t n_slices = (uint32_t)((m + slice - 1) / slice);
+      const uint32_t gy = (n_slices + (NT / 32) - 1) / (NT / 32);
+      if (groups <= 0x7fffffffull && gy <= 65535) {
+        CUDA_TRY(cudaMemsetAsync(out, 0x7f, n * sizeof(float), st));
+        ab_nn_split_kernel_f32<QW, NT><<<dim3((unsigned)groups, gy), NT, 0, st>>>(kp, slice);
+        CUDA_TRY(cudaGetLastError());
+        ab_nn_finalize_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, st>>>((float*)out, n);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 2;
+        return AB_OK;
+      }
+    }
+    return launch_nn<T, 8, 512>(kp, device, st);
+  }
   else return launch_nn<T, 4, 512>(kp, device, st);
 }
 

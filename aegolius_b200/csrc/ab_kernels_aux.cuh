@@ -229,6 +229,87 @@ __global__ void __launch_bounds__(NT) ab_nn_kernel_f32x2(const __grid_constant__
   }
 }
 
+// Few queries x many points (points mode with a short list, coarse grids): parallelism has to come from the cloud. Every
+// warp owns QW queries (held by all lanes) and one slice of the cloud; lane l scans points l, l+32, ... of the slice, the
+// 32 partial minima are combined with warp-shuffle min-reductions and lane 0 folds the result into the output with an
+// atomic min on the float bit pattern (monotonic for non-negative values). Output must be pre-filled with 0x7f7f7f7f
+// and is finalised (sqrt) by ab_nn_finalize_kernel.
+template <int QW, int NT>
+__global__ void __launch_bounds__(NT) ab_nn_split_kernel_f32(const __grid_constant__ NNParams<float> kp, uint32_t slice) {
+  static_assert(QW % 2 == 0, "pairs");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t q0 = (uint64_t)blockIdx.x * QW;
+  const uint32_t begin = (blockIdx.y * (NT / 32) + warp) * slice;
+  if (begin >= kp.m) return;
+  const uint32_t end = begin + slice < kp.m ? begin + slice : kp.m;
+  float2 qx[QW / 2], qy[QW / 2], qz[QW / 2];
+  float best[QW];
+#pragma unroll
+  for (int j = 0; j < QW; j++) {
+    const uint64_t k = q0 + j < kp.n ? q0 + j : kp.n - 1;
+    float x, y, z;
+    if (kp.grid_mode) {
+      uint32_t i0 = (uint32_t)(k / kp.g.plane);
+      uint32_t rem = (uint32_t)(k - (uint64_t)i0 * kp.g.plane);
+      uint32_t i1 = rem / kp.g.n2, i2 = rem - i1 * kp.g.n2;
+      i0 += kp.g.i0_begin;
+      i1 += kp.g.i1_begin;
+      if (kp.g.is2d) {
+        x = grid_coord(kp.g, 1, i1, 0.0f);
+        y = grid_coord(kp.g, 2, i2, 0.0f);
+        z = 0.0f;
+      } else {
+        x = grid_coord(kp.g, 0, i0, 0.0f);
+        y = grid_coord(kp.g, 1, i1, 0.0f);
+        z = kp.dim == 3 ? grid_coord(kp.g, 2, i2, 0.0f) : 0.0f;
+      }
+    } else if (kp.co_is_f64) {
+      const double* c = (const double*)kp.co;
+      x = (float)c[k];
+      y = (float)c[kp.co_stride + k];
+      z = kp.dim == 3 ? (float)c[2 * kp.co_stride + k] : 0.0f;
+    } else {
+      const float* c = (const float*)kp.co;
+      x = c[k];
+      y = c[kp.co_stride + k];
+      z = kp.dim == 3 ? c[2 * kp.co_stride + k] : 0.0f;
+    }
+    if (j & 1) {
+      qx[j / 2].y = x;
+      qy[j / 2].y = y;
+      qz[j / 2].y = z;
+    } else {
+      qx[j / 2].x = x;
+      qy[j / 2].x = y;
+      qz[j / 2].x = z;
+    }
+    best[j] = 3.0e38f;
+  }
+  for (uint32_t i = begin + lane; i < end; i += 32) {
+    const float4 c = kp.cloud[i];  // coalesced: a warp reads 512 contiguous bytes
+    const float2 nx = make_float2(-c.x, -c.x), ny = make_float2(-c.y, -c.y), nz = make_float2(-c.z, -c.z);
+#pragma unroll
+    for (int j = 0; j < QW / 2; j++) {
+      const float2 dx = __fadd2_rn(qx[j], nx), dy = __fadd2_rn(qy[j], ny), dz = __fadd2_rn(qz[j], nz);
+      const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+      best[2 * j] = fminf(best[2 * j], d.x);
+      best[2 * j + 1] = fminf(best[2 * j + 1], d.y);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < QW; j++) {
+    float b = best[j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, off));
+    if (lane == 0 && q0 + j < kp.n) atomicMin(reinterpret_cast<unsigned int*>(kp.out) + q0 + j, __float_as_uint(b));
+  }
+}
+
+__global__ void ab_nn_finalize_kernel(float* out, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = s_sqrt(out[i]);
+}
+
 // ---- from_sdf -----------------------------------------------------------------------------------------------------------
 template <typename T>
 struct FDParams {

@@ -133,3 +133,17 @@ def test_parameter_gradient_map_matches_oracle_differences():
         kink = np.abs(exp - got) > 1e-3  # points whose active branch flips inside the stencil
         assert kink.mean() < 0.02
         assert np.max(np.abs(exp - got)[~kink]) < 1e-5
+
+
+def test_point_cloud_few_queries_many_points_split_path():
+    """Short query lists take the split-cloud kernel (warp-shuffle min + atomic min); ragged sizes on purpose."""
+    import aegolius_b200 as ab
+    pts = _cloud(70_001, seed=21)
+    rng = np.random.default_rng(8)
+    for n in (1, 17, 1003):
+        co = rng.uniform(-1.3, 1.3, size=(3, n))
+        exp = interp_np.point_cloud_distance(co, pts, dim=3)
+        got = ab.point_cloud_sdf(co, pts, dim=3, dtype="f32")
+        assert got.shape == (n,) and np.max(np.abs(got - exp)) <= 1e-5 * 2.6
+        got2 = ab.point_cloud_sdf(co, pts, dim=2, dtype="f32")
+        assert np.max(np.abs(got2 - interp_np.point_cloud_distance(co, pts, dim=2))) <= 1e-5 * 2.6
