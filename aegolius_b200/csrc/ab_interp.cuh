@@ -323,7 +323,7 @@ __host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((si
 // n-gons ...) at 90 registers; TIER 2 adds the widest primitives (triangles, quads, sectors, polylines, point clouds).
 // minimum resident CTAs per SM asked of the register allocator, per tier (128-thread CTAs): lite 6, mid 5, full 4
 template <typename S, typename T, int TIER>
-__global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 5 : 4)) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
+__global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 6 : 4)) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
   static_assert(TIER == AB_TIER_FULL, "one tier per translation unit");
   constexpr int W = S::width;
   const int NT = blockDim.x;
