@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libaegolius_b200.so")
 UNITS = ["ab_capi.cu", "ab_interp_f32.cu", "ab_interp_f32g.cu", "ab_interp_f64.cu", "ab_interp_f64g.cu",
-         "ab_interp_f32_mid.cu", "ab_interp_f32g_mid.cu", "ab_interp_f32_lite.cu", "ab_interp_f32g_lite.cu", "ab_interp_f64_lite.cu", "ab_interp_f64g_lite.cu"]
+         "ab_interp_f32p.cu", "ab_interp_f64p.cu", "ab_interp_f32_mid.cu", "ab_interp_f32g_mid.cu", "ab_interp_f32_lite.cu", "ab_interp_f32g_lite.cu", "ab_interp_f64_lite.cu", "ab_interp_f64g_lite.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 

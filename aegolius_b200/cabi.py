@@ -122,8 +122,14 @@ class CProgram:
                 self._blobs[i] = ab_blob(device_blobs[i], b.shape[1], 3, 1)
             else:
                 self._blobs[i] = ab_blob(b.ctypes.data, b.shape[1], 3, 0)
+        self._dargs = None
+        if getattr(prog, "dargs", None) is not None:
+            self._dargs = np.ascontiguousarray(prog.dargs, dtype=np.float64)
+            if self._dargs.shape != self._args.shape:
+                raise ValueError("Program.dargs must have the shape of Program.args")
         self.struct = ab_program(self._ops.ctypes.data, self._ops.shape[0], self._args.ctypes.data,
-                                 self._args.shape[0], None, self._blobs, n_blobs, prog.n_pslots, prog.n_vslots)
+                                 self._args.shape[0], self._dargs.ctypes.data if self._dargs is not None else None,
+                                 self._blobs, n_blobs, prog.n_pslots, prog.n_vslots)
 
     def ref(self):
         return C.byref(self.struct)

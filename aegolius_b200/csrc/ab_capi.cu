@@ -248,6 +248,20 @@ extern "C" int ab_cloud_upload(const double* points_host, uint64_t m, int dim, u
 }
 
 // ---- interpreter launch ----------------------------------------------------------------------------------------------------
+static const uint32_t kParamHalf = (AB_MAX_ARGS / 2) & ~3u;
+
+// arguments that the kernels read as plain tables (no tangent): see raw_args() uses in ab_ops.cuh
+static bool structural_arg(int opcode, int k) {
+  switch (opcode) {
+    case AB_OP_ROTSYM: return k != 1;  // everything but the radius
+    case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D: case AB_OP_P_TRIANGLE3D:
+    case AB_OP_P_QUAD3D: case AB_OP_P_TRIANGLE2D: case AB_OP_P_RBOX2D:
+      return true;
+    case AB_OP_P_NEU_CIRCLE: return k == 1;  // the norm order
+    default: return false;
+  }
+}
+
 template <typename T>
 struct EvalTarget {
   int grid_mode;
@@ -283,14 +297,14 @@ static int dispatch_nt(const KParams<T>& kp, int device, cudaStream_t st) {
   return AB_OK;
 }
 
-template <typename S, typename T, int TIER>
+template <typename S, typename T, int TIER, bool PARAM = false>
 static int dispatch_fixed(const KParams<T>& kp, int device, cudaStream_t st) {
   DevInfo di;
   int rc = dev_info(device, di);
   if (rc) return rc;
   LaunchCfg cfg{di.sms, di.smem_optin};
   int status = AB_OK;
-  cudaError_t e = launch_interp<S, T, TIER>(kp, cfg, st, &status);
+  cudaError_t e = launch_interp<S, T, TIER, PARAM>(kp, cfg, st, &status);
   if (e != cudaSuccess) return fail(AB_ECUDA, "interpreter launch: %s", cudaGetErrorString(e));
   if (status != AB_OK) return fail(status, "interpreter stacks (%u P, %u V slots) do not fit in shared memory", kp.n_pslots, kp.n_vslots);
   g_launches++;
@@ -303,11 +317,11 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   if (rc) return rc;
   if (tg.n == 0) return AB_OK;
   if (!tg.out) return fail(AB_EINVAL, "null output pointer");
-  if (grad_mode == AB_GRAD_PARAM)
-    return fail(AB_EUNSUPPORTED_OP, "AB_GRAD_PARAM (parameter tangents) is not implemented in this build");
-  if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL) return fail(AB_EINVAL, "bad grad_mode %d", grad_mode);
-  if (grad_mode == AB_GRAD_SPATIAL && (!tg.grad || tg.grad_stride < tg.n))
+  if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL && grad_mode != AB_GRAD_PARAM)
+    return fail(AB_EINVAL, "bad grad_mode %d", grad_mode);
+  if (grad_mode != AB_GRAD_NONE && (!tg.grad || tg.grad_stride < tg.n))
     return fail(AB_EINVAL, "gradient output missing or grad_stride < n");
+  if (grad_mode == AB_GRAD_PARAM && !prog->dargs) return fail(AB_EINVAL, "AB_GRAD_PARAM needs ab_program.dargs");
 
   static thread_local KParams<T> kp;  // ~28 KB: keep it off the stack
   kp.n = tg.n;
@@ -338,9 +352,24 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
       return fail(AB_ETOOLARGE, "program arguments exceed %d after alignment", AB_MAX_ARGS);
     kp.ops[i] = make_uint2(dense, cursor | ((uint32_t)prog->ops[i].a << 16) | ((uint32_t)prog->ops[i].b << 24));
     for (int k = 0; k < cnt; k++) kp.args[cursor + k] = (T)prog->args[prog->ops[i].arg + k];
+    if (grad_mode == AB_GRAD_PARAM) {
+      // tangents of the arguments go to the upper half of the pool; table-driven ops are structural (their tables are
+      // read without tangents), so a parameter that reaches one of them cannot be differentiated here
+      if (cursor + (uint32_t)cnt + 4 > kParamHalf)
+        return fail(AB_ETOOLARGE, "program arguments exceed %u in parameter-tangent mode", kParamHalf);
+      for (int k = 0; k < cnt; k++) {
+        const double dk = prog->dargs[prog->ops[i].arg + k];
+        kp.args[kParamHalf + cursor + k] = (T)dk;
+        if (dk != 0.0 && structural_arg(prog->ops[i].opcode, k))
+          return fail(AB_EUNSUPPORTED_OP, "op %u (opcode %u): the differentiated parameter reaches a table argument (index %d); "
+                      "parameter tangents through instance / vertex / sector tables are not supported", i,
+                      (unsigned)prog->ops[i].opcode, k);
+      }
+    }
     cursor = (cursor + (uint32_t)cnt + 3u) & ~3u;
   }
-  kp.n_args = cursor;
+  kp.n_args = grad_mode == AB_GRAD_PARAM ? kParamHalf + cursor : cursor;
+  kp.dargs_off = grad_mode == AB_GRAD_PARAM ? kParamHalf : 0;
 
   std::vector<void*> temp_blobs;
   for (uint32_t b = 0; b < AB_MAX_BLOBS; b++) {
@@ -398,7 +427,8 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
         else rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
       } else rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
     }
-    else rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
+    else if (grad_mode == AB_GRAD_SPATIAL) rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
+    else rc = dispatch_fixed<Dual<Pack<T, WG>, 1>, T, 2, true>(kp, device, st);
     done += chunk;
   }
   for (void* d : temp_blobs) cudaFreeAsync(d, st);

@@ -10,6 +10,7 @@
 // Grid layout (generate_grid, helper_functions.py:23-93): flat k = (ix*ny + iy)*nz + iz, z fastest; the slab is a range
 // of ix planes, i.e. one contiguous range of k. Coordinates are regenerated from (ix,iy,iz): 0 bytes read per point.
 #pragma once
+#include <type_traits>
 #ifndef AB_TIER_FULL
 #define AB_TIER_FULL 2
 #endif
@@ -100,6 +101,7 @@ struct KParams {
   uint32_t n_ops, n_args, n_pslots, n_vslots;
   uint32_t off_args, off_pstack, off_vstack;  // byte offsets inside dynamic shared memory (filled in by the launcher)
   int32_t tier;  // 0 = every op is in the lite set (host-side choice of kernel variant)
+  uint32_t dargs_off;  // AB_GRAD_PARAM: args[dargs_off + i] = d args[i] / d theta (second half of the pool), else 0
   const void* blob[AB_MAX_BLOBS];  // (x, y, z, 0) records of T
   uint32_t blob_count[AB_MAX_BLOBS];
   uint2 ops[AB_MAX_OPS];  // kernel-side encoding: x = dense opcode (a full word), y = argument offset | a << 16 | b << 24
@@ -322,7 +324,7 @@ __host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((si
 // small table (twist, bend, rotational symmetry, instancing, Boltzmann combines, post-processing maps, cones, arcs,
 // n-gons ...) at 90 registers; TIER 2 adds the widest primitives (triangles, quads, sectors, polylines, point clouds).
 // minimum resident CTAs per SM asked of the register allocator, per tier (128-thread CTAs): lite 6, mid 5, full 4
-template <typename S, typename T, int TIER>
+template <typename S, typename T, int TIER, bool PARAM = false>
 __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 6 : 4)) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
   static_assert(TIER == AB_TIER_FULL, "one tier per translation unit");
   constexpr int W = S::width;
@@ -455,7 +457,11 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 6 : 4)) ab_i
       const uint2 w = s_ops[pc];
       const uint32_t code = AB_DISPATCH_BRX ? w.x : (w.x & 0xffu);
       const int sa = (int)((w.y >> 16) & 0xffu), sb = (int)(w.y >> 24);
-      const T* a = reinterpret_cast<const T*>(__builtin_assume_aligned(s_args + (w.y & 0xffffu), 16));
+      const T* a_val = reinterpret_cast<const T*>(__builtin_assume_aligned(s_args + (w.y & 0xffffu), 16));
+      // PARAM: every argument is read as a dual number carrying d arg / d theta (ab_ops.cuh, ArgD)
+      typename std::conditional<PARAM, ArgD<S>, const T*>::type a;
+      if constexpr (PARAM) a = ArgD<S>{a_val, a_val + kp.dargs_off};
+      else a = a_val;
       switch (code) {
         case D_END: break;
         case D_SAVE_P:
@@ -530,15 +536,15 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 6 : 4)) ab_i
         case D_EXTRUDE_END: acc = op_extrude_end<S, T>(acc, SK::ld(vstack, sa, NT)); break;
         // post-processing (post_processing.py:380-560)
 #if AB_TIER_FULL
-        case D_PP_SIGMOID: acc = div_(constant_like(acc, a[0]), exp_(acc * (T(4) * s_rcp(a[1]))) + T(1)); break;
+        case D_PP_SIGMOID: acc = div_(constant_like(acc, a[0]), exp_(acc * (T(4) * rcp_arg(a[1]))) + T(1)); break;
 #endif
 #if AB_TIER_FULL
         case D_PP_POS_SIGMOID:
-          acc = div_(constant_like(acc, a[0]), exp_((acc - a[1]) * (T(4) * s_rcp(a[1]))) + T(1));
+          acc = div_(constant_like(acc, a[0]), exp_((acc - a[1]) * (T(4) * rcp_arg(a[1]))) + T(1));
           break;
 #endif
 #if AB_TIER_FULL
-        case D_PP_CAPPED_EXP: acc = min_(exp_(acc * (T(-4) * s_rcp(a[1]))), T(1)) * a[0]; break;
+        case D_PP_CAPPED_EXP: acc = min_(exp_(acc * (T(-4) * rcp_arg(a[1]))), T(1)) * a[0]; break;
 #endif
 #if AB_TIER_FULL
         case D_PP_HARD_BIN:
@@ -546,32 +552,32 @@ __global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 6 : 4)) ab_i
           break;
 #endif
 #if AB_TIER_FULL
-        case D_PP_LINEAR: acc = clamp_(T(1) - acc * s_rcp(a[1]), T(0), T(1)) * a[0]; break;
+        case D_PP_LINEAR: acc = clamp_(T(1) - acc * rcp_arg(a[1]), T(0), T(1)) * a[0]; break;
 #endif
 #if AB_TIER_FULL
-        case D_PP_RELU: acc = max_(acc * s_rcp(a[0]), T(0)); break;
+        case D_PP_RELU: acc = max_(acc * rcp_arg(a[0]), T(0)); break;
 #endif
 #if AB_TIER_FULL
         case D_PP_SMOOTH_RELU: {
-          S v = acc * s_rcp(a[1]);
+          S v = acc * rcp_arg(a[1]);
           acc = (v + sqrt_(fma_(v, v, constant_like(v, a[0])))) * T(0.5);
         } break;
 #endif
 #if AB_TIER_FULL
         case D_PP_SLOWSTART: {
-          S v = max_(acc * s_rcp(a[0]), T(0));
+          S v = max_(acc * rcp_arg(a[0]), T(0));
           acc = sqrt_(fma_(v, v, constant_like(v, a[1]))) - a[2];
         } break;
 #endif
 #if AB_TIER_FULL
         case D_PP_GAUSS_BOUNDARY: {
-          S v = acc * s_rcp(a[1]);
+          S v = acc * rcp_arg(a[1]);
           acc = exp_(v * v * T(-4)) * a[0];
         } break;
 #endif
 #if AB_TIER_FULL
         case D_PP_GAUSS_FALLOFF: {
-          S v = max_(acc, T(0)) * s_rcp(a[1]);
+          S v = max_(acc, T(0)) * rcp_arg(a[1]);
           acc = exp_(v * v * T(-4)) * a[0];
         } break;
 #endif
@@ -680,7 +686,7 @@ struct LaunchCfg {
   size_t smem_optin;
 };
 // returns cudaSuccess or the CUDA error; *status is AB_OK / AB_ETOOLARGE
-template <typename S, typename T, int TIER>
+template <typename S, typename T, int TIER, bool PARAM = false>
 cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream_t st, int* status);
 
 inline int op_tier(int ab_opcode);
@@ -712,7 +718,7 @@ inline int op_tier(int ab_opcode) {
 }
 
 #ifdef AB_INTERP_INSTANTIATE
-template <typename S, typename T, int TIER>
+template <typename S, typename T, int TIER, bool PARAM>
 cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream_t st, int* status) {
   typedef StackOf<S> SK;
   *status = AB_OK;
@@ -727,7 +733,7 @@ cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream
     *status = AB_ETOOLARGE;
     return cudaSuccess;
   }
-  auto kern = ab_interp_kernel<S, T, TIER>;
+  auto kern = ab_interp_kernel<S, T, TIER, PARAM>;
   cudaError_t e;
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -602,6 +602,18 @@ AB_DEV Dual<P, K> mod_(const Dual<P, K>& a, AB_DUAL_T b) {
   r.v = mod_(a.v, b);
   return r;
 }
+// floor-mod by a dual divisor: a - b floor(a/b); the quotient is piecewise constant
+template <typename P, int K>
+AB_DEV Dual<P, K> mod_(const Dual<P, K>& a, const Dual<P, K>& b) {
+  Dual<P, K> r;
+  r.v = mod_(a.v, b.v);
+  const P q = floor_(div_(a.v, b.v));
+#pragma unroll
+  AB_DK r.d[k] = a.d[k] - q * b.d[k];
+  return r;
+}
+template <typename P, int K>
+AB_DEV Dual<P, K> constant_like(const Dual<P, K>&, const Dual<P, K>& c) { return c; }
 template <typename P, int K>
 AB_DEV Dual<P, K> pow_(const Dual<P, K>& a, AB_DUAL_T b) {  // a >= 0
   Dual<P, K> r;
@@ -656,8 +668,8 @@ AB_DEV P value_sign(const Dual<P, K>& a) { return sign_(a.v); }
 // ------------------------------------------------------------------------------------------------------------------
 // shared helpers written once for both kinds of S
 
-template <typename S, typename T>
-AB_DEV S clamp_(const S& a, T lo, T hi) { return min_(max_(a, lo), hi); }
+template <typename S, typename L, typename H>
+AB_DEV S clamp_(const S& a, const L& lo, const H& hi) { return min_(max_(a, lo), hi); }
 template <typename S>
 AB_DEV S norm2_(const S& a, const S& b) { return sqrt_(fma_(a, a, b * b)); }
 template <typename S>

@@ -11,11 +11,43 @@ struct Pt {
   S x, y, z;
 };
 
+// ---- argument access ------------------------------------------------------------------------------------------------
+// Ops read their arguments through `A a`: either a plain `const T*` (value / spatial-gradient kernels: a[i] is a scalar)
+// or ArgD<S> (parameter-tangent kernel, AB_GRAD_PARAM: a[i] is a dual number whose tangent is d arg_i / d theta, so the
+// op bodies below propagate d/d theta through every arithmetic use of a parameter without being rewritten).
+template <typename S>
+struct ArgD {
+  typedef typename S::scalar T;
+  const T* v;
+  const T* d;
+  AB_DEV S operator[](int i) const {
+    S r(v[i]);
+    r.d[0] = decltype(r.v)(d[i]);
+    return r;
+  }
+  AB_DEV ArgD operator+(int k) const { return ArgD{v + k, d + k}; }
+};
+template <typename T>
+AB_DEV const T* raw_args(const T* a) { return a; }  // tables (instances, polylines, vertices) carry no tangents
+template <typename S>
+AB_DEV const typename S::scalar* raw_args(const ArgD<S>& a) { return a.v; }
+// uniform value of an argument (for counts, flags and branch selection)
+AB_DEV float aval(float x) { return x; }
+AB_DEV double aval(double x) { return x; }
+template <typename P, int K>
+AB_DEV typename P::scalar aval(const Dual<P, K>& x) { return x.v.v[0]; }
+// reciprocal of an argument
+AB_DEV float rcp_arg(float x) { return s_rcp(x); }
+AB_DEV double rcp_arg(double x) { return s_rcp(x); }
+template <typename P, int K>
+AB_DEV Dual<P, K> rcp_arg(const Dual<P, K>& x) { return div_(Dual<P, K>(typename P::scalar(1)), x); }
+
 // ---- coordinate ops -------------------------------------------------------------------------------------------------
 
 // p = M p + b : folded apply_ec_transforms (transformations.py:232-242), shears, frames
-template <typename S, typename T>
-AB_DEV void op_affine(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_affine(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   S nx = fma_(p.x, a[0], fma_(p.y, a[1], fma_(p.z, a[2], a[9])));
   S ny = fma_(p.x, a[3], fma_(p.y, a[4], fma_(p.z, a[5], a[10])));
   S nz = fma_(p.x, a[6], fma_(p.y, a[7], fma_(p.z, a[8], a[11])));
@@ -23,28 +55,32 @@ AB_DEV void op_affine(Pt<S>& p, const T* a) {
   p.y = ny;
   p.z = nz;
 }
-template <typename S, typename T>
-AB_DEV void op_translate(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_translate(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   p.x = p.x + a[0];
   p.y = p.y + a[1];
   p.z = p.z + a[2];
 }
-template <typename S, typename T>
-AB_DEV void op_scale_p(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_scale_p(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   p.x = p.x * a[0];
   p.y = p.y * a[0];
   p.z = p.z * a[0];
 }
 // modifications.py:91-93  q = p - clip(p, -e/2, e/2)
-template <typename S, typename T>
-AB_DEV void op_elongate(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_elongate(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   p.x = p.x - clamp_(p.x, a[0], a[3]);
   p.y = p.y - clamp_(p.y, a[1], a[4]);
   p.z = p.z - clamp_(p.z, a[2], a[5]);
 }
 // modifications.py:516-522
-template <typename S, typename T>
-AB_DEV void op_twist(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_twist(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   S s, c;
   sincos_(p.z * a[0], s, c);
   S nx = c * p.x - s * p.y;
@@ -53,9 +89,10 @@ AB_DEV void op_twist(Pt<S>& p, const T* a) {
   p.y = ny;
 }
 // modifications.py:545-573; args r, angle/2, cos, sin, r*angle/2, r*sin, r*(1-cos), r*(angle/2)
-template <typename S, typename T>
-AB_DEV void op_bend(Pt<S>& p, const T* a) {
-  const T r = a[0], c = a[2], s = a[3], thr = a[4], rs = a[5], r1c = a[6], rha = a[7];
+template <typename S, typename A>
+AB_DEV void op_bend(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
+  const auto r = a[0], c = a[2], s = a[3], thr = a[4], rs = a[5], r1c = a[6], rha = a[7];
   S qy = p.y - r;
   S phi = atan2_(p.x, -qy);
   S ny = norm2_(p.x, qy) - r;
@@ -77,17 +114,20 @@ AB_DEV void op_bend(Pt<S>& p, const T* a) {
   p.y = ny;
 }
 // modifications.py:991-993
-template <typename S, typename T>
-AB_DEV void op_absx_sub(Pt<S>& p, const T* a) { p.x = abs_(p.x) - a[0]; }
+template <typename S, typename A>
+AB_DEV void op_absx_sub(Pt<S>& p, A a) { typedef typename S::scalar T; p.x = abs_(p.x) - a[0]; }
 // modifications.py:1023-1029 (pre-rotation emitted as AFFINE); args angle, radius, n_sectors, pad, (cos, sin)[n_sectors].
 // The reference maps phi -> mod(phi, angle) - angle/2 and rebuilds (r cos, r sin); that is a rotation by
 // -theta_k, theta_k = k*angle + angle/2, k = floor(phi/angle): the sector comes from atan2, the rotation from the
 // host-computed table (fewer roundings than the polar round trip, no sqrt / sincos / mod).
-template <typename S, typename T>
-AB_DEV void op_rotsym(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_rotsym(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   constexpr int W = S::width;
-  const T ang = a[0], rad = a[1];
-  const int nsec = (int)a[2];
+  const T* tab = raw_args(a);  // angle and sector table are structural: no parameter tangent flows through them
+  const T ang = tab[0];
+  const auto rad = a[1];
+  const int nsec = (int)tab[2];
   const T inv = s_rcp(ang);
   auto vx = value_of(p.x), vy = value_of(p.y);
   const Pack<T, W> ph = atan2_(vy, vx);
@@ -101,8 +141,8 @@ AB_DEV void op_rotsym(Pt<S>& p, const T* a) {
     // one more exact step: phi*inv may round across an integer
     if (phi < (T)k * ang && k > 0) k--;
     else if (phi >= (T)(k + 1) * ang && k + 1 < nsec) k++;
-    c.v[i] = a[4 + 2 * k];
-    s.v[i] = a[5 + 2 * k];
+    c.v[i] = tab[4 + 2 * k];
+    s.v[i] = tab[5 + 2 * k];
   }
   S nx = mul_lane(p.x, c) + mul_lane(p.y, s) - rad;
   S ny = mul_lane(p.y, c) - mul_lane(p.x, s);
@@ -110,15 +150,17 @@ AB_DEV void op_rotsym(Pt<S>& p, const T* a) {
   p.y = ny;
 }
 // modifications.py:427-431
-template <typename S, typename T>
-AB_DEV void op_revolve(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_revolve(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   p.x = norm2_(p.x, p.z) - a[0];
   p.z = constant_like(p.z, T(0));
 }
 // modifications.py:455-467; args radius, cos, sin
-template <typename S, typename T>
-AB_DEV void op_axis_revolve(Pt<S>& p, const T* a) {
-  const T rad = a[0], c = a[1], s = a[2];
+template <typename S, typename A>
+AB_DEV void op_axis_revolve(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
+  const auto rad = a[0], c = a[1], s = a[2];
   S xr = fma_(p.x, c, p.y * s);
   S yr = fma_(p.y, c, -(p.x * s));
   S m = norm2_(xr, p.z);
@@ -127,30 +169,34 @@ AB_DEV void op_axis_revolve(Pt<S>& p, const T* a) {
   p.z = constant_like(p.z, T(0));
 }
 // modifications.py:819-820; args d(3), d/2(3)
-template <typename S, typename T>
-AB_DEV void op_rep_inf(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_rep_inf(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   p.x = mod_(p.x + a[3], a[0]) - a[3];
   p.y = mod_(p.y + a[4], a[1]) - a[4];
   p.z = mod_(p.z + a[5], a[2]) - a[5];
 }
 // modifications.py:847-868 per axis; args c(3), d(3), s(3), s/2(3)
-template <typename S, typename T>
-AB_DEV S rep_fin_axis(const S& q, T c, T d, T s, T sh) {
+template <typename S, typename U>
+AB_DEV S rep_fin_axis(const S& q, const U& c, const U& d, const U& s, const U& sh) {
+  typedef typename S::scalar T;
   Mask<S::width> inner = ge_(q, -d) & le_(q, d);
   S v = abs_(q) - c;
   v = select_(lt_(q, T(0)), -v, v);
   S u = mod_(q - d, s) - sh;
   return select_(inner, u, v);
 }
-template <typename S, typename T>
-AB_DEV void op_rep_fin(Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV void op_rep_fin(Pt<S>& p, A a) {
+  typedef typename S::scalar T;
   p.x = rep_fin_axis(p.x, a[0], a[3], a[6], a[9]);
   p.y = rep_fin_axis(p.y, a[1], a[4], a[7], a[10]);
   p.z = rep_fin_axis(p.z, a[2], a[5], a[8], a[11]);
 }
 // modifications.py:1069-1083 (frame emitted as AFFINE); args l/2, s, d, lo, hi, off ; inner = (n > 2)
-template <typename S, typename T>
-AB_DEV void op_lin_inst(Pt<S>& p, const T* a, int inner_on) {
+template <typename S, typename A>
+AB_DEV void op_lin_inst(Pt<S>& p, A a, int inner_on) {
+  typedef typename S::scalar T;
   S v = abs_(p.x) - a[0];
   v = select_(lt_(p.x, T(0)), -v, v);
   if (inner_on) {
@@ -167,11 +213,13 @@ AB_DEV void op_lin_inst(Pt<S>& p, const T* a, int inner_on) {
 // reference point C; with R = max distance of the warp's points from C, instance j can only win if
 // d(C, j) <= min_j d(C, j) + 2R (triangle inequality). Every thread then scans just that candidate list for its W points.
 // Cost ~ n/32 + (#candidates) per point instead of n; scattered point sets degrade gracefully to the full scan.
-template <typename S, typename T>
-AB_DEV void op_curve_inst(Pt<S>& p, const T* a, int mode) {
-  const int n = (int)a[0];
+template <typename S, typename A>
+AB_DEV void op_curve_inst(Pt<S>& p, A a, int mode) {
+  typedef typename S::scalar T;
+  const T* tab = raw_args(a);  // instance table: structural (no parameter tangents)
+  const int n = (int)tab[0];
   const int stride = mode ? 12 : 3;
-  const T* rec = a + 4;  // records start on a 16-byte boundary
+  const T* rec = tab + 4;  // records start on a 16-byte boundary
   constexpr int W = S::width;
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -260,52 +308,55 @@ AB_DEV S op_extrude_end(const S& d, const S& w1) {
 }
 
 // ---- combine ops (combine.py:12-78) --------------------------------------------------------------------------------------
-template <typename S, typename T>
-AB_DEV S smin_poly2(const S& x, const S& y, T w) {  // combine.py:12-18
-  S h = max_(w - abs_(x - y), T(0)) * s_rcp(w);
+template <typename S, typename U>
+AB_DEV S smin_poly2(const S& x, const S& y, const U& w) {  // combine.py:12-18
+  typedef typename S::scalar T;
+  S h = max_(w - abs_(x - y), T(0)) * rcp_arg(w);
   return min_(x, y) - h * h * (w * T(0.25));
 }
-template <typename S, typename T>
-AB_DEV S smin_poly3(const S& x, const S& y, T w) {  // combine.py:20-26
-  S h = max_(w - abs_(x - y), T(0)) * s_rcp(w);
+template <typename S, typename U>
+AB_DEV S smin_poly3(const S& x, const S& y, const U& w) {  // combine.py:20-26
+  typedef typename S::scalar T;
+  S h = max_(w - abs_(x - y), T(0)) * rcp_arg(w);
   return min_(x, y) - h * h * h * (w * T(1.0 / 6.0));
 }
 // combine.py:29-34, evaluated in the shifted form (x e^{(x-m)/a} + y e^{(y-m)/a}) / (e^{(x-m)/a} + e^{(y-m)/a}),
 // m = max(x,y): algebraically identical, but does not overflow in fp32 where exp(x/a) would for x/a > 88.
-template <typename S, typename T>
-AB_DEV S smax_boltz(const S& x, const S& y, T w) {
-  const T iw = s_rcp(w);
-  S m = (w > T(0)) ? max_(x, y) : min_(x, y);
+template <typename S, typename U>
+AB_DEV S smax_boltz(const S& x, const S& y, const U& w) {
+  typedef typename S::scalar T;
+  const U iw = rcp_arg(w);
+  S m = (aval(w) > T(0)) ? max_(x, y) : min_(x, y);
   S e1 = exp_((x - m) * iw);
   S e2 = exp_((y - m) * iw);
   return div_(x * e1 + y * e2, e1 + e2);
 }
 
 // ---- 3D primitives (sdf_3D.py) ----------------------------------------------------------------------------------------------
-template <typename S, typename T>
-AB_DEV S prim_sphere(const Pt<S>& p, const T* a) { return norm3_(p.x, p.y, p.z) - a[0]; }  // :25-27
-template <typename S, typename T>
-AB_DEV S prim_cylinder(const Pt<S>& p, const T* a) {  // :30-37 ; args radius, height/2
+template <typename S, typename A>
+AB_DEV S prim_sphere(const Pt<S>& p, A a) { typedef typename S::scalar T; return norm3_(p.x, p.y, p.z) - a[0]; }  // :25-27
+template <typename S, typename A>
+AB_DEV S prim_cylinder(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :30-37 ; args radius, height/2
   S d0 = norm2_(p.x, p.y) - a[0];
   S d1 = abs_(p.z) - a[1];
   return min_(max_(d0, d1), T(0)) + norm2_(max_(d0, T(0)), max_(d1, T(0)));
 }
-template <typename S, typename T>
-AB_DEV S prim_box(const Pt<S>& p, const T* a) {  // :40-47 ; args half sizes
+template <typename S, typename A>
+AB_DEV S prim_box(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :40-47 ; args half sizes
   S q0 = abs_(p.x) - a[0], q1 = abs_(p.y) - a[1], q2 = abs_(p.z) - a[2];
   return norm3_(max_(q0, T(0)), max_(q1, T(0)), max_(q2, T(0))) + min_(max_(q0, max_(q1, q2)), T(0));
 }
-template <typename S, typename T>
-AB_DEV S prim_torus(const Pt<S>& p, const T* a) {  // :50-53
+template <typename S, typename A>
+AB_DEV S prim_torus(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :50-53
   return norm2_(norm2_(p.x, p.y) - a[0], p.z) - a[1];
 }
-template <typename S, typename T>
-AB_DEV S prim_chainlink(const Pt<S>& p, const T* a) {  // :56-61 ; args R, r, length/2
+template <typename S, typename A>
+AB_DEV S prim_chainlink(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :56-61 ; args R, r, length/2
   S xx = p.x - clamp_(p.x, -a[2], a[2]);
   return norm2_(norm2_(xx, p.y) - a[0], p.z) - a[1];
 }
-template <typename S, typename T>
-AB_DEV S prim_braid(const Pt<S>& p, const T* a) {  // :64-75 ; args length/2, R, r, pitch
+template <typename S, typename A>
+AB_DEV S prim_braid(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :64-75 ; args length/2, R, r, pitch
   S s, c;
   sincos_(p.z * a[3], s, c);
   S xr = c * p.x - s * p.y;
@@ -315,8 +366,9 @@ AB_DEV S prim_braid(const Pt<S>& p, const T* a) {  // :64-75 ; args length/2, R,
 }
 // shared by sdf_arc (sdf_2D.py:85-102) and sdf_arc_3d (sdf_3D.py:78-96): rotate by the centre angle, fold, subtract
 // the closest point on the arc. args C, S, R, ea
-template <typename S, typename T>
-AB_DEV void arc_core(const S& x, const S& y, T C, T Sn, T R, T ea, S& dx, S& dy) {
+template <typename S, typename U>
+AB_DEV void arc_core(const S& x, const S& y, const U& C, const U& Sn, const U& R, const U& ea, S& dx, S& dy) {
+  typedef typename S::scalar T;
   S xr = fma_(x, C, y * Sn);
   S yr = abs_(fma_(y, C, -(x * Sn)));
   S psi = clamp_(atan2_(yr, xr), T(0), ea);
@@ -325,40 +377,40 @@ AB_DEV void arc_core(const S& x, const S& y, T C, T Sn, T R, T ea, S& dx, S& dy)
   dx = xr - c * R;
   dy = yr - s * R;
 }
-template <typename S, typename T>
-AB_DEV S prim_arc3d(const Pt<S>& p, const T* a) {  // args R, r, C, S, ea
+template <typename S, typename A>
+AB_DEV S prim_arc3d(const Pt<S>& p, A a) { typedef typename S::scalar T;  // args R, r, C, S, ea
   S dx, dy;
   arc_core(p.x, p.y, a[2], a[3], a[0], a[4], dx, dy);
   return norm3_(dx, dy, p.z) - a[1];
 }
-template <typename S, typename T>
-AB_DEV S prim_plane(const Pt<S>& p, const T* a) {  // :99-102
+template <typename S, typename A>
+AB_DEV S prim_plane(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :99-102
   return fma_(p.x, a[0], fma_(p.y, a[1], p.z * a[2])) - a[3];
 }
-template <typename S, typename T>
-AB_DEV S prim_uplane(const Pt<S>& p, const T* a) {  // :105-108
+template <typename S, typename A>
+AB_DEV S prim_uplane(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :105-108
   return abs_(fma_(p.x, a[0], fma_(p.y, a[1], p.z * a[2]))) - a[3];
 }
-template <typename S, typename T>
-AB_DEV S prim_segment(const Pt<S>& p, const T* a) {  // :111-118 ; args a(3), ba(3), dot(ba,ba)
+template <typename S, typename A>
+AB_DEV S prim_segment(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :111-118 ; args a(3), ba(3), dot(ba,ba)
   S px = p.x - a[0], py = p.y - a[1], pz = p.z - a[2];
-  S h = clamp_(fma_(px, a[3], fma_(py, a[4], pz * a[5])) * s_rcp(a[6]), T(0), T(1));
+  S h = clamp_(fma_(px, a[3], fma_(py, a[4], pz * a[5])) * rcp_arg(a[6]), T(0), T(1));
   return norm3_(px - h * a[3], py - h * a[4], pz - h * a[5]);
 }
-template <typename S, typename T>
-AB_DEV S prim_cone(const Pt<S>& p, const T* a) {  // :121-136 ; args q0, q1, zoff, dot(q,q)
-  const T q0 = a[0], q1 = a[1];
+template <typename S, typename A>
+AB_DEV S prim_cone(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :121-136 ; args q0, q1, zoff, dot(q,q)
+  const auto q0 = a[0], q1 = a[1];
   S w0 = norm2_(p.x, p.y), w1 = p.z - a[2];
-  S t = clamp_(fma_(w0, q0, w1 * q1) * s_rcp(a[3]), T(0), T(1));
+  S t = clamp_(fma_(w0, q0, w1 * q1) * rcp_arg(a[3]), T(0), T(1));
   S a0 = w0 - t * q0, a1 = w1 - t * q1;
-  S b0 = w0 - clamp_(w0 * s_rcp(q0), T(0), T(1)) * q0, b1 = w1 - q1;
+  S b0 = w0 - clamp_(w0 * rcp_arg(q0), T(0), T(1)) * q0, b1 = w1 - q1;
   S d = min_(fma_(a0, a0, a1 * a1), fma_(b0, b0, b1 * b1));
   S s = max_(-(w0 * q1 - w1 * q0), -(w1 - q1));
   return mul_lane(sqrt_(d), value_sign(s));
 }
-template <typename S, typename T>
-AB_DEV S prim_inf_cone(const Pt<S>& p, const T* a, bool oriented) {  // :139-157 ; args sin, cos
-  const T v0 = a[0], v1 = a[1];
+template <typename S, typename A>
+AB_DEV S prim_inf_cone(const Pt<S>& p, A a, bool oriented) { typedef typename S::scalar T;  // :139-157 ; args sin, cos
+  const auto v0 = a[0], v1 = a[1];
   S q0 = norm2_(p.x, p.y), q1 = -p.z;
   S t = max_(fma_(q0, v0, q1 * v1), T(0));
   S d = norm2_(q0 - t * v0, q1 - t * v1);
@@ -366,8 +418,9 @@ AB_DEV S prim_inf_cone(const Pt<S>& p, const T* a, bool oriented) {  // :139-157
   return d;
 }
 // shared by sdf_sector (sdf_2D.py:105-129) and sdf_solid_angle (sdf_3D.py:160-183) after rotation + fold
-template <typename S, typename T>
-AB_DEV S sector_core(const S& x, const S& y, T radius, T ad, T cad, T sad) {
+template <typename S, typename U>
+AB_DEV S sector_core(const S& x, const S& y, const U& radius, const U& ad, const U& cad, const U& sad) {
+  typedef typename S::scalar T;
   S phi = atan2_(y, x);
   S psi = clamp_(phi, T(0), ad);
   S s, c;
@@ -379,8 +432,8 @@ AB_DEV S sector_core(const S& x, const S& y, T radius, T ad, T cad, T sad) {
   S out = min_(m, length);
   return select_(msk, -out, out);
 }
-template <typename S, typename T>
-AB_DEV S prim_solid_angle(const Pt<S>& p, const T* a) {  // args radius, C, S, ad, cos ad, sin ad
+template <typename S, typename A>
+AB_DEV S prim_solid_angle(const Pt<S>& p, A a) { typedef typename S::scalar T;  // args radius, C, S, ad, cos ad, sin ad
   S xr = fma_(p.x, a[1], p.y * a[2]);
   S yr = norm2_(fma_(p.y, a[1], -(p.x * a[2])), p.z);
   return sector_core(xr, yr, a[0], a[3], a[4], a[5]);
@@ -393,8 +446,9 @@ AB_DEV S edge_sq(const T* s, T ss, const S& x, const S& y, const S& z) {  // one
   S t0 = h * s[0] - x, t1 = h * s[1] - y, t2 = h * s[2] - z;
   return fma_(t0, t0, fma_(t1, t1, t2 * t2));
 }
-template <typename S, typename T>
-AB_DEV S prim_triangle3d(const Pt<S>& p, const T* g) {  // :186-214 ; layout in program.py
+template <typename S, typename A>
+AB_DEV S prim_triangle3d(const Pt<S>& p, A g_) { typedef typename S::scalar T;  // :186-214 ; layout in program.py
+  const T* g = raw_args(g_);  // vertex-derived table: structural
   S ax = p.x - g[0], ay = p.y - g[1], az = p.z - g[2];
   S bx = p.x - g[3], by = p.y - g[4], bz = p.z - g[5];
   S cx = p.x - g[6], cy = p.y - g[7], cz = p.z - g[8];
@@ -403,11 +457,12 @@ AB_DEV S prim_triangle3d(const Pt<S>& p, const T* g) {  // :186-214 ; layout in 
   S ex1 = min_(min_(edge_sq(g + 9, g[30], ax, ay, az), edge_sq(g + 12, g[31], bx, by, bz)),
                edge_sq(g + 15, g[32], cx, cy, cz));
   S dn = dot3(g + 18, ax, ay, az);
-  S ex2 = dn * dn * s_rcp(g[33]);
+  S ex2 = dn * dn * rcp_arg(g[33]);
   return sqrt_(select_(lt_(sg, T(2)), ex1, ex2));
 }
-template <typename S, typename T>
-AB_DEV S prim_quad3d(const Pt<S>& p, const T* g) {  // :217-250
+template <typename S, typename A>
+AB_DEV S prim_quad3d(const Pt<S>& p, A g_) { typedef typename S::scalar T;  // :217-250
+  const T* g = raw_args(g_);
   S ax = p.x - g[0], ay = p.y - g[1], az = p.z - g[2];
   S bx = p.x - g[3], by = p.y - g[4], bz = p.z - g[5];
   S cx = p.x - g[6], cy = p.y - g[7], cz = p.z - g[8];
@@ -417,11 +472,12 @@ AB_DEV S prim_quad3d(const Pt<S>& p, const T* g) {  // :217-250
   S ex1 = min_(min_(edge_sq(g + 21, g[42], dx, dy, dz), edge_sq(g + 18, g[41], cx, cy, cz)),
                min_(edge_sq(g + 12, g[39], ax, ay, az), edge_sq(g + 15, g[40], bx, by, bz)));
   S dn = dot3(g + 24, ax, ay, az);
-  S ex2 = dn * dn * s_rcp(g[43]);
+  S ex2 = dn * dn * rcp_arg(g[43]);
   return sqrt_(select_(lt_(sg, T(3)), ex1, ex2));
 }
-template <typename S, typename T>
-AB_DEV S prim_segline(const Pt<S>& p, const T* a, int dim) {  // sdf_3D.py:264-271 / sdf_2D.py:191-198
+template <typename S, typename A>
+AB_DEV S prim_segline(const Pt<S>& p, A a_, int dim) { typedef typename S::scalar T;  // sdf_3D.py:264-271 / sdf_2D.py:191-198
+  const T* a = raw_args(a_);  // vertex table: structural
   const int n = (int)a[0];
   const T* pts = a + 1;
   S best = constant_like(p.x, T(1e32));  // squared: the reference starts from 1e16 on the distance
@@ -448,30 +504,31 @@ AB_DEV S prim_segline(const Pt<S>& p, const T* a, int dim) {  // sdf_3D.py:264-2
 }
 
 // ---- 2D primitives (sdf_2D.py) ----------------------------------------------------------------------------------------------
-template <typename S, typename T>
-AB_DEV S prim_circle(const Pt<S>& p, const T* a) { return norm2_(p.x, p.y) - a[0]; }  // :12-14
-template <typename S, typename T>
-AB_DEV S prim_neu_circle(const Pt<S>& p, const T* a) {  // :17-19 ; args radius, order
-  const T ord = a[1];
+template <typename S, typename A>
+AB_DEV S prim_circle(const Pt<S>& p, A a) { typedef typename S::scalar T; return norm2_(p.x, p.y) - a[0]; }  // :12-14
+template <typename S, typename A>
+AB_DEV S prim_neu_circle(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :17-19 ; args radius, order
+  const T ord = aval(a[1]);
   S ax = abs_(p.x), ay = abs_(p.y);
   if (isinf(ord)) return max_(ax, ay) - a[0];
   if (ord == T(1)) return ax + ay - a[0];
   if (ord == T(2)) return norm2_(ax, ay) - a[0];
   return pow_(pow_(ax, ord) + pow_(ay, ord), s_rcp(ord)) - a[0];
 }
-template <typename S, typename T>
-AB_DEV S prim_box2d(const Pt<S>& p, const T* a) {  // :22-28
+template <typename S, typename A>
+AB_DEV S prim_box2d(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :22-28
   S d0 = abs_(p.x) - a[0], d1 = abs_(p.y) - a[1];
   return norm2_(max_(d0, T(0)), max_(d1, T(0))) + min_(max_(d0, d1), T(0));
 }
-template <typename S, typename T>
-AB_DEV S prim_segment2d(const Pt<S>& p, const T* a) {  // :31-38 ; args a(2), ba(2), dot
+template <typename S, typename A>
+AB_DEV S prim_segment2d(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :31-38 ; args a(2), ba(2), dot
   S px = p.x - a[0], py = p.y - a[1];
-  S h = clamp_(fma_(px, a[2], py * a[3]) * s_rcp(a[4]), T(0), T(1));
+  S h = clamp_(fma_(px, a[2], py * a[3]) * rcp_arg(a[4]), T(0), T(1));
   return norm2_(px - h * a[2], py - h * a[3]);
 }
-template <typename S, typename T>
-AB_DEV S prim_rbox2d(const Pt<S>& p, const T* a) {  // :41-57 ; args hx, hy, r0..r3
+template <typename S, typename A>
+AB_DEV S prim_rbox2d(const Pt<S>& p, A a_) { typedef typename S::scalar T;  // :41-57 ; args hx, hy, r0..r3
+  const T* a = raw_args(a_);  // per-quadrant radius selection: structural
   constexpr int W = S::width;
   auto vx = value_of(p.x), vy = value_of(p.y);
   Pack<T, W> r;
@@ -481,14 +538,15 @@ AB_DEV S prim_rbox2d(const Pt<S>& p, const T* a) {  // :41-57 ; args hx, hy, r0.
   S d0 = add_lane(abs_(p.x) - a[0], r), d1 = add_lane(abs_(p.y) - a[1], r);
   return norm2_(max_(d0, T(0)), max_(d1, T(0))) + add_lane(min_(max_(d0, d1), T(0)), -r);
 }
-template <typename S, typename T>
-AB_DEV S prim_triangle2d(const Pt<S>& p, const T* g) {  // :60-82 ; args p0,p1,p2,e0,e1,e2,ee(3),s
+template <typename S, typename A>
+AB_DEV S prim_triangle2d(const Pt<S>& p, A g_) { typedef typename S::scalar T;  // :60-82 ; args p0,p1,p2,e0,e1,e2,ee(3),s
+  const T* g = raw_args(g_);  // vertex-derived table: structural
   S d0, d1;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     const T ex = g[6 + 2 * i], ey = g[7 + 2 * i];
     S v0 = p.x - g[2 * i], v1 = p.y - g[2 * i + 1];
-    S h = clamp_(fma_(v0, ex, v1 * ey) * s_rcp(g[12 + i]), T(0), T(1));
+    S h = clamp_(fma_(v0, ex, v1 * ey) * rcp_arg(g[12 + i]), T(0), T(1));
     S q0 = v0 - h * ex, q1 = v1 - h * ey;
     S dd = fma_(q0, q0, q1 * q1);
     S cr = (v0 * ey - v1 * ex) * g[15];
@@ -502,20 +560,20 @@ AB_DEV S prim_triangle2d(const Pt<S>& p, const T* g) {  // :60-82 ; args p0,p1,p
   }
   return -mul_lane(sqrt_(d0), value_sign(d1));
 }
-template <typename S, typename T>
-AB_DEV S prim_arc(const Pt<S>& p, const T* a) {  // :85-102 ; args R, C, S, ea
+template <typename S, typename A>
+AB_DEV S prim_arc(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :85-102 ; args R, C, S, ea
   S dx, dy;
   arc_core(p.x, p.y, a[1], a[2], a[0], a[3], dx, dy);
   return norm2_(dx, dy);
 }
-template <typename S, typename T>
-AB_DEV S prim_sector(const Pt<S>& p, const T* a) {  // :105-129
+template <typename S, typename A>
+AB_DEV S prim_sector(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :105-129
   S xr = fma_(p.x, a[1], p.y * a[2]);
   S yr = abs_(fma_(p.y, a[1], -(p.x * a[2])));
   return sector_core(xr, yr, a[0], a[3], a[4], a[5]);
 }
-template <typename S, typename T>
-AB_DEV S prim_inf_sector(const Pt<S>& p, const T* a) {  // :132-150 ; args C, S, ad, cos ad, sin ad
+template <typename S, typename A>
+AB_DEV S prim_inf_sector(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :132-150 ; args C, S, ad, cos ad, sin ad
   S xr = fma_(p.x, a[0], p.y * a[1]);
   S yr = abs_(fma_(p.y, a[0], -(p.x * a[1])));
   S phi = atan2_(yr, xr);
@@ -523,8 +581,8 @@ AB_DEV S prim_inf_sector(const Pt<S>& p, const T* a) {  // :132-150 ; args C, S,
   S m = norm2_(xr - t * a[3], yr - t * a[4]);
   return mul_lane(m, value_sign(phi - a[2]));
 }
-template <typename S, typename T>
-AB_DEV S prim_ngon(const Pt<S>& p, const T* a) {  // :153-177 ; args radius, alpha, tx, ty, nox, noy, l
+template <typename S, typename A>
+AB_DEV S prim_ngon(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :153-177 ; args radius, alpha, tx, ty, nox, noy, l
   S phi = atan2_(p.y, p.x);
   phi = select_(lt_(phi, T(0)), phi + T(6.283185307179586476925286766559), phi);
   phi = mod_(phi, a[1]);
@@ -540,9 +598,11 @@ AB_DEV S prim_ngon(const Pt<S>& p, const T* a) {  // :153-177 ; args radius, alp
 // sdf_polygon_2d (sdf_2D.py:201-218) for simple polygons: unsigned distance = min over the closed edge loop, interior
 // by the crossing-number rule (equals the union of the reference's ear-clipping triangles,
 // triangulation_functions.py:390-430). args: n, then n (x, y) vertices.
-template <typename S, typename T>
-AB_DEV S prim_polygon2d(const Pt<S>& p, const T* a) {
+template <typename S, typename A>
+AB_DEV S prim_polygon2d(const Pt<S>& p, A a_) {
+  typedef typename S::scalar T;
   constexpr int W = S::width;
+  const T* a = raw_args(a_);  // vertex table: structural
   const int n = (int)a[0];
   const T* pts = a + 1;
   auto vx = value_of(p.x), vy = value_of(p.y);

@@ -43,7 +43,9 @@ def _grad_mode(grad):
         return cabi.AB_GRAD_NONE, 0
     if grad in (True, "spatial", "xyz"):
         return cabi.AB_GRAD_SPATIAL, 3
-    raise ValueError(f"unknown grad mode {grad!r} (use None or 'spatial')")
+    if grad == "param":
+        return cabi.AB_GRAD_PARAM, 1
+    raise ValueError(f"unknown grad mode {grad!r} (use None, 'spatial' or 'param')")
 
 
 def slab_ranges(n_planes: int, parts: int):
@@ -139,14 +141,38 @@ def create_with_gradient(obj, co, **kw):
 # ---- parameter sensitivities (stand-in for jacfwd(geometry, argnums=k), Code/examples/autodiff/gradient_map_3D.py:84) ----
 
 
-def jacfwd(geometry, argnums=0, *, rel_step=1e-6, device=0):
-    """Returns g(co, *params) -> d field / d params[argnums] for a builder `geometry(*params) -> geometry object`.
+def program_tangent(geometry, params, argnum, rel_step=1e-6):
+    """Flattens geometry(*params) and attaches Program.dargs = d args / d params[argnum].
 
-    The reference obtains this map with JAX forward mode through its jnp twin of the NumPy functions. Here the builder
-    is flattened at params[k] +- h and both programs are evaluated in fp64 on the GPU; the map is their central
-    difference (truncation O(h^2), rounding ~1e-16/h: ~1e-9 relative with the default step). This is a numerical
-    derivative: dual-number ARGUMENT tangents inside the interpreter (AB_GRAD_PARAM) are not built yet, the spatial
-    gradient (grad="spatial") is true forward mode. Every op is supported, including host-folded parameters."""
+    The host-side folding (rotation matrices, frames, sin/cos of constant angles ...) is differentiated numerically in
+    fp64 by a central difference of the flattened argument pools (structure must not change with the parameter); the
+    kernel then propagates the tangent analytically (forward-mode dual numbers) through every op."""
+    params = list(params)
+    theta = float(params[argnum])
+    h = rel_step * max(1.0, abs(theta))
+    lo, hi = list(params), list(params)
+    lo[argnum], hi[argnum] = theta - h, theta + h
+    p0, p_lo, p_hi = flatten(geometry(*params)), flatten(geometry(*lo)), flatten(geometry(*hi))
+    if not (np.array_equal(p0.ops, p_lo.ops) and np.array_equal(p0.ops, p_hi.ops)):
+        raise ValueError("the program structure changes with the parameter; cannot differentiate through it")
+    p0.dargs = (p_hi.args - p_lo.args) / (2.0 * h)
+    p0.dargs[np.abs(p0.dargs) < 1e-9 * (1.0 + np.abs(p0.args))] = 0.0  # rounding noise of unaffected arguments
+    return p0
+
+
+def jacfwd(geometry, argnums=0, *, mode="dual", dtype="f64", rel_step=1e-6, device=0):
+    """Returns g(co, *params) -> d field / d params[argnums] for a builder `geometry(*params) -> geometry object`:
+    the counterpart of jacfwd(geometry, argnums=k)(*p) in Code/examples/autodiff/gradient_map_3D.py:84.
+
+    mode="dual" (default): forward-mode dual numbers inside the interpreter (AB_GRAD_PARAM): every op reads its
+        arguments as (value, d/d theta) pairs. Parameters that reach a table argument (curve-instance records,
+        polyline / polygon / triangle vertices, sector tables) are not supported there.
+    mode="fd": both programs at params[k] +- h evaluated in fp64 on the GPU, central difference (~1e-9 relative);
+        works for every op."""
+
+    def grad_map_dual(co, *params):
+        prog = program_tangent(geometry, params, argnums, rel_step)
+        return create(prog, co, dtype=dtype, grad="param", device=device)[1][0]
 
     def grad_map(co, *params):
         params = list(params)
@@ -160,7 +186,11 @@ def jacfwd(geometry, argnums=0, *, rel_step=1e-6, device=0):
         f_hi *= 1.0 / (2.0 * h)
         return f_hi
 
-    return grad_map
+    if mode == "dual":
+        return grad_map_dual
+    if mode == "fd":
+        return grad_map
+    raise ValueError("mode must be 'dual' or 'fd'")
 
 
 # ---- device-resident evaluation (torch owns the memory and the stream) ------------------------------------------------------

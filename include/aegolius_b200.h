@@ -41,7 +41,10 @@ typedef enum ab_grad_mode {
   AB_GRAD_NONE = 0,
   AB_GRAD_SPATIAL = 1, /* d field / d(x,y,z): analytic counterpart of from_sdf (vector_functions.py:130-139) */
   AB_GRAD_PARAM = 2    /* d field / d theta for one scalar parameter: replaces jacfwd(geometry, argnums=k),
-                          Code/examples/autodiff/gradient_map_3D.py:84. Needs ab_program.dargs. */
+                          Code/examples/autodiff/gradient_map_3D.py:84. ab_program.dargs holds d args / d theta; every
+                          argument is read as a dual number and the tangent is propagated op by op. Limits: at most
+                          AB_MAX_ARGS/2 arguments; table arguments (instance / vertex / sector tables, per-quadrant
+                          radii, norm order) must have zero tangent (AB_EUNSUPPORTED_OP otherwise). */
 } ab_grad_mode;
 
 /* Limits of one program (it travels to the kernel as a __grid_constant__ parameter, i.e. constant bank 0). */

@@ -124,7 +124,9 @@ def test_parameter_gradient_map_matches_oracle_differences():
     rng = np.random.default_rng(4)
     co = rng.uniform(-3, 3, size=(3, 5003))
     for k in range(4):
-        got = ab.jacfwd(geometry, argnums=k)(co, *p)
+        got = ab.jacfwd(geometry, argnums=k, mode="fd")(co, *p)
+        dual64 = ab.jacfwd(geometry, argnums=k, mode="dual", dtype="f64")(co, *p)
+        dual32 = ab.jacfwd(geometry, argnums=k, mode="dual", dtype="f32")(co, *p)
         h = 1e-5
         lo, hi = list(p), list(p)
         lo[k] -= h
@@ -133,6 +135,27 @@ def test_parameter_gradient_map_matches_oracle_differences():
         kink = np.abs(exp - got) > 1e-3  # points whose active branch flips inside the stencil
         assert kink.mean() < 0.02
         assert np.max(np.abs(exp - got)[~kink]) < 1e-5
+        # forward-mode dual numbers through the interpreter (AB_GRAD_PARAM) agree with the differences
+        kd = np.abs(exp - dual64) > 1e-3
+        assert kd.mean() < 0.02
+        assert np.max(np.abs(exp - dual64)[~kd]) < 1e-5
+        assert np.max(np.abs(dual32 - dual64)[~kd]) < 2e-3
+
+
+def test_parameter_tangent_through_a_table_is_refused():
+    import aegolius_b200 as ab
+    from aegolius_b200 import cabi
+
+    def geometry(r):
+        b = ab.Box(0.3, 0.2, 0.2)
+        b.curve_instancing(lambda t, rr: np.asarray((rr * np.cos(2 * np.pi * t), rr * np.sin(2 * np.pi * t), 0 * t)),
+                           (r,), (0, 0.9, 7))
+        return b
+    co = np.random.default_rng(1).uniform(-1, 1, size=(3, 100))
+    with pytest.raises(cabi.AegoliusError) as e:
+        ab.jacfwd(geometry, mode="dual")(co, 1.0)
+    assert e.value.code == cabi.AB_EUNSUPPORTED_OP and "table" in str(e.value)
+    assert np.isfinite(ab.jacfwd(geometry, mode="fd")(co, 1.0)).all()  # the difference mode handles every op
 
 
 def test_point_cloud_few_queries_many_points_split_path():
