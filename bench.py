@@ -40,6 +40,23 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic(n_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
+    (profiles/r01_c5_dual_kernel_ncu_summary.json, taken on the whole 1025^3 grid), scaled to this rank's slab."""
+    p = os.path.join(ROOT, "profiles", "r01_c5_dual_kernel_ncu_summary.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)
+
+        def gb(key):
+            v, unit = d[key].split()[:2]
+            return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+        total = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+        return total * n_local / 1076890625.0
+    except Exception:
+        return None
+
+
 def _workload(name):
     from aegolius_b200 import workloads, GridSpec, flatten
     cfg = workloads.CONFIGS[name]
@@ -260,6 +277,34 @@ def run_gpu(args):
     pf.free()
     pg.free()
 
+    # ---- secondary device-time probes (rank 0, N=1 only): the shallow-tree side of the roofline ----
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = {}
+        sph = ab.Sphere(1.0)
+        sph.move((0.3, 0.1, -0.2))
+        probes = {"sphere_1025^3_f32": (ab.flatten(sph), ab.GridSpec((4, 4, 4), (1024,) * 3), None),
+                  "C1_tree_1025^3_f32": (ab.flatten(ab.workloads.build_c1()), ab.GridSpec((4, 4, 4), (1024,) * 3), None),
+                  "C5_tree_1025^3_f32_value_only": (prog, spec, None)}
+        peak_hbm, _ = _peaks()
+        for name, (pg, sp, gr) in probes.items():
+            buf = torch.empty(sp.n_points, dtype=torch.float32, device=dev)
+            for _ in range(3):
+                engine.create_torch(pg, sp, dtype="f32", grad=gr, device=local, out=buf)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            a.record()
+            for _ in range(5):
+                engine.create_torch(pg, sp, dtype="f32", grad=gr, device=local, out=buf)
+            b.record()
+            torch.cuda.synchronize(dev)
+            t = a.elapsed_time(b) / 5
+            secondary[name] = {"ms": round(t, 4), "Gpts_per_s": round(sp.n_points / t / 1e6, 1),
+                               "output_GBps": round(4 * sp.n_points / t / 1e6, 1),
+                               "hbm_frac": round(4 * sp.n_points / t / 1e6 / peak_hbm, 4), "ops": pg.n_ops}
+            del buf
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peak, peak_src = _peaks()
         alg_bytes = 16.0 * n_local  # 4 B field + 12 B gradient written per point, 0 B read (grid mode)
@@ -278,11 +323,14 @@ def run_gpu(args):
                     "note": "aegolius_b200.create(obj, grid, grad='spatial') into pinned host arrays (per rank)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": _traffic(n_local), "peak_source": peak_src,
                          "kernel": "ab_interp_kernel<Dual<Pack<float,2>,3>,float>", "algorithmic_bytes_per_point": 16,
-                         "note": "deep tree: FP32-issue-bound, not HBM-bound (SURVEY §8d); see DESIGN.md"},
+                         "note": "deep tree: FP32-issue-bound, not HBM-bound (SURVEY §8d); 'secondary' holds the shallow-tree "
+                                 "probes that are write-bound; traffic: ncu capture in profiles/ scaled to this slab"},
             "checksum": checksum,
         }
+        if secondary:
+            line["secondary"] = secondary
         if not args.no_cpu and world == 1:
             cores = 1
             pts, wall = cpu_sample(prog, spec, 2, 1)
@@ -303,6 +351,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C5", choices=["C5", "C3", "C1"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the shallow-tree roofline probes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -165,3 +165,25 @@ def test_introspection_rejects_custom_closures_by_name():
     s.custom_modification(lambda f, co, p, mp: f(co, *p), (), "wobble")
     with pytest.raises(NotImplementedError, match="custom_modification"):
         ab.flatten(s)
+
+
+@pytest.mark.reference
+def test_patch_rebinds_spomso_create_and_has_no_silent_fallback():
+    """aegolius_b200.patch() routes an unmodified SPOMSO object's create() to the GPU library; in this GPU-less container
+    that must raise NoDeviceError (there is no CPU fallback), and unpatch() restores SPOMSO's own NumPy path."""
+    from spomso.cores.geom_3d import Sphere
+    from spomso.cores.helper_functions import generate_grid
+    from aegolius_b200 import cabi, engine
+    co, _ = generate_grid((2, 2, 2), (4, 4, 4))
+    s = Sphere(0.5)
+    ref = s.create(co)
+    engine.patch(dtype="f64")
+    try:
+        if cabi.device_count() == 0:
+            with pytest.raises(cabi.NoDeviceError):
+                s.create(co)
+        else:
+            assert np.max(np.abs(s.create(co) - ref)) < 1e-12
+    finally:
+        engine.unpatch()
+    assert np.array_equal(s.create(co), ref)
