@@ -193,6 +193,38 @@ def jacfwd(geometry, argnums=0, *, mode="dual", dtype="f64", rel_step=1e-6, devi
     raise ValueError("mode must be 'dual' or 'fd'")
 
 
+def value_and_grad(geometry, spec, target, *, dtype="f32", device=0, post=None):
+    """Counterpart of jax.value_and_grad(worker)(params) in Code/examples/autodiff/position_optimization.py:101-179 for the
+    least-squares objective used there: loss(params) = sum((F(params) - target)^2), F = field of geometry(*params) on the
+    grid `spec`. Returns f(params) -> (loss, d loss / d params).
+
+    Everything stays on the device: one AB_GRAD_PARAM launch per parameter gives (F, dF/dtheta_k) as torch tensors and the
+    sums  sum(r^2), sum(2 r dF/dtheta_k)  are torch reductions (K forward-mode passes; K is a handful of shape parameters).
+    `target` is a torch CUDA tensor or array of N values; `post(F, dF)` may map the field before the residual (e.g. a
+    falloff) and must return the transformed pair."""
+    import torch
+    dev = torch.device("cuda", device)
+    tdt = torch.float32 if _dtype(dtype)[0] == cabi.AB_F32 else torch.float64
+    tgt = torch.as_tensor(np.asarray(target) if not torch.is_tensor(target) else target, dtype=tdt, device=dev)
+
+    def f(params):
+        params = [float(v) for v in params]
+        grads, loss = [], None
+        for k in range(len(params)):
+            prog = program_tangent(geometry, params, k)
+            field, dfield = create_torch(prog, spec, dtype=dtype, grad="param", device=device)
+            dfield = dfield[0]
+            if post is not None:
+                field, dfield = post(field, dfield)
+            r = field - tgt
+            if loss is None:
+                loss = float(torch.sum(r * r))
+            grads.append(float(torch.sum(2.0 * r * dfield)))
+        return loss, np.asarray(grads)
+
+    return f
+
+
 # ---- device-resident evaluation (torch owns the memory and the stream) ------------------------------------------------------
 
 

@@ -170,3 +170,35 @@ def test_point_cloud_few_queries_many_points_split_path():
         assert got.shape == (n,) and np.max(np.abs(got - exp)) <= 1e-5 * 2.6
         got2 = ab.point_cloud_sdf(co, pts, dim=2, dtype="f32")
         assert np.max(np.abs(got2 - interp_np.point_cloud_distance(co, pts, dim=2))) <= 1e-5 * 2.6
+
+
+def test_position_optimisation_converges_like_the_jax_example():
+    """position_optimization.py:60-179 without JAX/optax: a circle is moved onto a target circle by Adam on the
+    least-squares field mismatch; value and gradient come from aegolius_b200.value_and_grad (AB_GRAD_PARAM passes +
+    device reductions)."""
+    import aegolius_b200 as ab
+    spec = ab.GridSpec((4, 4), (128, 128))
+    radius, target_xy = 0.5, (0.7, -0.4)
+
+    def circle_at(x0, y0):
+        c = ab.Circle(radius)
+        c.move((x0, y0, 0.0))
+        return c
+
+    target = ab.create(circle_at(*target_xy), spec, dtype="f32")
+    vg = ab.value_and_grad(circle_at, spec, target)
+    params = np.array([-0.6, 0.5])
+    loss0, g0 = vg(params)
+    # gradient against a central difference of the loss itself
+    h = 1e-3
+    fd = np.array([(vg(params + h * e)[0] - vg(params - h * e)[0]) / (2 * h) for e in np.eye(2)])
+    assert np.allclose(g0, fd, rtol=2e-2, atol=1e-2 * abs(fd).max())
+    m, v, lr = np.zeros(2), np.zeros(2), 0.05
+    for it in range(1, 200):
+        loss, g = vg(params)
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        params = params - lr * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+        if loss < 1e-3 * loss0:
+            break
+    assert loss < 1e-2 * loss0 and np.max(np.abs(params - np.array(target_xy))) < 0.05
