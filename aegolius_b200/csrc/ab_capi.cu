@@ -550,10 +550,10 @@ extern "C" int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, in
   Pipe* pp = nullptr;
   rc = pipe_for(device, &pp);
   if (rc) return rc;
-  // chunk = whole planes, about 128 MB of output each (at least one plane, at most the slab)
+  // chunk = whole planes, about 256 MB of output each (at least one plane, at most the slab)
   const uint64_t plane = g.is2d ? g.n2 : g.plane;  // one ix plane (a row of y in 2D)
   const uint64_t bytes_per_plane = plane * es * (1 + rows);
-  uint64_t planes_per_chunk = (128ull << 20) / (bytes_per_plane ? bytes_per_plane : 1);
+  uint64_t planes_per_chunk = (256ull << 20) / (bytes_per_plane ? bytes_per_plane : 1);
   if (planes_per_chunk < 1) planes_per_chunk = 1;
   const uint64_t total_planes = grid->slab_end - grid->slab_begin;
   if (planes_per_chunk > total_planes) planes_per_chunk = total_planes;
@@ -584,9 +584,9 @@ extern "C" int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, in
     CUDA_TRY(cudaEventRecord(pp->done[b], pp->comp));
     CUDA_TRY(cudaStreamWaitEvent(pp->copy, pp->done[b], 0));
     CUDA_TRY(cudaMemcpyAsync((char*)out_host + off * es, d_out[b], pts * es, cudaMemcpyDeviceToHost, pp->copy));
-    for (int r = 0; r < rows; r++)
-      CUDA_TRY(cudaMemcpyAsync((char*)out_grad_host + ((size_t)r * grad_stride + off) * es,
-                               (char*)d_grad[b] + (size_t)r * dstride * es, pts * es, cudaMemcpyDeviceToHost, pp->copy));
+    if (rows)  // all gradient rows of the chunk in one strided copy
+      CUDA_TRY(cudaMemcpy2DAsync((char*)out_grad_host + off * es, (size_t)grad_stride * es, d_grad[b], (size_t)dstride * es,
+                                 pts * es, rows, cudaMemcpyDeviceToHost, pp->copy));
     CUDA_TRY(cudaEventRecord(pp->freed[b], pp->copy));
     done_planes += np;
     c++;
