@@ -283,9 +283,10 @@ static int dispatch_nt(const KParams<T>& kp, int device, cudaStream_t st) {
   LaunchCfg cfg{di.sms, di.smem_optin};
   int status = AB_OK;
   cudaError_t e;
-  if (kp.tier == 0 && !std::is_same<S, Pack<float, 4>>::value) {
-    // (fp32 value-only lite programs never get here: run_program sends them to the 8-wide lite kernel)
-    if constexpr (!std::is_same<S, Pack<float, 4>>::value) e = launch_interp<S, T, 0>(kp, cfg, st, &status);
+  constexpr bool kHasOwnLite = !std::is_same<S, Pack<float, 4>>::value && !std::is_same<S, Dual<Pack<float, 2>, 3>>::value;
+  if (kp.tier == 0 && kHasOwnLite) {
+    // (fp32 lite programs never get here: run_program sends them to the wider lite kernels)
+    if constexpr (kHasOwnLite) e = launch_interp<S, T, 0>(kp, cfg, st, &status);
     else e = cudaErrorInvalidValue;
   } else if (kp.tier <= 1) {
     if constexpr (sizeof(T) == 4) e = launch_interp<S, T, 1>(kp, cfg, st, &status);
@@ -427,7 +428,12 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
         else rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
       } else rc = dispatch_nt<Pack<T, WV>, T>(kp, device, st);
     }
-    else if (grad_mode == AB_GRAD_SPATIAL) rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
+    else if (grad_mode == AB_GRAD_SPATIAL) {
+      if constexpr (sizeof(T) == 4) {
+        if (kp.tier == 0) rc = dispatch_fixed<Dual<Pack<T, 4>, 3>, T, 0>(kp, device, st);  // lite: 4 points per thread
+        else rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
+      } else rc = dispatch_nt<Dual<Pack<T, WG>, 3>, T>(kp, device, st);
+    }
     else rc = dispatch_fixed<Dual<Pack<T, WG>, 1>, T, 2, true>(kp, device, st);
     done += chunk;
   }

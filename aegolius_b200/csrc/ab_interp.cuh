@@ -324,8 +324,17 @@ __host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((si
 // small table (twist, bend, rotational symmetry, instancing, Boltzmann combines, post-processing maps, cones, arcs,
 // n-gons ...) at 90 registers; TIER 2 adds the widest primitives (triangles, quads, sectors, polylines, point clouds).
 // minimum resident CTAs per SM asked of the register allocator, per tier (128-thread CTAs): lite 6, mid 5, full 4
+template <typename S>
+struct IsDual { static constexpr bool value = false; };
+template <typename P, int K>
+struct IsDual<Dual<P, K>> { static constexpr bool value = true; };
+template <typename S, int TIER>
+constexpr int min_ctas() {  // the wide lite dual kernel (4 points x 4 components) needs ~3x the registers
+  return (IsDual<S>::value && S::width >= 4) ? 3 : (TIER <= 1 ? 6 : 4);
+}
+
 template <typename S, typename T, int TIER, bool PARAM = false>
-__global__ void __launch_bounds__(128, TIER == 0 ? 6 : (TIER == 1 ? 6 : 4)) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
+__global__ void __launch_bounds__(128, min_ctas<S, TIER>()) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
   static_assert(TIER == AB_TIER_FULL, "one tier per translation unit");
   constexpr int W = S::width;
   const int NT = blockDim.x;
