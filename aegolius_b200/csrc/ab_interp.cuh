@@ -329,12 +329,23 @@ struct IsDual { static constexpr bool value = false; };
 template <typename P, int K>
 struct IsDual<Dual<P, K>> { static constexpr bool value = true; };
 template <typename S, int TIER>
-constexpr int min_ctas() {  // the wide lite dual kernel (4 points x 4 components) needs ~3x the registers
+__host__ __device__ constexpr int min_ctas() {  // the wide lite dual kernel (4 points x 4 components) needs ~3x the registers
   return (IsDual<S>::value && S::width >= 4) ? 3 : (TIER <= 1 ? 6 : 4);
 }
 
+#ifndef AB_BIG_CTA
+#define AB_BIG_CTA 0
+#endif
+// AB_BIG_CTA (experiment): one CTA of AB_BIG_CTA threads per SM for the mid/full tiers; the warps that share an SM
+// sub-partition (wid % 4) are kept in lockstep with a named barrier per op, so they fetch every op body once instead of
+// thrashing the per-sub-partition instruction cache from unrelated program positions.
+template <typename S, int TIER>
+__host__ __device__ constexpr bool big_cta() { return AB_BIG_CTA > 0 && TIER >= 1 && !(IsDual<S>::value && S::width >= 4); }
+template <typename S, int TIER>
+__host__ __device__ constexpr int max_threads() { return big_cta<S, TIER>() ? AB_BIG_CTA : 128; }
+
 template <typename S, typename T, int TIER, bool PARAM = false>
-__global__ void __launch_bounds__(128, min_ctas<S, TIER>()) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
+__global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() ? 1 : min_ctas<S, TIER>())) ab_interp_kernel(const __grid_constant__ KParams<T> kp) {
   static_assert(TIER == AB_TIER_FULL, "one tier per translation unit");
   constexpr int W = S::width;
   const int NT = blockDim.x;
@@ -463,6 +474,10 @@ __global__ void __launch_bounds__(128, min_ctas<S, TIER>()) ab_interp_kernel(con
       // branch (LDC of the table entry + BRX); with a value it can narrow to 8/16 bits it emits a ~7-level tree of
       // uniform compares and branches. Measured on B200 (profiles/r01_sweeps.md) the tree is FASTER here (C1: 254 vs
       // 228 Gpts/s): the indexed branch waits on a dependent constant load and resolves late, the uniform tree does not.
+      if constexpr (big_cta<S, TIER>()) {
+        const int part = (threadIdx.x >> 5) & 3;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + part), "r"(NT / 4));
+      }
       const uint2 w = s_ops[pc];
       const uint32_t code = AB_DISPATCH_BRX ? w.x : (w.x & 0xffu);
       const int sa = (int)((w.y >> 16) & 0xffu), sb = (int)(w.y >> 24);
@@ -735,7 +750,8 @@ cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream
   const size_t prog_bytes = prog_ops_bytes(kp.n_ops) + prog_args_bytes<T>(kp.n_args);
   // prefer 128 threads; shrink the CTA when the stacks would not leave room for >= 2 CTAs per SM
   int nt = 128;
-  if (prog_bytes + per_thread * 128 > 96 * 1024) nt = 64;
+  if (big_cta<S, TIER>()) nt = AB_BIG_CTA;
+  else if (prog_bytes + per_thread * 128 > 96 * 1024) nt = 64;
   if (prog_bytes + per_thread * nt > cfg.smem_optin) nt = 32;
   const size_t smem = prog_bytes + per_thread * nt;
   if (smem > cfg.smem_optin) {
