@@ -704,7 +704,7 @@ static int nn_t(const void* cloud, uint64_t m, int dim, int grid_mode, const Gri
         return AB_OK;
       }
     }
-    return launch_nn<T, 8, 512>(kp, device, st);
+    return launch_nn<T, 16, 512>(kp, device, st);
   }
   else return launch_nn<T, 4, 512>(kp, device, st);
 }
