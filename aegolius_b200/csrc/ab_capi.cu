@@ -2,16 +2,19 @@
 // interfaces each entry point replaces). Plain pointers and sizes in, status codes out; no torch types.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <type_traits>
 #include <vector>
 
 #include "ab_kernels_aux.cuh"
+#include "ab_nn_tree.cuh"
 
 using namespace ab;
 
@@ -66,6 +69,13 @@ static int dev_info(int device, DevInfo& out) {
     CUDA_TRY(cudaGetDeviceProperties(&p, device));
     g_dev[device].sms = p.multiProcessorCount;
     g_dev[device].smem_optin = p.sharedMemPerBlockOptin;
+    // stream-ordered scratch (the octree of ab_nn_tree.cuh) stays in the pool between calls instead of going back to the
+    // driver at every synchronisation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     g_dev[device].ok = true;
   }
   out = g_dev[device];
@@ -659,6 +669,92 @@ static int launch_nn(const NNParams<T>& kp, int device, cudaStream_t st) {
   return AB_OK;
 }
 
+// exact nearest neighbour through the implicit octree of ab_nn_tree.cuh: build on the stream, then one thread per query
+template <typename T>
+static int launch_nn_tree(const NNParams<T>& kp, int device, cudaStream_t st) {
+  typedef typename Vec4<T>::type V4;
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  const int dim = kp.dim;
+  const double lg = std::log2((double)kp.m);
+  int levels = dim == 3 ? (int)std::ceil(lg / 3.0) : (int)std::ceil(lg / 2.0) - 1;  // tuned on B200, flat optimum
+  const int max_levels = dim == 3 ? 8 : 12;
+  levels = levels < 1 ? 1 : (levels > max_levels ? max_levels : levels);
+  const uint64_t cells = 1ull << (dim * levels);
+  const uint64_t n_chunks = (cells + 1 + kScanChunk - 1) / kScanChunk;
+  const uint64_t start_len = n_chunks * kScanChunk;
+  const uint64_t n_inner = ((1ull << (dim * levels)) - 1) / ((1ull << dim) - 1);
+  auto al = [](uint64_t b) { return (b + 255) & ~255ull; };
+  const uint64_t off_start = 0, off_totals = off_start + al(start_len * 4), off_key = off_totals + al(n_chunks * 4),
+                 off_rank = off_key + al((uint64_t)kp.m * 4), off_bbox = off_rank + al((uint64_t)kp.m * 4),
+                 off_geom = off_bbox + al(6 * 8), off_pts = off_geom + al(sizeof(TreeGeom<T>)),
+                 off_occ = off_pts + al((uint64_t)kp.m * sizeof(V4)), total = off_occ + al(n_inner);
+  char* buf = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&buf, total, st));
+  uint32_t* start = (uint32_t*)(buf + off_start);
+  uint32_t* totals = (uint32_t*)(buf + off_totals);
+  uint32_t* key = (uint32_t*)(buf + off_key);
+  uint32_t* rank = (uint32_t*)(buf + off_rank);
+  unsigned long long* bbox = (unsigned long long*)(buf + off_bbox);
+  TreeGeom<T>* geom = (TreeGeom<T>*)(buf + off_geom);
+  V4* pts = (V4*)(buf + off_pts);
+  uint8_t* occ = (uint8_t*)(buf + off_occ);
+  int status = AB_OK;
+  auto run = [&]() -> int {
+    CUDA_TRY(cudaMemsetAsync(start, 0, start_len * 4, st));
+    CUDA_TRY(cudaMemsetAsync(bbox, 0xff, 3 * 8, st));
+    CUDA_TRY(cudaMemsetAsync(bbox + 3, 0, 3 * 8, st));
+    const unsigned gm = (unsigned)std::min<uint64_t>(((uint64_t)kp.m + 255) / 256, (uint64_t)di.sms * 16);
+    ab_tree_bbox_kernel<T><<<std::min<unsigned>(gm, (unsigned)di.sms * 4), 256, 0, st>>>(kp.cloud, kp.m, bbox);
+    ab_tree_geom_kernel<T><<<1, 1, 0, st>>>(bbox, levels, geom);
+    if (dim == 3) ab_tree_count_kernel<T, 3><<<gm, 256, 0, st>>>(kp.cloud, kp.m, geom, levels, start, key, rank);
+    else ab_tree_count_kernel<T, 2><<<gm, 256, 0, st>>>(kp.cloud, kp.m, geom, levels, start, key, rank);
+    ab_scan_totals_kernel<<<(unsigned)n_chunks, kScanNT, 0, st>>>(start, totals);
+    ab_scan_offsets_kernel<<<1, kScanNT, 0, st>>>(totals, (uint32_t)n_chunks);
+    ab_scan_apply_kernel<<<(unsigned)n_chunks, kScanNT, 0, st>>>(start, totals);
+    ab_tree_scatter_kernel<T><<<gm, 256, 0, st>>>(kp.cloud, kp.m, start, key, rank, pts);
+    const unsigned go = (unsigned)std::min<uint64_t>((n_inner + 255) / 256, (uint64_t)di.sms * 16);
+    if (dim == 3) ab_tree_occupancy_kernel<3><<<go, 256, 0, st>>>(start, levels, occ);
+    else ab_tree_occupancy_kernel<2><<<go, 256, 0, st>>>(start, levels, occ);
+    CUDA_TRY(cudaGetLastError());
+    TreeParams<T> tp{};
+    tp.q = kp;
+    tp.pts = pts;
+    tp.start = start;
+    tp.occ = occ;
+    tp.geom = geom;
+    tp.levels = levels;
+    tp.leaf = 32;
+    constexpr int NT = 128;
+    uint64_t warps;
+    if (kp.grid_mode) {  // one warp per 2x4x4 (1x4x8) block of samples, see the kernel
+      const uint64_t n0 = kp.n / kp.g.plane;
+      warps = n0 == 1 ? (uint64_t)((kp.g.n1 + 3) / 4) * ((kp.g.n2 + 7) / 8)
+                      : ((n0 + 1) / 2) * ((kp.g.n1 + 3) / 4) * ((kp.g.n2 + 3) / 4);
+    } else {
+      warps = (kp.n + 31) / 32;
+    }
+    const uint64_t ctas = (warps + NT / 32 - 1) / (NT / 32);
+    if (ctas > 0x7fffffffull) return fail(AB_ETOOLARGE, "too many queries for one launch (%llu)", (unsigned long long)kp.n);
+    const unsigned gq = (unsigned)ctas;
+    const bool packet = kp.grid_mode != 0;  // point lists have no spatial order to share a walk
+    if (packet) {
+      if (dim == 3) ab_nn_tree_packet_kernel<T, 3, NT><<<gq, NT, 0, st>>>(tp);
+      else ab_nn_tree_packet_kernel<T, 2, NT><<<gq, NT, 0, st>>>(tp);
+    } else {
+      if (dim == 3) ab_nn_tree_kernel<T, 3, NT><<<gq, NT, 0, st>>>(tp);
+      else ab_nn_tree_kernel<T, 2, NT><<<gq, NT, 0, st>>>(tp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 9;
+    return AB_OK;
+  };
+  status = run();
+  cudaFreeAsync(buf, st);
+  return status;
+}
+
 template <typename T>
 static int nn_t(const void* cloud, uint64_t m, int dim, int grid_mode, const GridK& g, const void* co, int co_dtype,
                 uint64_t co_stride, uint64_t n, void* out, int device, cudaStream_t st) {
@@ -677,6 +773,12 @@ static int nn_t(const void* cloud, uint64_t m, int dim, int grid_mode, const Gri
   kp.co = co;
   kp.co_stride = co_stride;
   kp.co_is_f64 = co_dtype == AB_F64;
+  {
+    // AB_NN_ALGO=brute|tree forces one of the two exact paths (they return identical bits); default: by problem size
+    const char* algo = getenv("AB_NN_ALGO");
+    const bool force_tree = algo && !strcmp(algo, "tree"), force_brute = algo && !strcmp(algo, "brute");
+    if (force_tree || (!force_brute && m >= 256 && (double)n * (double)m >= 1073741824.0)) return launch_nn_tree<T>(kp, device, st);
+  }
   if constexpr (sizeof(T) == 4) {
     // few queries: split the cloud across lanes / warps / CTAs (warp-shuffle min + atomic min), else one query per lane
     DevInfo di;

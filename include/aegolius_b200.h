@@ -189,8 +189,10 @@ int ab_eval_points_host(const ab_program* prog, const double* co_host, uint64_t 
                         int grad_mode, void* out_host, void* out_grad_host, uint64_t grad_stride, int device);
 
 /* Replaces sdf_point_cloud_3d / sdf_point_cloud_2d (sdf_3D.py:283-286, sdf_2D.py:221-224) on a grid: unsigned
- * distance to the nearest cloud point, brute force, exact (q-p)^2 form. cloud: DEVICE float4 records from
- * ab_cloud_upload. */
+ * distance to the nearest cloud point, exact (q-p)^2 form. cloud: DEVICE (x, y, z, 0) records from ab_cloud_upload.
+ * Two exact paths that return identical bits: tiled brute force (small n*m) and an implicit octree / quadtree built
+ * per call on `stream` (n*m >= 2^30; the reference asks a cKDTree). The environment variable AB_NN_ALGO=brute|tree
+ * forces one of them (used by the parity tests). */
 int ab_nn_grid(const void* cloud_dev, uint64_t m, int dim, const ab_grid* grid, int dtype, void* out, int device,
                void* stream);
 int ab_nn_points(const void* cloud_dev, uint64_t m, int dim, const void* co, int co_dtype, uint64_t co_stride,

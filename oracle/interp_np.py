@@ -540,3 +540,13 @@ def point_cloud_distance(co, points, dim=3):
         d2 = ((q[:, :, None] - pts[:, None, :]) ** 2).sum(axis=0)
         out[s:s + step] = np.sqrt(d2.min(axis=1))
     return out
+
+
+def point_cloud_distance_kdtree(co, points, dim=3):
+    """The same field the way the reference computes it (sdf_3D.py:283-286): scipy's cKDTree, nearest neighbour.
+    For clouds too large for the exhaustive definition above."""
+    from scipy.spatial import cKDTree
+
+    co = np.asarray(co, dtype=np.float64)
+    pts = np.asarray(points, dtype=np.float64)[:dim]
+    return cKDTree(pts.T).query(co[:dim].T)[0]

@@ -202,3 +202,57 @@ def test_position_optimisation_converges_like_the_jax_example():
         if loss < 1e-3 * loss0:
             break
     assert loss < 1e-2 * loss0 and np.max(np.abs(params - np.array(target_xy))) < 0.05
+
+
+def _cloud_cases():
+    rng = np.random.default_rng(1)
+    from aegolius_b200 import workloads
+    return {
+        "uniform": rng.uniform(-1, 1, (3, 20000)),
+        "surface": workloads.c4_cloud(50000, 3),
+        "clusters": np.concatenate([rng.normal(0, 0.01, (3, 5000)), rng.normal(1.5, 0.3, (3, 5000))], axis=1),
+        "single": np.array([[0.3], [0.2], [-0.1]]),
+        "duplicates": np.repeat(rng.uniform(-1, 1, (3, 10)), 300, axis=1),
+        "collinear": np.stack([np.linspace(-1, 1, 3000), np.zeros(3000), np.zeros(3000)]),
+        "far_from_origin": rng.uniform(100, 100.5, (3, 4000)),
+    }
+
+
+@pytest.mark.parametrize("name", ["uniform", "surface", "clusters", "single", "duplicates", "collinear", "far_from_origin"])
+def test_point_cloud_octree_and_brute_force_return_identical_bits(name, monkeypatch):
+    """The octree path prunes, it never approximates: same bits as the exhaustive kernel (grid + point-list queries,
+    2D + 3D, both precisions), including degenerate clouds."""
+    import aegolius_b200 as ab
+    pts = _cloud_cases()[name]
+    rng = np.random.default_rng(7)
+    co = rng.uniform(-3, 3, (3, 20011))
+    for dt in ("f32", "f64"):
+        for dim, target in ((3, ab.GridSpec((4, 4, 4), (40, 38, 42))), (2, ab.GridSpec((4, 4), (150, 131))), (3, co), (2, co)):
+            monkeypatch.setenv("AB_NN_ALGO", "brute")
+            a = ab.point_cloud_sdf(target, pts, dim=dim, dtype=dt)
+            monkeypatch.setenv("AB_NN_ALGO", "tree")
+            b = ab.point_cloud_sdf(target, pts, dim=dim, dtype=dt)
+            assert np.array_equal(a, b), (name, dt, dim, float(np.max(np.abs(a - b))))
+
+
+def test_point_cloud_octree_default_dispatch_matches_oracle(monkeypatch):
+    """n*m >= 2^30 takes the octree without being asked; checked against the k-d tree oracle."""
+    monkeypatch.delenv("AB_NN_ALGO", raising=False)
+    import aegolius_b200 as ab
+    from aegolius_b200 import workloads
+    pts = workloads.c4_cloud(300000, 5)
+    spec = ab.GridSpec((2.5, 2.5, 1.5), (32, 32, 32))
+    from aegolius_b200 import cabi
+    before = cabi.launch_count()
+    got32 = ab.point_cloud_sdf(spec, pts, dtype="f32")
+    assert cabi.launch_count() - before == 9  # octree build (8 launches) + packet walk
+    exp = interp_np.point_cloud_distance_kdtree(spec.materialize(), pts)
+    assert np.max(np.abs(got32 - exp)) <= 1e-5 * 2.5
+    got64 = ab.point_cloud_sdf(spec, pts, dtype="f64")
+    assert np.max(np.abs(got64 - exp)) <= 1e-12 * 2.5
+    spec2 = ab.GridSpec((2.5, 2.5), (128, 128))
+    exp2 = interp_np.point_cloud_distance_kdtree(spec2.materialize(), pts, dim=2)
+    assert np.max(np.abs(ab.point_cloud_sdf(spec2, pts, dim=2, dtype="f64") - exp2)) <= 1e-12 * 2.5
+    # slabs of the grid see the same tree
+    part = ab.point_cloud_sdf(spec, pts, dtype="f32", slab=(7, 19))
+    assert np.array_equal(part, got32.reshape(33, -1)[7:19].ravel())
