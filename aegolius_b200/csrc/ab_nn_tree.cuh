@@ -301,13 +301,21 @@ AB_DEV uint32_t xor_permute(uint32_t m, uint32_t pref) {
   return m;
 }
 
-// per-axis distances from r to the low and the high half of the node [2i*cs, (2i+2)*cs) (widened by the slack)
+AB_DEV float max3_(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+AB_DEV double max3_(double a, double b, double c) { return fmax(fmax(a, b), c); }
+
+// per-axis distances from r to the low and the high half of the node [mid - cs, mid + cs), mid = (2i+1)*cs, both widened
+// by the slack (css = cs + slack): with t = r - mid, low half: max(t, -t - cs), high half: max(-t, t - cs)
 template <typename T>
-AB_DEV void half_distances(T r, uint32_t i, T cs, T slack, T& d0, T& d1, uint32_t& high) {
-  const T lo = (T)(2 * i) * cs, mid = (T)(2 * i + 1) * cs, hi = (T)(2 * i + 2) * cs;
-  d0 = s_max(s_max(lo - r, r - mid) - slack, T(0));
-  d1 = s_max(s_max(mid - r, r - hi) - slack, T(0));
-  high = r >= mid ? 1u : 0u;
+AB_DEV void half_distances(T r, uint32_t i, T cs, T css, T slack, T& d0, T& d1, uint32_t& high) {
+  const T t = s_fma(-(T)(2 * i + 1), cs, r);
+  d0 = max3_(t - slack, -t - css, T(0));
+  d1 = max3_(-t - slack, t - css, T(0));
+  high = t >= T(0) ? 1u : 0u;
 }
 
 template <typename T, int DIM, int NT>
@@ -360,11 +368,12 @@ __global__ void __launch_bounds__(NT) ab_nn_tree_kernel(const __grid_constant__ 
     while (true) {
       // per-node values (recomputed after coming back up: cheaper than keeping seven registers per level)
       const T cs = g.cell * (T)(1u << (L - l - 1));  // child edge
+      const T css = cs + slack;
       T ax0, ax1, ay0, ay1, az0 = T(0), az1 = T(0);
       uint32_t hx, hy, hz = 0;
-      half_distances(rx, ix, cs, slack, ax0, ax1, hx);
-      half_distances(ry, iy, cs, slack, ay0, ay1, hy);
-      if constexpr (DIM == 3) half_distances(rz, iz, cs, slack, az0, az1, hz);
+      half_distances(rx, ix, cs, css, slack, ax0, ax1, hx);
+      half_distances(ry, iy, cs, css, slack, ay0, ay1, hy);
+      if constexpr (DIM == 3) half_distances(rz, iz, cs, css, slack, az0, az1, hz);
       const uint32_t pref = hx | (hy << 1) | (hz << 2);
       if (fresh) todo = xor_permute<DIM>(occ[level_offset<DIM>(l) + code], pref);
       bool descended = false;
@@ -471,13 +480,15 @@ __global__ void __launch_bounds__(NT) ab_nn_tree_packet_kernel(const __grid_cons
   bool fresh = true;
   while (true) {
     const T cs = g.cell * (T)(1u << (L - l - 1));
+    const T css = cs + slack;
     T ax0, ax1, ay0, ay1, az0 = T(0), az1 = T(0);
     uint32_t hx, hy, hz = 0;
-    half_distances(rx, ix, cs, slack, ax0, ax1, hx);
-    half_distances(ry, iy, cs, slack, ay0, ay1, hy);
-    if constexpr (DIM == 3) half_distances(rz, iz, cs, slack, az0, az1, hz);
+    half_distances(rx, ix, cs, css, slack, ax0, ax1, hx);
+    half_distances(ry, iy, cs, css, slack, ay0, ay1, hy);
+    if constexpr (DIM == 3) half_distances(rz, iz, cs, css, slack, az0, az1, hz);
     uint32_t pref = (ux >= (T)(2 * ix + 1) * cs ? 1u : 0u) | (uy >= (T)(2 * iy + 1) * cs ? 2u : 0u);
     if constexpr (DIM == 3) pref |= uz >= (T)(2 * iz + 1) * cs ? 4u : 0u;
+    (void)hx, (void)hy, (void)hz;
     if (fresh) todo = xor_permute<DIM>(occ[level_offset<DIM>(l) + code], pref);
     bool descended = false;
     while (todo) {

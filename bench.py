@@ -303,6 +303,33 @@ def run_gpu(args):
                                "output_GBps": round(4 * sp.n_points / t / 1e6, 1),
                                "hbm_frac": round(4 * sp.n_points / t / 1e6 / peak_hbm, 4), "ops": pg.n_ops}
             del buf
+        # C4: point cloud -> unsigned distance (exact octree nearest neighbour), device time of ab_nn_grid incl. tree build
+        import ctypes as C
+        from aegolius_b200 import cabi, workloads
+        cloud = workloads.c4_cloud()
+        c4 = ab.GridSpec(workloads.CONFIGS["C4"]["size"], workloads.CONFIGS["C4"]["res"])
+        lib, d_cloud = cabi.lib(), C.c_void_p()
+        cabi.check(lib.ab_cloud_upload(cloud.ctypes.data, cloud.shape[1], 3, cloud.shape[1], cabi.AB_F32, local, C.byref(d_cloud)))
+        buf = torch.empty(c4.n_points, dtype=torch.float32, device=dev)
+        g = cabi.make_grid(c4.size, c4.res)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        l0 = cabi.launch_count()
+        for _ in range(2):
+            cabi.check(lib.ab_nn_grid(d_cloud, cloud.shape[1], 3, C.byref(g), cabi.AB_F32, buf.data_ptr(), local, st))
+        per_call = (cabi.launch_count() - l0) // 2
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a.record()
+        for _ in range(5):
+            cabi.check(lib.ab_nn_grid(d_cloud, cloud.shape[1], 3, C.byref(g), cabi.AB_F32, buf.data_ptr(), local, st))
+        b.record()
+        torch.cuda.synchronize(dev)
+        t = a.elapsed_time(b) / 5
+        secondary["C4_cloud_1M_points_257^3_f32"] = {"ms": round(t, 4), "Mqueries_per_s": round(c4.n_points / t / 1e3, 1),
+                                                    "launches_per_call": per_call,
+                                                    "equivalent_Tpairs_per_s": round(c4.n_points * cloud.shape[1] / t / 1e9, 1)}
+        lib.ab_device_free(d_cloud, local)
+        del buf
         torch.cuda.empty_cache()
 
     if rank == 0:
