@@ -257,6 +257,12 @@ extern "C" int ab_cloud_upload(const double* points_host, uint64_t m, int dim, u
                          : upload_cloud<float>(points_host, m, dim, row_stride, 0, out_dev, false);
 }
 
+// clouds of at least this many points get an octree when they are a leaf of a program
+static const uint64_t kTreeLeafMin = 2048;
+template <typename T>
+static int build_tree(const typename Vec4<T>::type* cloud, uint32_t m, int dim, const DevInfo& di, cudaStream_t st,
+                      void** buf_out, const TreeRef<T>** ref_out);
+
 // ---- interpreter launch ----------------------------------------------------------------------------------------------------
 static const uint32_t kParamHalf = (AB_MAX_ARGS / 2) & ~3u;
 
@@ -386,6 +392,7 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   for (uint32_t b = 0; b < AB_MAX_BLOBS; b++) {
     kp.blob[b] = nullptr;
     kp.blob_count[b] = 0;
+    kp.blob_tree[b] = nullptr;
   }
   for (uint32_t b = 0; b < prog->n_blobs; b++) {
     const ab_blob& bl = prog->blobs[b];
@@ -400,6 +407,24 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
       kp.blob[b] = d;
     }
     kp.blob_count[b] = (uint32_t)bl.count;
+    // large clouds: the leaf walks an octree instead of scanning the blob (dimension = that of the leaf using the blob)
+    if (bl.count >= kTreeLeafMin) {
+      int bdim = 3;
+      for (uint32_t i = 0; i < prog->n_ops; i++)
+        if (prog->ops[i].opcode == AB_OP_P_POINT_CLOUD && prog->ops[i].b == b) bdim = prog->ops[i].a == 2 ? 2 : 3;
+      DevInfo di;
+      rc = dev_info(device, di);
+      if (rc) return rc;
+      void* tbuf = nullptr;
+      const TreeRef<T>* ref = nullptr;
+      rc = build_tree<T>((const typename Vec4<T>::type*)kp.blob[b], (uint32_t)bl.count, bdim, di, st, &tbuf, &ref);
+      if (tbuf) temp_blobs.push_back(tbuf);
+      if (rc) {
+        for (void* d : temp_blobs) cudaFreeAsync(d, st);
+        return rc;
+      }
+      kp.blob_tree[b] = ref;
+    }
   }
 
   constexpr int WV = sizeof(T) == 4 ? 4 : 2;  // one 128-bit store per thread
@@ -669,15 +694,13 @@ static int launch_nn(const NNParams<T>& kp, int device, cudaStream_t st) {
   return AB_OK;
 }
 
-// exact nearest neighbour through the implicit octree of ab_nn_tree.cuh: build on the stream, then one thread per query
+// Builds the implicit octree / quadtree of ab_nn_tree.cuh over a device cloud on the stream (8 launches). *buf_out owns
+// every piece (release with cudaFreeAsync on the same stream), *ref_out is the device descriptor inside it.
 template <typename T>
-static int launch_nn_tree(const NNParams<T>& kp, int device, cudaStream_t st) {
+static int build_tree(const typename Vec4<T>::type* cloud, uint32_t m, int dim, const DevInfo& di, cudaStream_t st,
+                      void** buf_out, const TreeRef<T>** ref_out) {
   typedef typename Vec4<T>::type V4;
-  DevInfo di;
-  int rc = dev_info(device, di);
-  if (rc) return rc;
-  const int dim = kp.dim;
-  const double lg = std::log2((double)kp.m);
+  const double lg = std::log2((double)m);
   int levels = dim == 3 ? (int)std::ceil(lg / 3.0) : (int)std::ceil(lg / 2.0) - 1;  // tuned on B200, flat optimum
   const int max_levels = dim == 3 ? 8 : 12;
   levels = levels < 1 ? 1 : (levels > max_levels ? max_levels : levels);
@@ -687,45 +710,55 @@ static int launch_nn_tree(const NNParams<T>& kp, int device, cudaStream_t st) {
   const uint64_t n_inner = ((1ull << (dim * levels)) - 1) / ((1ull << dim) - 1);
   auto al = [](uint64_t b) { return (b + 255) & ~255ull; };
   const uint64_t off_start = 0, off_totals = off_start + al(start_len * 4), off_key = off_totals + al(n_chunks * 4),
-                 off_rank = off_key + al((uint64_t)kp.m * 4), off_bbox = off_rank + al((uint64_t)kp.m * 4),
-                 off_geom = off_bbox + al(6 * 8), off_pts = off_geom + al(sizeof(TreeGeom<T>)),
-                 off_occ = off_pts + al((uint64_t)kp.m * sizeof(V4)), total = off_occ + al(n_inner);
+                 off_rank = off_key + al((uint64_t)m * 4), off_bbox = off_rank + al((uint64_t)m * 4),
+                 off_ref = off_bbox + al(6 * 8), off_pts = off_ref + al(sizeof(TreeRef<T>)),
+                 off_occ = off_pts + al((uint64_t)m * sizeof(V4)), total = off_occ + al(n_inner);
   char* buf = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&buf, total, st));
+  *buf_out = buf;
   uint32_t* start = (uint32_t*)(buf + off_start);
   uint32_t* totals = (uint32_t*)(buf + off_totals);
   uint32_t* key = (uint32_t*)(buf + off_key);
   uint32_t* rank = (uint32_t*)(buf + off_rank);
   unsigned long long* bbox = (unsigned long long*)(buf + off_bbox);
-  TreeGeom<T>* geom = (TreeGeom<T>*)(buf + off_geom);
+  TreeRef<T>* ref = (TreeRef<T>*)(buf + off_ref);
   V4* pts = (V4*)(buf + off_pts);
   uint8_t* occ = (uint8_t*)(buf + off_occ);
-  int status = AB_OK;
+  *ref_out = ref;
+  CUDA_TRY(cudaMemsetAsync(start, 0, start_len * 4, st));
+  CUDA_TRY(cudaMemsetAsync(bbox, 0xff, 3 * 8, st));
+  CUDA_TRY(cudaMemsetAsync(bbox + 3, 0, 3 * 8, st));
+  const unsigned gm = (unsigned)std::min<uint64_t>(((uint64_t)m + 255) / 256, (uint64_t)di.sms * 16);
+  ab_tree_bbox_kernel<T><<<std::min<unsigned>(gm, (unsigned)di.sms * 4), 256, 0, st>>>(cloud, m, bbox);
+  ab_tree_geom_kernel<T><<<1, 1, 0, st>>>(bbox, levels, 32u, pts, start, occ, ref);
+  if (dim == 3) ab_tree_count_kernel<T, 3><<<gm, 256, 0, st>>>(cloud, m, ref, levels, start, key, rank);
+  else ab_tree_count_kernel<T, 2><<<gm, 256, 0, st>>>(cloud, m, ref, levels, start, key, rank);
+  ab_scan_totals_kernel<<<(unsigned)n_chunks, kScanNT, 0, st>>>(start, totals);
+  ab_scan_offsets_kernel<<<1, kScanNT, 0, st>>>(totals, (uint32_t)n_chunks);
+  ab_scan_apply_kernel<<<(unsigned)n_chunks, kScanNT, 0, st>>>(start, totals);
+  ab_tree_scatter_kernel<T><<<gm, 256, 0, st>>>(cloud, m, start, key, rank, pts);
+  const unsigned go = (unsigned)std::min<uint64_t>((n_inner + 255) / 256, (uint64_t)di.sms * 16);
+  if (dim == 3) ab_tree_occupancy_kernel<3><<<go, 256, 0, st>>>(start, levels, occ);
+  else ab_tree_occupancy_kernel<2><<<go, 256, 0, st>>>(start, levels, occ);
+  CUDA_TRY(cudaGetLastError());
+  g_launches += 8;
+  return AB_OK;
+}
+
+// exact nearest neighbour through the octree: build, then one packet walk per warp (grids) / one walk per thread (lists)
+template <typename T>
+static int launch_nn_tree(const NNParams<T>& kp, int device, cudaStream_t st) {
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  const int dim = kp.dim;
+  void* buf = nullptr;
+  const TreeRef<T>* ref = nullptr;
+  int status = build_tree<T>(kp.cloud, kp.m, dim, di, st, &buf, &ref);
   auto run = [&]() -> int {
-    CUDA_TRY(cudaMemsetAsync(start, 0, start_len * 4, st));
-    CUDA_TRY(cudaMemsetAsync(bbox, 0xff, 3 * 8, st));
-    CUDA_TRY(cudaMemsetAsync(bbox + 3, 0, 3 * 8, st));
-    const unsigned gm = (unsigned)std::min<uint64_t>(((uint64_t)kp.m + 255) / 256, (uint64_t)di.sms * 16);
-    ab_tree_bbox_kernel<T><<<std::min<unsigned>(gm, (unsigned)di.sms * 4), 256, 0, st>>>(kp.cloud, kp.m, bbox);
-    ab_tree_geom_kernel<T><<<1, 1, 0, st>>>(bbox, levels, geom);
-    if (dim == 3) ab_tree_count_kernel<T, 3><<<gm, 256, 0, st>>>(kp.cloud, kp.m, geom, levels, start, key, rank);
-    else ab_tree_count_kernel<T, 2><<<gm, 256, 0, st>>>(kp.cloud, kp.m, geom, levels, start, key, rank);
-    ab_scan_totals_kernel<<<(unsigned)n_chunks, kScanNT, 0, st>>>(start, totals);
-    ab_scan_offsets_kernel<<<1, kScanNT, 0, st>>>(totals, (uint32_t)n_chunks);
-    ab_scan_apply_kernel<<<(unsigned)n_chunks, kScanNT, 0, st>>>(start, totals);
-    ab_tree_scatter_kernel<T><<<gm, 256, 0, st>>>(kp.cloud, kp.m, start, key, rank, pts);
-    const unsigned go = (unsigned)std::min<uint64_t>((n_inner + 255) / 256, (uint64_t)di.sms * 16);
-    if (dim == 3) ab_tree_occupancy_kernel<3><<<go, 256, 0, st>>>(start, levels, occ);
-    else ab_tree_occupancy_kernel<2><<<go, 256, 0, st>>>(start, levels, occ);
-    CUDA_TRY(cudaGetLastError());
     TreeParams<T> tp{};
     tp.q = kp;
-    tp.pts = pts;
-    tp.start = start;
-    tp.occ = occ;
-    tp.geom = geom;
-    tp.levels = levels;
-    tp.leaf = 32;
+    tp.tree = ref;
     constexpr int NT = 128;
     uint64_t warps;
     if (kp.grid_mode) {  // one warp per 2x4x4 (1x4x8) block of samples, see the kernel
@@ -738,8 +771,7 @@ static int launch_nn_tree(const NNParams<T>& kp, int device, cudaStream_t st) {
     const uint64_t ctas = (warps + NT / 32 - 1) / (NT / 32);
     if (ctas > 0x7fffffffull) return fail(AB_ETOOLARGE, "too many queries for one launch (%llu)", (unsigned long long)kp.n);
     const unsigned gq = (unsigned)ctas;
-    const bool packet = kp.grid_mode != 0;  // point lists have no spatial order to share a walk
-    if (packet) {
+    if (kp.grid_mode) {
       if (dim == 3) ab_nn_tree_packet_kernel<T, 3, NT><<<gq, NT, 0, st>>>(tp);
       else ab_nn_tree_packet_kernel<T, 2, NT><<<gq, NT, 0, st>>>(tp);
     } else {
@@ -747,11 +779,11 @@ static int launch_nn_tree(const NNParams<T>& kp, int device, cudaStream_t st) {
       else ab_nn_tree_kernel<T, 2, NT><<<gq, NT, 0, st>>>(tp);
     }
     CUDA_TRY(cudaGetLastError());
-    g_launches += 9;
+    g_launches += 1;
     return AB_OK;
   };
-  status = run();
-  cudaFreeAsync(buf, st);
+  if (status == AB_OK) status = run();
+  if (buf) cudaFreeAsync(buf, st);
   return status;
 }
 

@@ -86,6 +86,10 @@ struct Vec4<double> {
   typedef double4 type;
 };
 
+}  // namespace ab
+#include "ab_tree.cuh"
+namespace ab {
+
 template <typename T>
 struct KParams {
   uint64_t n;        // points in this launch (< 2^31: the host splits larger slabs on plane boundaries)
@@ -104,6 +108,7 @@ struct KParams {
   uint32_t dargs_off;  // AB_GRAD_PARAM: args[dargs_off + i] = d args[i] / d theta (second half of the pool), else 0
   const void* blob[AB_MAX_BLOBS];  // (x, y, z, 0) records of T
   uint32_t blob_count[AB_MAX_BLOBS];
+  const void* blob_tree[AB_MAX_BLOBS];  // device TreeRef<T> of the blob (large clouds) or nullptr: scan the blob
   uint2 ops[AB_MAX_OPS];  // kernel-side encoding: x = dense opcode (a full word), y = argument offset | a << 16 | b << 24
   T args[AB_MAX_ARGS];
 };
@@ -264,31 +269,50 @@ AB_DEV void emit(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint32_t 
   for (int k = 0; k < K; k++) store_pack(kp.grad + (uint64_t)k * kp.grad_stride, acc.d[k], idx, kp.n, ga);
 }
 
-// brute-force nearest cloud point inside the interpreter (sdf_3D.py:283-286): uniform (broadcast) loads of float4
-// records, exact (q-p)^2 form. The dedicated kernel in ab_nn.cu is the fast path for a bare cloud; this one lets a
-// cloud sit anywhere in a tree.
+// nearest cloud point inside the interpreter (sdf_3D.py:283-286), for a cloud that sits anywhere in a tree: queries arrive
+// already warped by the ops above the leaf. Large clouds come with an octree (built by the host per call, ab_tree.cuh) and
+// every lane walks it; small ones are scanned with uniform (broadcast) loads. Same (q-p)^2 expression either way, so the
+// two agree to the bit (up to which of two exactly equidistant points wins). The walk is inlined on purpose: as a
+// __noinline__ function (divergent loops inside a callee) it returned wrong winners / faulted when called from this kernel
+// with nvcc 12.9, while the identical code inlined, or called from a small kernel, is correct.
+template <typename T>
+AB_DEV uint32_t cloud_nearest_tree(const TreeRef<T>& t, T x, T y, T z, int dim) {
+  T best;
+  uint32_t bi;
+  if (dim == 3) tree_nearest<T, 3, 0, true>(t, x, y, z, best, bi);
+  else tree_nearest<T, 2, 0, true>(t, x, y, T(0), best, bi);
+  return bi;
+}
+
 template <typename S, typename T>
-AB_DEV S prim_point_cloud(const Pt<S>& p, const void* __restrict__ cloud_v, uint32_t m, int dim) {
+AB_DEV S prim_point_cloud(const Pt<S>& p, const void* __restrict__ cloud_v, uint32_t m, int dim, const void* tree_v) {
   typedef typename Vec4<T>::type V4;
   const V4* __restrict__ cloud = reinterpret_cast<const V4*>(cloud_v);
   constexpr int W = S::width;
   auto vx = value_of(p.x), vy = value_of(p.y), vz = value_of(p.z);
   T best[W];
   uint32_t bi[W];
-#pragma unroll
-  for (int i = 0; i < W; i++) {
-    best[i] = T(3.0e38);
-    bi[i] = 0;
-  }
-  for (uint32_t j = 0; j < m; j++) {
-    const V4 c = cloud[j];
+  if (tree_v) {
+    const TreeRef<T> tree = *reinterpret_cast<const TreeRef<T>*>(tree_v);
+    cloud = tree.pts;  // winners are positions in the cell-ordered copy
+#pragma unroll 1
+    for (int i = 0; i < W; i++) bi[i] = cloud_nearest_tree<T>(tree, vx.v[i], vy.v[i], vz.v[i], dim);
+  } else {
 #pragma unroll
     for (int i = 0; i < W; i++) {
-      T dx = vx.v[i] - (T)c.x, dy = vy.v[i] - (T)c.y, dz = (dim == 3) ? vz.v[i] - (T)c.z : T(0);
-      T d2 = s_fma(dx, dx, s_fma(dy, dy, dz * dz));
-      if (d2 < best[i]) {
-        best[i] = d2;
-        bi[i] = j;
+      best[i] = T(3.0e38);
+      bi[i] = 0;
+    }
+    for (uint32_t j = 0; j < m; j++) {
+      const V4 c = cloud[j];
+#pragma unroll
+      for (int i = 0; i < W; i++) {
+        T dx = vx.v[i] - (T)c.x, dy = vy.v[i] - (T)c.y, dz = (dim == 3) ? vz.v[i] - (T)c.z : T(0);
+        T d2 = s_fma(dx, dx, s_fma(dy, dy, dz * dz));
+        if (d2 < best[i]) {
+          best[i] = d2;
+          bi[i] = j;
+        }
       }
     }
   }
@@ -663,7 +687,7 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
           else acc = p.z - a[0];
           break;
 #if AB_TIER_FULL >= 2
-        case D_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[sb], kp.blob_count[sb], sa); break;
+        case D_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[sb], kp.blob_count[sb], sa, kp.blob_tree[sb]); break;
 #endif
         // 2D primitives
         case D_P_CIRCLE: acc = prim_circle(p, a); break;

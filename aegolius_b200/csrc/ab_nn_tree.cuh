@@ -22,22 +22,9 @@
 namespace ab {
 
 template <typename T>
-struct TreeGeom {
-  T org[3];
-  T cell;      // finest cell edge
-  T inv_cell;
-  T slack;
-};
-
-template <typename T>
 struct TreeParams {
   NNParams<T> q;  // queries + output (q.cloud = the caller's unsorted cloud)
-  const typename Vec4<T>::type* pts;
-  const uint32_t* start;
-  const uint8_t* occ;  // child occupancy of every inner node, level by level
-  const TreeGeom<T>* geom;
-  int32_t levels;
-  uint32_t leaf;  // ranges of at most this many points are scanned instead of subdivided
+  const TreeRef<T>* tree;
 };
 
 // ---- order-preserving encoding of doubles for atomicMin/Max ------------------------------------------------------------
@@ -87,7 +74,8 @@ __global__ void __launch_bounds__(256) ab_tree_bbox_kernel(const typename Vec4<T
 }
 
 template <typename T>
-__global__ void ab_tree_geom_kernel(const unsigned long long* bbox, int levels, TreeGeom<T>* g) {
+__global__ void ab_tree_geom_kernel(const unsigned long long* bbox, int levels, uint32_t leaf, const typename Vec4<T>::type* pts,
+                                    const uint32_t* start, const uint8_t* occ, TreeRef<T>* ref) {
   double lo[3], hi[3], ext = 0.0, mag = 0.0;
   for (int a = 0; a < 3; a++) {
     lo[a] = ord_decode(bbox[a]);
@@ -98,10 +86,17 @@ __global__ void ab_tree_geom_kernel(const unsigned long long* bbox, int levels, 
   const double eps = sizeof(T) == 4 ? 1.1920928955078125e-7 : 2.220446049250313e-16;
   ext = fmax(ext * (1.0 + 1.0e-6), fmax(mag * 64.0 * eps, 1.0e-30));  // never zero (single point / coincident points)
   const double cells = (double)(1u << levels);
-  for (int a = 0; a < 3; a++) g->org[a] = (T)lo[a];
-  g->cell = (T)(ext / cells);
-  g->inv_cell = (T)(cells / ext);
-  g->slack = (T)(ext * 9.5367431640625e-7 + 8.0 * eps * (mag + ext));
+  TreeGeom<T> g;
+  for (int a = 0; a < 3; a++) g.org[a] = (T)lo[a];
+  g.cell = (T)(ext / cells);
+  g.inv_cell = (T)(cells / ext);
+  g.slack = (T)(ext * 9.5367431640625e-7 + 8.0 * eps * (mag + ext));
+  ref->geom = g;
+  ref->pts = pts;
+  ref->start = start;
+  ref->occ = occ;
+  ref->levels = levels;
+  ref->leaf = leaf;
 }
 
 // bit spreading for Morton codes: x bit i -> bit B*i
@@ -140,9 +135,9 @@ AB_DEV uint32_t morton_of(T x, T y, T z, const TreeGeom<T>& g, int levels) {
 
 // counts[code]++ and remember the arrival rank inside the cell (it becomes the offset of the scatter)
 template <typename T, int DIM>
-__global__ void ab_tree_count_kernel(const typename Vec4<T>::type* __restrict__ cloud, uint32_t m, const TreeGeom<T>* geom,
+__global__ void ab_tree_count_kernel(const typename Vec4<T>::type* __restrict__ cloud, uint32_t m, const TreeRef<T>* ref,
                                      int levels, uint32_t* counts, uint32_t* __restrict__ key, uint32_t* __restrict__ rank) {
-  const TreeGeom<T> g = *geom;
+  const TreeGeom<T> g = ref->geom;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     const auto c = cloud[i];
     const uint32_t k = morton_of<T, DIM>(c.x, c.y, c.z, g, levels);
@@ -229,10 +224,6 @@ __global__ void __launch_bounds__(kScanNT) ab_scan_apply_kernel(uint32_t* data, 
 }
 
 // ---- the query kernel ---------------------------------------------------------------------------------------------------------
-// the pair expressions of the brute-force kernels (ab_kernels_aux.cuh), reused for the box bound
-AB_DEV float nn_d2(float dx, float dy, float dz) { return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))); }
-AB_DEV double nn_d2(double dx, double dy, double dz) { return __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz))); }
-
 template <typename T>
 AB_DEV void nn_query_point(const NNParams<T>& kp, uint64_t k, T& x, T& y, T& z) {
   if (kp.grid_mode) {
@@ -263,12 +254,6 @@ AB_DEV void nn_query_point(const NNParams<T>& kp, uint64_t k, T& x, T& y, T& z) 
   }
 }
 
-// first node of level l in the occupancy table: (NC^l - 1) / (NC - 1)
-template <int DIM>
-AB_DEV constexpr uint32_t level_offset(int l) {
-  return ((1u << (DIM * l)) - 1u) / ((1u << DIM) - 1u);
-}
-
 // occ[level_offset(l) + code] = which children of node (l, code) hold points (bit c = child c), for l < L
 template <int DIM>
 __global__ void ab_tree_occupancy_kernel(const uint32_t* __restrict__ start, int levels, uint8_t* __restrict__ occ) {
@@ -291,142 +276,17 @@ __global__ void ab_tree_occupancy_kernel(const uint32_t* __restrict__ start, int
   }
 }
 
-// bit k of the result = bit (k XOR pref) of m: the children in the order they are visited
-template <int DIM>
-AB_DEV uint32_t xor_permute(uint32_t m, uint32_t pref) {
-  if (pref & 1u) m = ((m & 0x55u) << 1) | ((m & 0xaau) >> 1);
-  if (pref & 2u) m = ((m & 0x33u) << 2) | ((m & 0xccu) >> 2);
-  if constexpr (DIM == 3)
-    if (pref & 4u) m = ((m & 0x0fu) << 4) | ((m & 0xf0u) >> 4);
-  return m;
-}
-
-AB_DEV float max3_(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-AB_DEV double max3_(double a, double b, double c) { return fmax(fmax(a, b), c); }
-
-// per-axis distances from r to the low and the high half of the node [mid - cs, mid + cs), mid = (2i+1)*cs, both widened
-// by the slack (css = cs + slack): with t = r - mid, low half: max(t, -t - cs), high half: max(-t, t - cs)
-template <typename T>
-AB_DEV void half_distances(T r, uint32_t i, T cs, T css, T slack, T& d0, T& d1, uint32_t& high) {
-  const T t = s_fma(-(T)(2 * i + 1), cs, r);
-  d0 = max3_(t - slack, -t - css, T(0));
-  d1 = max3_(-t - slack, t - css, T(0));
-  high = t >= T(0) ? 1u : 0u;
-}
-
+// Point-list queries (no spatial order to share a walk): one thread per query, ab_tree.cuh's walk
 template <typename T, int DIM, int NT>
 __global__ void __launch_bounds__(NT) ab_nn_tree_kernel(const __grid_constant__ TreeParams<T> tp) {
-  typedef typename Vec4<T>::type V4;
-  constexpr int B = DIM;            // Morton bits per level
-  constexpr uint32_t NC = 1u << B;  // children per node = bits of one stack entry
-  const uint32_t kLeaf = tp.leaf;
-  const TreeGeom<T> g = *tp.geom;
-  const int L = tp.levels;
-  const uint32_t* __restrict__ start = tp.start;
-  const uint8_t* __restrict__ occ = tp.occ;
-  const V4* __restrict__ pts = tp.pts;
-
-  // query of this thread. Grids: every warp takes a compact 2x4x4 (1x4x8 on 2D grids) block of samples so that its lanes
-  // walk nearly the same nodes; point lists: consecutive points.
-  uint64_t k;
-  if (tp.q.grid_mode) {
-    const GridK& gk = tp.q.g;
-    const uint32_t n0 = (uint32_t)(tp.q.n / gk.plane), n1 = gk.n1, n2 = gk.n2;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t b0, b1, b2, l0, l1, l2;
-    if (n0 == 1) { b0 = 1; b1 = 4; b2 = 8; l0 = 0; l1 = lane >> 3; l2 = lane & 7u; }
-    else { b0 = 2; b1 = 4; b2 = 4; l0 = lane >> 4; l1 = (lane >> 2) & 3u; l2 = lane & 3u; }
-    const uint32_t t1 = (n1 + b1 - 1) / b1, t2 = (n2 + b2 - 1) / b2;
-    const uint64_t w = ((uint64_t)blockIdx.x * NT + threadIdx.x) >> 5;
-    const uint32_t w2 = (uint32_t)(w % t2), w1 = (uint32_t)((w / t2) % t1);
-    const uint64_t w0 = w / ((uint64_t)t1 * t2);
-    const uint64_t i0 = w0 * b0 + l0;
-    const uint32_t i1 = w1 * b1 + l1, i2 = w2 * b2 + l2;
-    if (i0 >= n0 || i1 >= n1 || i2 >= n2) return;
-    k = (i0 * n1 + i1) * n2 + i2;
-  } else {
-    k = (uint64_t)blockIdx.x * NT + threadIdx.x;
-    if (k >= tp.q.n) return;
-  }
-  {
-    T qx, qy, qz;
-    nn_query_point(tp.q, k, qx, qy, qz);
-    // work relative to the cube's corner
-    const T rx = qx - g.org[0], ry = qy - g.org[1], rz = qz - g.org[2];
-    // rounding of rx/ry/rz grows with the query's distance from the corner: widen the boxes accordingly
-    const T slack = g.slack + T(sizeof(T) == 4 ? 4.8e-7 : 8.9e-16) * (s_abs(rx) + s_abs(ry) + s_abs(rz));
-    T best = T(3.0e38);
-    uint32_t ix = 0, iy = 0, iz = 0, code = 0;
-    uint64_t stack = 0;
-    int l = 0;             // level of the current node; its children live on level l+1
-    uint32_t todo = 0;     // children still to visit, in visiting order (bit k = child k XOR pref)
-    bool fresh = true;     // just descended: fetch the occupancy
-    while (true) {
-      // per-node values (recomputed after coming back up: cheaper than keeping seven registers per level)
-      const T cs = g.cell * (T)(1u << (L - l - 1));  // child edge
-      const T css = cs + slack;
-      T ax0, ax1, ay0, ay1, az0 = T(0), az1 = T(0);
-      uint32_t hx, hy, hz = 0;
-      half_distances(rx, ix, cs, css, slack, ax0, ax1, hx);
-      half_distances(ry, iy, cs, css, slack, ay0, ay1, hy);
-      if constexpr (DIM == 3) half_distances(rz, iz, cs, css, slack, az0, az1, hz);
-      const uint32_t pref = hx | (hy << 1) | (hz << 2);
-      if (fresh) todo = xor_permute<DIM>(occ[level_offset<DIM>(l) + code], pref);
-      bool descended = false;
-      while (todo) {
-        const uint32_t c = (uint32_t)(__ffs((int)todo) - 1) ^ pref;
-        todo &= todo - 1u;
-        const T bx = (c & 1u) ? ax1 : ax0, by = (c & 2u) ? ay1 : ay0, bz = (c & 4u) ? az1 : az0;
-        if (nn_d2(bx, by, bz) >= best) continue;
-        const uint32_t ccode = (code << B) | c;
-        const int shift = B * (L - l - 1);
-        const uint32_t s = start[(size_t)ccode << shift], e = start[(size_t)(ccode + 1) << shift];
-        if (shift == 0 || e - s <= kLeaf) {
-          for (uint32_t i = s; i < e; i++) {
-            const V4 p = pts[i];
-            T dx, dy, dz;
-            if constexpr (sizeof(T) == 4) {  // the fp32 brute-force kernel adds the negated point
-              dx = qx + (-p.x);
-              dy = qy + (-p.y);
-              dz = qz + (-p.z);
-            } else {
-              dx = qx - p.x;
-              dy = qy - p.y;
-              dz = qz - p.z;
-            }
-            best = s_min(best, nn_d2(dx, dy, dz));
-          }
-          continue;
-        }
-        stack = (stack << NC) | todo;
-        l++;
-        ix = 2 * ix + (c & 1u);
-        iy = 2 * iy + ((c >> 1) & 1u);
-        if constexpr (DIM == 3) iz = 2 * iz + (c >> 2);
-        code = ccode;
-        descended = true;
-        break;
-      }
-      if (descended) {
-        fresh = true;
-        continue;
-      }
-      if (l == 0) break;
-      l--;
-      ix >>= 1;
-      iy >>= 1;
-      iz >>= 1;
-      code >>= B;
-      todo = (uint32_t)(stack & (uint64_t)((1u << NC) - 1u));
-      stack >>= NC;
-      fresh = false;
-    }
-    __stcs(tp.q.out + k, s_sqrt(best));
-  }
+  const uint64_t k = (uint64_t)blockIdx.x * NT + threadIdx.x;
+  if (k >= tp.q.n) return;
+  const TreeRef<T> t = *tp.tree;
+  T qx, qy, qz, best;
+  uint32_t bi;
+  nn_query_point(tp.q, k, qx, qy, qz);
+  tree_nearest<T, DIM, 1, false>(t, qx, qy, qz, best, bi);
+  __stcs(tp.q.out + k, s_sqrt(best));
 }
 
 // Grid queries: packet traversal. A warp owns a compact 2x4x4 (1x4x8 on 2D grids) block of samples and walks the tree
@@ -440,12 +300,13 @@ __global__ void __launch_bounds__(NT) ab_nn_tree_packet_kernel(const __grid_cons
   constexpr int B = DIM;
   constexpr uint32_t NC = 1u << B;
   constexpr uint32_t kFull = 0xffffffffu;
-  const uint32_t kLeaf = tp.leaf;
-  const TreeGeom<T> g = *tp.geom;
-  const int L = tp.levels;
-  const uint32_t* __restrict__ start = tp.start;
-  const uint8_t* __restrict__ occ = tp.occ;
-  const V4* __restrict__ pts = tp.pts;
+  const TreeRef<T> tr = *tp.tree;
+  const uint32_t kLeaf = tr.leaf;
+  const TreeGeom<T> g = tr.geom;
+  const int L = tr.levels;
+  const uint32_t* __restrict__ start = tr.start;
+  const uint8_t* __restrict__ occ = tr.occ;
+  const V4* __restrict__ pts = tr.pts;
 
   const GridK& gk = tp.q.g;
   const uint32_t n0 = (uint32_t)(tp.q.n / gk.plane), n1 = gk.n1, n2 = gk.n2;
@@ -495,7 +356,7 @@ __global__ void __launch_bounds__(NT) ab_nn_tree_packet_kernel(const __grid_cons
       const uint32_t c = (uint32_t)(__ffs((int)todo) - 1) ^ pref;
       todo &= todo - 1u;
       const T bx = (c & 1u) ? ax1 : ax0, by = (c & 2u) ? ay1 : ay0, bz = (c & 4u) ? az1 : az0;
-      if (!__any_sync(kFull, nn_d2(bx, by, bz) < best)) continue;
+      if (!__any_sync(kFull, tree_d2<1>(bx, by, bz) < best)) continue;
       const uint32_t ccode = (code << B) | c;
       const int shift = B * (L - l - 1);
       const uint32_t s = start[(size_t)ccode << shift], e = start[(size_t)(ccode + 1) << shift];
@@ -512,7 +373,7 @@ __global__ void __launch_bounds__(NT) ab_nn_tree_packet_kernel(const __grid_cons
             dy = qy - p.y;
             dz = qz - p.z;
           }
-          best = s_min(best, nn_d2(dx, dy, dz));
+          best = s_min(best, tree_d2<1>(dx, dy, dz));
         }
         continue;
       }

@@ -40,10 +40,12 @@ def test_point_cloud_2d_and_points_mode():
     assert np.max(np.abs(ab.point_cloud_sdf(co, pts, dim=3, dtype="f32") - exp3)) <= 1e-5 * 2.4
 
 
-def test_point_cloud_leaf_inside_a_tree_matches_oracle():
-    """PointCloud3D(points).onion(t) under a transform, the pointcloud_terrain_3D.py:39-47 pattern."""
+@pytest.mark.parametrize("m", [2000, 60000])
+def test_point_cloud_leaf_inside_a_tree_matches_oracle(m):
+    """PointCloud3D(points).onion(t) under a transform, the pointcloud_terrain_3D.py:39-47 pattern. Clouds of >= 2048
+    points are searched through the octree inside the interpreter, smaller ones are scanned."""
     import aegolius_b200 as ab
-    pts = _cloud(2000, seed=9)
+    pts = _cloud(m, seed=9)
     pc = ab.PointCloud3D(pts)
     pc.onion(0.03)
     pc.rotate(0.3, (0, 0, 1))
@@ -53,6 +55,27 @@ def test_point_cloud_leaf_inside_a_tree_matches_oracle():
     exp = interp_np.run_grid(prog, spec.size, spec.res)
     assert np.max(np.abs(ab.create(prog, spec, dtype="f64") - exp)) <= 1e-12 * 2.5
     assert np.max(np.abs(ab.create(prog, spec, dtype="f32") - exp)) <= 1e-5 * 2.5
+    # analytic gradient of the leaf: unit vector from the nearest point (away from ties), through the rotation
+    f, g = ab.create(prog, spec, dtype="f64", grad="spatial")
+    assert np.max(np.abs(f - exp)) <= 1e-12 * 2.5
+    nrm = np.sqrt((g * g).sum(axis=0))
+    assert np.max(np.abs(nrm - 1.0)) <= 1e-9
+
+
+def test_point_cloud_2d_leaf_with_octree_matches_oracle():
+    import aegolius_b200 as ab
+    rng = np.random.default_rng(3)
+    t = rng.uniform(0, 2 * np.pi, 30000)
+    pts = np.stack([np.cos(t) * (1 + 0.2 * np.sin(5 * t)), np.sin(t) * (1 + 0.2 * np.sin(5 * t))])
+    pc = ab.PointCloud2D(pts)
+    pc.rescale(0.8)
+    pc.move((0.2, -0.1, 0.0))
+    u = ab.CombineGeometry("UNION2").combine(pc, ab.Circle(0.3))
+    prog = ab.flatten(u)
+    spec = ab.GridSpec((4, 4), (96, 80))
+    exp = interp_np.run_grid(prog, spec.size, spec.res)
+    assert np.max(np.abs(ab.create(prog, spec, dtype="f64") - exp)) <= 1e-12 * 4
+    assert np.max(np.abs(ab.create(prog, spec, dtype="f32") - exp)) <= 1e-5 * 4
 
 
 @pytest.mark.parametrize("res", [(9, 7, 11), (13, 5), (2, 2, 2), (33, 2, 3)])
