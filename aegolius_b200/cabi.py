@@ -34,6 +34,20 @@ class ab_grid(C.Structure):
                 ("slab_end", C.c_uint32)]
 
 
+class ab_vec_op(C.Structure):
+    _fields_ = [("opcode", C.c_uint32), ("kind0", C.c_uint32), ("kind1", C.c_uint32), ("c", C.c_double * 3),
+                ("s0", C.c_double), ("s1", C.c_double), ("a0", C.c_void_p), ("a1", C.c_void_p),
+                ("stride0", C.c_uint64), ("stride1", C.c_uint64)]
+
+
+# ab_vec_opcode / ab_vec_kind / ab_vec_component_id (include/aegolius_b200.h)
+(AB_VOP_ADD, AB_VOP_SUB, AB_VOP_RESCALE, AB_VOP_ROT_Z, AB_VOP_ROT_THETA, AB_VOP_ROT_X, AB_VOP_ROT_Y, AB_VOP_ROT_AXIS,
+ AB_VOP_REVOLVE_X, AB_VOP_REVOLVE_Y, AB_VOP_REVOLVE_Z, AB_VOP_NORMALIZE) = range(1, 13)
+AB_VK_NONE, AB_VK_SCALAR, AB_VK_VEC3, AB_VK_ARRAY, AB_VK_VEC_ARRAY = range(5)
+AB_VC_X, AB_VC_Y, AB_VC_Z, AB_VC_PHI, AB_VC_THETA, AB_VC_LENGTH = range(6)
+AB_MAX_VEC_OPS = 32
+
+
 class AegoliusError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libaegolius_b200 error {code}: {msg}")
@@ -66,6 +80,13 @@ _SIGNATURES = {
                                   C.POINTER(C.c_void_p)]),
     "ab_fd_gradient": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ab_grid), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_uint64, C.c_int, C.c_void_p]),
+    "ab_box_filter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_int,
+                                C.c_void_p, C.c_int, C.c_void_p]),
+    "ab_edge_filter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "ab_vec_apply": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ab_vec_op), C.c_uint32, C.c_int, C.c_int,
+                               C.c_void_p]),
+    "ab_vec_component": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p]),
     "ab_device_alloc": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "ab_device_free": (C.c_int, [C.c_void_p, C.c_int]),
     "ab_host_alloc_pinned": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),

@@ -15,6 +15,7 @@
 
 #include "ab_kernels_aux.cuh"
 #include "ab_nn_tree.cuh"
+#include "ab_fields.cuh"
 
 using namespace ab;
 
@@ -909,6 +910,188 @@ extern "C" int ab_fd_gradient(const void* field, uint32_t field_plane0, const ab
   if (dtype == AB_F32) return fd_t<float>(field, field_plane0, grid, dims, normalize, out, out_stride, device, (cudaStream_t)stream);
   if (dtype == AB_F64) return fd_t<double>(field, field_plane0, grid, dims, normalize, out, out_stride, device, (cudaStream_t)stream);
   return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+// ---- whole-field kernels: box filter, edge filter, vector-field modifiers ------------------------------------------------------
+static unsigned stream_grid(const DevInfo& di, uint64_t n, int nt) {
+  const uint64_t want = (n + nt - 1) / nt, cap = (uint64_t)di.sms * 32;
+  return (unsigned)std::max<uint64_t>(1, std::min(want, cap));
+}
+
+template <typename T>
+static int box_filter_t(const void* field, const uint32_t res[3], const uint32_t ksize[3], uint32_t iterations, void* out,
+                        int device, cudaStream_t st) {
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
+  const T norm = (T)((double)ksize[0] * ksize[1] * ksize[2]);
+  const unsigned grid = stream_grid(di, n, 256);
+  int axes[3], n_axes = 0;
+  for (int a = 0; a < 3; a++)
+    if (ksize[a] > 1) axes[n_axes++] = a;
+  if (iterations == 0) {
+    CUDA_TRY(cudaMemcpyAsync(out, field, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    return AB_OK;
+  }
+  if (n_axes == 0) {  // a 1x1x1 kernel: u / 1
+    ab_scale_copy_kernel<T><<<grid, 256, 0, st>>>((const T*)field, (T*)out, n, norm);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return AB_OK;
+  }
+  const uint32_t passes = iterations * (uint32_t)n_axes;
+  T* tmp = nullptr;
+  if (passes > 1) CUDA_TRY(cudaMallocAsync((void**)&tmp, n * sizeof(T), st));
+  const T* src = (const T*)field;
+  uint32_t p = 0;
+  for (uint32_t it = 0; it < iterations; it++) {
+    for (int ai = 0; ai < n_axes; ai++, p++) {
+      const int a = axes[ai];
+      T* dst = ((passes - 1 - p) & 1u) ? tmp : (T*)out;  // the last pass lands in `out`
+      const uint32_t n_axis = res[a];
+      const uint32_t n_inner = a == 0 ? res[1] * res[2] : (a == 1 ? res[2] : 1);
+      const int k = (int)ksize[a];
+      const int t0 = -((k & 1) ? k / 2 : k / 2 - 1);  // scipy.ndimage.convolve placement, see oracle/fields_np.py
+      ab_box_axis_kernel<T><<<grid, 256, 0, st>>>(src, dst, n, n_axis, n_inner, k, t0, norm, ai == n_axes - 1 ? 1 : 0);
+      src = dst;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (tmp) cudaFreeAsync(tmp, st);
+  if (e != cudaSuccess) return fail(AB_ECUDA, "box filter launch: %s", cudaGetErrorString(e));
+  g_launches += passes;
+  return AB_OK;
+}
+
+static int check_field_args(const void* field, const uint32_t* res, const void* out) {
+  if (!field || !out || !res) return fail(AB_EINVAL, "null pointer");
+  if (res[0] == 0 || res[1] == 0 || res[2] == 0) return fail(AB_EINVAL, "empty field");
+  if ((uint64_t)res[0] * res[1] * res[2] > 0x7fffffffull * 4) return fail(AB_ETOOLARGE, "field too large");
+  return AB_OK;
+}
+
+extern "C" int ab_box_filter(const void* field_dev, const uint32_t res[3], const uint32_t ksize[3], uint32_t iterations,
+                             int dtype, void* out_dev, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  rc = check_field_args(field_dev, res, out_dev);
+  if (rc) return rc;
+  if (!ksize || ksize[0] == 0 || ksize[1] == 0 || ksize[2] == 0) return fail(AB_EINVAL, "kernel sizes must be >= 1");
+  if (field_dev == out_dev) return fail(AB_EINVAL, "box filter cannot run in place");
+  if (dtype == AB_F32) return box_filter_t<float>(field_dev, res, ksize, iterations, out_dev, device, (cudaStream_t)stream);
+  if (dtype == AB_F64) return box_filter_t<double>(field_dev, res, ksize, iterations, out_dev, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+extern "C" int ab_edge_filter(const void* field_dev, const uint32_t res[3], int dtype, void* out_dev, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  rc = check_field_args(field_dev, res, out_dev);
+  if (rc) return rc;
+  if (field_dev == out_dev) return fail(AB_EINVAL, "edge filter cannot run in place");
+  DevInfo di;
+  rc = dev_info(device, di);
+  if (rc) return rc;
+  const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
+  const unsigned grid = stream_grid(di, n, 256);
+  if (dtype == AB_F32) ab_edge_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)field_dev, (float*)out_dev, res[0], res[1], res[2]);
+  else if (dtype == AB_F64) ab_edge_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)field_dev, (double*)out_dev, res[0], res[1], res[2]);
+  else return fail(AB_EINVAL, "bad dtype %d", dtype);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return AB_OK;
+}
+
+static int check_vec_op(const ab_vec_op& op, uint32_t i, uint64_t n) {
+  auto scalar_ok = [&](uint32_t kind, const void* a) { return kind == AB_VK_SCALAR || (kind == AB_VK_ARRAY && a); };
+  switch (op.opcode) {
+    case AB_VOP_ADD: case AB_VOP_SUB:
+      if (scalar_ok(op.kind0, op.a0) || op.kind0 == AB_VK_VEC3 || (op.kind0 == AB_VK_VEC_ARRAY && op.a0 && op.stride0 >= n)) return AB_OK;
+      break;
+    case AB_VOP_RESCALE:
+      if (scalar_ok(op.kind0, op.a0) || (op.kind0 == AB_VK_VEC_ARRAY && op.a0 && op.stride0 >= n)) return AB_OK;
+      break;
+    case AB_VOP_ROT_Z: case AB_VOP_ROT_THETA: case AB_VOP_ROT_X: case AB_VOP_ROT_Y:
+      if (scalar_ok(op.kind0, op.a0)) return AB_OK;
+      break;
+    case AB_VOP_ROT_AXIS:
+      if ((op.kind0 == AB_VK_VEC3 || (op.kind0 == AB_VK_VEC_ARRAY && op.a0 && op.stride0 >= n)) && scalar_ok(op.kind1, op.a1)) return AB_OK;
+      break;
+    case AB_VOP_REVOLVE_X: case AB_VOP_REVOLVE_Y: case AB_VOP_REVOLVE_Z:
+      if (op.kind0 == AB_VK_VEC_ARRAY && op.a0 && op.stride0 >= n) return AB_OK;
+      break;
+    case AB_VOP_NORMALIZE: return AB_OK;
+    default: return fail(AB_EUNSUPPORTED_OP, "vector op %u: unknown opcode %u", i, op.opcode);
+  }
+  return fail(AB_EINVAL, "vector op %u (opcode %u): operand kinds (%u, %u) not accepted or array missing / too short", i,
+              op.opcode, op.kind0, op.kind1);
+}
+
+template <typename T>
+static int vec_apply_t(void* vec, uint64_t stride, uint64_t n, const ab_vec_op* ops, uint32_t n_ops, int device, cudaStream_t st) {
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  VecParams<T> vp{};
+  vp.vec = (T*)vec;
+  vp.stride = stride;
+  vp.n = n;
+  vp.n_ops = n_ops;
+  for (uint32_t i = 0; i < n_ops; i++) {
+    VecOpK& k = vp.ops[i];
+    k.opcode = ops[i].opcode;
+    k.kind0 = ops[i].kind0;
+    k.kind1 = ops[i].kind1;
+    for (int j = 0; j < 3; j++) k.c[j] = ops[i].c[j];
+    k.s0 = ops[i].s0;
+    k.s1 = ops[i].s1;
+    k.a0 = ops[i].a0;
+    k.a1 = ops[i].a1;
+    k.stride0 = ops[i].stride0;
+    k.stride1 = ops[i].stride1;
+  }
+  ab_vec_kernel<T><<<stream_grid(di, n, 256), 256, 0, st>>>(vp);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return AB_OK;
+}
+
+extern "C" int ab_vec_apply(void* vec_dev, uint64_t vec_stride, uint64_t n, const ab_vec_op* ops, uint32_t n_ops, int dtype,
+                            int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (n == 0 || n_ops == 0) return AB_OK;
+  if (!vec_dev || !ops) return fail(AB_EINVAL, "null pointer");
+  if (vec_stride < n) return fail(AB_EINVAL, "vec_stride < n");
+  if (n_ops > AB_MAX_VEC_OPS) return fail(AB_ETOOLARGE, "too many vector ops (%u > %d)", n_ops, AB_MAX_VEC_OPS);
+  for (uint32_t i = 0; i < n_ops; i++) {
+    rc = check_vec_op(ops[i], i, n);
+    if (rc) return rc;
+  }
+  if (dtype == AB_F32) return vec_apply_t<float>(vec_dev, vec_stride, n, ops, n_ops, device, (cudaStream_t)stream);
+  if (dtype == AB_F64) return vec_apply_t<double>(vec_dev, vec_stride, n, ops, n_ops, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+extern "C" int ab_vec_component(const void* vec_dev, uint64_t vec_stride, uint64_t n, int what, int dtype, void* out_dev,
+                                int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (n == 0) return AB_OK;
+  if (!vec_dev || !out_dev) return fail(AB_EINVAL, "null pointer");
+  if (vec_stride < n) return fail(AB_EINVAL, "vec_stride < n");
+  if (what < AB_VC_X || what > AB_VC_LENGTH) return fail(AB_EINVAL, "bad component id %d", what);
+  DevInfo di;
+  rc = dev_info(device, di);
+  if (rc) return rc;
+  const unsigned grid = stream_grid(di, n, 256);
+  if (dtype == AB_F32) ab_vec_component_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)vec_dev, vec_stride, n, what, (float*)out_dev);
+  else if (dtype == AB_F64) ab_vec_component_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)vec_dev, vec_stride, n, what, (double*)out_dev);
+  else return fail(AB_EINVAL, "bad dtype %d", dtype);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return AB_OK;
 }
 
 // ---- memory helpers ---------------------------------------------------------------------------------------------------------------

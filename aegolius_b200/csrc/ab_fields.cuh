@@ -1,0 +1,205 @@
+// ab_fields.cuh — kernels on whole fields that sit AFTER the interpreter in SPOMSO pipelines:
+//   * ab_box_axis_kernel / ab_edge_kernel : conv_averaging / conv_edge_detection (post_processing.py:552-623), i.e.
+//     scipy.ndimage.convolve with mode='reflect' restated tap by tap (oracle/fields_np.py documents the tap placement);
+//   * ab_vec_kernel : the elementwise vector-field modifiers of vector_modification_functions.py:14-172 as a short op
+//     list applied in one pass over the (3, N) field, so a from_sdf -> rotate_z -> rotate_axis pipeline
+//     (sdf_vector_field.py:152-165) stays on the device and touches HBM once;
+//   * ab_vec_component_kernel : x / y / z / phi / theta / length (geom.py:262-362).
+// All are HBM-bound streaming kernels: one element per thread, coalesced along the fastest axis.
+#pragma once
+#include "ab_math.cuh"
+
+namespace ab {
+
+// scipy.ndimage 'reflect' (d c b a | a b c d | d c b a), valid for any offset
+AB_DEV int reflect_index(int i, int n) {
+  const int period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i >= n ? period - 1 - i : i;
+}
+
+// one axis of the separable box filter over a C-ordered (n_outer, n_axis, n_inner) view: the sum of k taps starting at
+// offset t0; the last pass of an iteration also divides by the kernel volume (the reference's filter is ones / norm)
+template <typename T>
+__global__ void ab_box_axis_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t n, uint32_t n_axis, uint32_t n_inner,
+                                   int k, int t0, T norm, int divide) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = e / n_inner;
+    const uint32_t j = (uint32_t)(e - row * n_inner);
+    const uint64_t o = row / n_axis;
+    const int i = (int)(row - o * n_axis);
+    const T* base = in + o * n_axis * (uint64_t)n_inner + j;
+    T s = T(0);
+    for (int t = 0; t < k; t++) s = s + base[(uint64_t)reflect_index(i + t0 + t, (int)n_axis) * n_inner];
+    out[e] = divide ? s / norm : s;
+  }
+}
+
+template <typename T>
+__global__ void ab_scale_copy_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t n, T norm) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) out[e] = in[e] / norm;
+}
+
+// 9 u - sum of the 3x3 neighbourhood in the first two axes of a C-ordered (nx, ny, nz) field
+template <typename T>
+__global__ void ab_edge_kernel(const T* __restrict__ in, T* __restrict__ out, uint32_t nx, uint32_t ny, uint32_t nz) {
+  const uint64_t n = (uint64_t)nx * ny * nz;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t z = (uint32_t)(e % nz);
+    const uint64_t r = e / nz;
+    const int y = (int)(r % ny), x = (int)(r / ny);
+    T s = T(0);
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+      const uint64_t xo = (uint64_t)reflect_index(x + dx, (int)nx) * ny;
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++) s = s + in[(xo + (uint64_t)reflect_index(y + dy, (int)ny)) * nz + z];
+    }
+    out[e] = T(9) * in[e] - s;
+  }
+}
+
+// ---- vector-field modifiers ----------------------------------------------------------------------------------------------
+struct VecOpK {
+  uint32_t opcode;
+  uint32_t kind0, kind1;  // AB_VK_*
+  double c[3];            // constant 3-vector operand
+  double s0, s1;          // constant scalar operands
+  const void* a0;         // per-point operand 0: (N,) or (3, stride0) of T
+  const void* a1;         // per-point operand 1 (rotate_axis: the angle)
+  uint64_t stride0, stride1;
+};
+
+template <typename T>
+struct VecParams {
+  T* vec;  // (3, stride), updated in place
+  uint64_t stride, n;
+  uint32_t n_ops;
+  VecOpK ops[AB_MAX_VEC_OPS];
+};
+
+AB_DEV void sincos_(float a, float& s, float& c) { sincosf(a, &s, &c); }
+AB_DEV void sincos_(double a, double& s, double& c) { sincos(a, &s, &c); }
+AB_DEV float atan2_(float y, float x) { return atan2f(y, x); }
+AB_DEV double atan2_(double y, double x) { return atan2(y, x); }
+
+template <typename T>
+AB_DEV T scalar_operand(uint32_t kind, double s, const void* a, uint64_t e) {
+  return kind == AB_VK_ARRAY ? reinterpret_cast<const T*>(a)[e] : (T)s;
+}
+
+template <typename T>
+AB_DEV void rot2(T& a, T& b, T sa, T ca) {  // (a, b) <- (a ca - b sa, a sa + b ca)
+  const T na = a * ca - b * sa, nb = a * sa + b * ca;
+  a = na;
+  b = nb;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ab_vec_kernel(const __grid_constant__ VecParams<T> vp) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < vp.n; e += (uint64_t)gridDim.x * blockDim.x) {
+    T v0 = vp.vec[e], v1 = vp.vec[vp.stride + e], v2 = vp.vec[2 * vp.stride + e];
+    for (uint32_t k = 0; k < vp.n_ops; k++) {
+      const VecOpK& op = vp.ops[k];
+      switch (op.opcode) {
+        case AB_VOP_ADD: case AB_VOP_SUB: case AB_VOP_RESCALE: {
+          T o0, o1, o2;
+          if (op.kind0 == AB_VK_VEC3) {
+            o0 = (T)op.c[0]; o1 = (T)op.c[1]; o2 = (T)op.c[2];
+          } else if (op.kind0 == AB_VK_VEC_ARRAY) {
+            const T* a = reinterpret_cast<const T*>(op.a0);
+            o0 = a[e]; o1 = a[op.stride0 + e]; o2 = a[2 * op.stride0 + e];
+          } else {
+            o0 = o1 = o2 = scalar_operand<T>(op.kind0, op.s0, op.a0, e);
+          }
+          if (op.opcode == AB_VOP_ADD) { v0 = v0 + o0; v1 = v1 + o1; v2 = v2 + o2; }
+          else if (op.opcode == AB_VOP_SUB) { v0 = v0 - o0; v1 = v1 - o1; v2 = v2 - o2; }
+          else { v0 = v0 * o0; v1 = v1 * o1; v2 = v2 * o2; }
+          break;
+        }
+        case AB_VOP_ROT_Z: case AB_VOP_ROT_X: case AB_VOP_ROT_Y: {
+          T sa, ca;
+          sincos_(scalar_operand<T>(op.kind0, op.s0, op.a0, e), sa, ca);
+          if (op.opcode == AB_VOP_ROT_Z) rot2(v0, v1, sa, ca);
+          else if (op.opcode == AB_VOP_ROT_X) rot2(v1, v2, sa, ca);
+          else rot2(v0, v2, sa, ca);  // the reference's convention (vector_modification_functions.py:84-93)
+          break;
+        }
+        case AB_VOP_ROT_THETA: {  // :55-69
+          T sa, ca;
+          sincos_(scalar_operand<T>(op.kind0, op.s0, op.a0, e), sa, ca);
+          T r0 = v0, r1 = v1;
+          const T m = s_sqrt(r0 * r0 + r1 * r1);
+          if (m != T(0)) { r0 = r0 / m; r1 = r1 / m; }
+          const T t0 = r0 * v2, t1 = r1 * v2, t2 = -r0 * v0 - r1 * v1;
+          v0 = v0 * ca + t0 * sa;
+          v1 = v1 * ca + t1 * sa;
+          v2 = v2 * ca + t2 * sa;
+          break;
+        }
+        case AB_VOP_ROT_AXIS: {  // Rodrigues with the axis as given (:116-131)
+          T a0, a1, a2;
+          if (op.kind0 == AB_VK_VEC3) {
+            a0 = (T)op.c[0]; a1 = (T)op.c[1]; a2 = (T)op.c[2];
+          } else {
+            const T* a = reinterpret_cast<const T*>(op.a0);
+            a0 = a[e]; a1 = a[op.stride0 + e]; a2 = a[2 * op.stride0 + e];
+          }
+          T sa, ca;
+          sincos_(scalar_operand<T>(op.kind1, op.s1, op.a1, e), sa, ca);
+          const T c0 = a1 * v2 - a2 * v1, c1 = a2 * v0 - a0 * v2, c2 = a0 * v1 - a1 * v0;
+          const T dot = a0 * v0 + a1 * v1 + a2 * v2, w = (T(1) - ca) * dot;
+          v0 = v0 * ca + sa * c0 + w * a0;
+          v1 = v1 * ca + sa * c1 + w * a1;
+          v2 = v2 * ca + sa * c2 + w * a2;
+          break;
+        }
+        case AB_VOP_REVOLVE_X: case AB_VOP_REVOLVE_Y: case AB_VOP_REVOLVE_Z: {  // :134-172
+          const T* r = reinterpret_cast<const T*>(op.a0);
+          const T r0 = r[e], r1 = r[op.stride0 + e], r2 = r[2 * op.stride0 + e];
+          T sa, ca;
+          if (op.opcode == AB_VOP_REVOLVE_X) {
+            sincos_(atan2_(r2, r1), sa, ca);
+            rot2(v1, v2, sa, ca);
+          } else if (op.opcode == AB_VOP_REVOLVE_Y) {
+            sincos_(atan2_(r2, r0), sa, ca);
+            rot2(v0, v2, sa, ca);
+          } else {
+            sincos_(atan2_(r1, r0), sa, ca);
+            rot2(v0, v1, sa, ca);
+          }
+          break;
+        }
+        case AB_VOP_NORMALIZE: {  // batch_normalize (:14-20): zero vectors stay zero
+          const T m = s_sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+          if (m != T(0)) { v0 = v0 / m; v1 = v1 / m; v2 = v2 / m; }
+          break;
+        }
+        default: break;
+      }
+    }
+    vp.vec[e] = v0;
+    vp.vec[vp.stride + e] = v1;
+    vp.vec[2 * vp.stride + e] = v2;
+  }
+}
+
+template <typename T>
+__global__ void ab_vec_component_kernel(const T* __restrict__ vec, uint64_t stride, uint64_t n, int what, T* __restrict__ out) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+    const T v0 = vec[e], v1 = vec[stride + e], v2 = vec[2 * stride + e];
+    T r;
+    switch (what) {
+      case AB_VC_X: r = v0; break;
+      case AB_VC_Y: r = v1; break;
+      case AB_VC_Z: r = v2; break;
+      case AB_VC_PHI: r = atan2_(v1, v0); break;
+      case AB_VC_THETA: r = sizeof(T) == 4 ? (T)acosf((float)v2) : (T)acos((double)v2); break;
+      default: r = s_sqrt(v0 * v0 + v1 * v1 + v2 * v2); break;
+    }
+    out[e] = r;
+  }
+}
+
+}  // namespace ab

@@ -297,14 +297,250 @@ def from_sdf(sdf_, co_resolution, *, dtype=None, device=0, normalize=True):
     return out
 
 
+class _DevBuf:
+    """A device allocation through the C ABI (freed on close / garbage collection)."""
+
+    def __init__(self, nbytes, device):
+        self.ptr = C.c_void_p()
+        self.device = device
+        cabi.check(cabi.lib().ab_device_alloc(int(nbytes), device, C.byref(self.ptr)))
+
+    @classmethod
+    def upload(cls, arr, device):
+        arr = np.ascontiguousarray(arr)
+        buf = cls(arr.nbytes, device)
+        cabi.check(cabi.lib().ab_memcpy_h2d(buf.ptr, arr.ctypes.data, arr.nbytes, device, None))
+        return buf
+
+    def download(self, out, offset=0):
+        cabi.check(cabi.lib().ab_memcpy_d2h(out.ctypes.data, C.c_void_p(self.ptr.value + offset), out.nbytes, self.device,
+                                            None))
+
+    def close(self):
+        if self.ptr.value:
+            cabi.lib().ab_device_free(self.ptr, self.device)
+            self.ptr = C.c_void_p()
+
+    __del__ = close
+
+
+def _field_args(u, dtype):
+    u = np.asarray(u)
+    if u.ndim not in (2, 3):
+        raise ValueError("the field must be a 2D or 3D array")
+    if dtype is None:
+        dtype = "f32" if u.dtype == np.float32 else "f64"
+    code, npdt = _dtype(dtype)
+    res = tuple(u.shape) + ((1,) if u.ndim == 2 else ())
+    return np.ascontiguousarray(u, dtype=npdt), (C.c_uint32 * 3)(*res), code, npdt
+
+
+def conv_averaging(u, kernel_size, iterations, *, dtype=None, device=0):
+    """post_processing.py:552-599 on the GPU: `iterations` passes of a box filter (scipy.ndimage.convolve placement,
+    mode 'reflect'). `u` is the field reshaped to the grid (smarter_reshape), `kernel_size` an int or one per axis."""
+    if iterations == 0:
+        return u
+    f, res, code, npdt = _field_args(u, dtype)
+    if isinstance(kernel_size, (int, np.integer)):
+        kernel_size = (int(kernel_size),) * f.ndim
+    kernel_size = tuple(int(k) for k in np.asarray(kernel_size).reshape(-1))
+    if len(kernel_size) != f.ndim:
+        raise ValueError("Dimension of the kernel and the field must match!")
+    ks = (C.c_uint32 * 3)(*(kernel_size + ((1,) if f.ndim == 2 else ())))
+    d_in, d_out = _DevBuf.upload(f, device), _DevBuf(f.nbytes, device)
+    try:
+        cabi.check(cabi.lib().ab_box_filter(d_in.ptr, res, ks, int(iterations), code, d_out.ptr, device, None))
+        out = np.empty(f.shape, dtype=npdt)
+        d_out.download(out)
+        cabi.check(cabi.lib().ab_stream_sync(device, None))
+    finally:
+        d_in.close()
+        d_out.close()
+    return out
+
+
+def conv_edge_detection(u, *, dtype=None, device=0):
+    """post_processing.py:602-623 on the GPU: the 3x3 edge kernel over the first two axes."""
+    f, res, code, npdt = _field_args(u, dtype)
+    d_in, d_out = _DevBuf.upload(f, device), _DevBuf(f.nbytes, device)
+    try:
+        cabi.check(cabi.lib().ab_edge_filter(d_in.ptr, res, code, d_out.ptr, device, None))
+        out = np.empty(f.shape, dtype=npdt)
+        d_out.download(out)
+        cabi.check(cabi.lib().ab_stream_sync(device, None))
+    finally:
+        d_in.close()
+        d_out.close()
+    return out
+
+
 class VectorFieldFromSDF:
-    """geom_vector.py:188-198: VectorFieldFromSDF(co_resolution).create(sdf_flat)."""
+    """geom_vector.py:188-198 + the modifiers of ModifyVectorObject (modifications.py:1712-1971): the gradient field of
+    an SDF (from_sdf) followed by the recorded elementwise modifiers, evaluated in two launches on the device
+    (ab_fd_gradient, ab_vec_apply) without the (3, N) field visiting the host in between."""
 
     def __init__(self, co_resolution):
         self.co_resolution = co_resolution
+        self._ops = []
+        self._mod = []
 
-    def create(self, sdf_, **kw):
-        return from_sdf(sdf_, self.co_resolution, **kw)
+    @property
+    def modifications(self):
+        return self._mod
+
+    def _record(self, name, opcode, *operands):
+        if len(self._ops) >= cabi.AB_MAX_VEC_OPS:
+            raise ValueError(f"at most {cabi.AB_MAX_VEC_OPS} vector modifiers per field")
+        self._mod.append(name)
+        self._ops.append((opcode, operands))
+        return self
+
+    def add(self, second_field):
+        return self._record("add", cabi.AB_VOP_ADD, ("any", second_field))
+
+    def subtract(self, second_field):
+        return self._record("subtract", cabi.AB_VOP_SUB, ("any", second_field))
+
+    def rescale(self, second_field):
+        return self._record("rescale", cabi.AB_VOP_RESCALE, ("scale", second_field))
+
+    def rotate_phi(self, phi):
+        return self._record("rotate_phi", cabi.AB_VOP_ROT_Z, ("angle", phi))
+
+    def rotate_theta(self, theta):
+        return self._record("rotate_theta", cabi.AB_VOP_ROT_THETA, ("angle", theta))
+
+    def rotate_x(self, alpha):
+        return self._record("rotate_x", cabi.AB_VOP_ROT_X, ("angle", alpha))
+
+    def rotate_y(self, alpha):
+        return self._record("rotate_y", cabi.AB_VOP_ROT_Y, ("angle", alpha))
+
+    def rotate_z(self, alpha):
+        return self._record("rotate_z", cabi.AB_VOP_ROT_Z, ("angle", alpha))
+
+    def rotate_axis(self, axis, alpha):
+        return self._record("rotate_axis", cabi.AB_VOP_ROT_AXIS, ("axis", axis), ("angle", alpha))
+
+    def revolution_x(self, co):
+        return self._record("revolution_x", cabi.AB_VOP_REVOLVE_X, ("coords", co))
+
+    def revolution_y(self, co):
+        return self._record("revolution_y", cabi.AB_VOP_REVOLVE_Y, ("coords", co))
+
+    def revolution_z(self, co):
+        return self._record("revolution_z", cabi.AB_VOP_REVOLVE_Z, ("coords", co))
+
+    def normalize(self):
+        return self._record("normalize", cabi.AB_VOP_NORMALIZE)
+
+    # ---- evaluation ----
+    @staticmethod
+    def _operand(role, value, n, npdt, device, keep):
+        """-> (kind, vec3, scalar, device pointer, stride) of one operand; arrays are uploaded as `npdt`."""
+        v = np.asarray(value, dtype=np.float64)
+        if role == "coords" or (role in ("any", "scale", "axis") and v.ndim == 2):
+            if v.shape != (3, n):
+                raise ValueError(f"a per-point vector operand must have shape (3, {n}), got {v.shape}")
+            buf = _DevBuf.upload(v.astype(npdt), device)
+            keep.append(buf)
+            return cabi.AB_VK_VEC_ARRAY, (0.0, 0.0, 0.0), 0.0, buf.ptr.value, n
+        if role in ("any", "axis") and v.size == 3 and n != 3:
+            return cabi.AB_VK_VEC3, tuple(float(x) for x in v.reshape(3)), 0.0, None, 0
+        if v.size == 1 and role != "axis":
+            return cabi.AB_VK_SCALAR, (0.0, 0.0, 0.0), float(v.reshape(())), None, 0
+        if v.shape == (n,) and role != "axis":
+            buf = _DevBuf.upload(v.astype(npdt), device)
+            keep.append(buf)
+            return cabi.AB_VK_ARRAY, (0.0, 0.0, 0.0), 0.0, buf.ptr.value, n
+        raise ValueError(f"operand of shape {v.shape} is not accepted here (field of {n} points)")
+
+    def _run(self, sdf_, dtype, device, components=()):
+        res = tuple(int(r) for r in np.asarray(self.co_resolution).reshape(-1))
+        dims = len(res)
+        f = np.asarray(sdf_)
+        if dtype is None:
+            dtype = "f32" if f.dtype == np.float32 else "f64"
+        code, npdt = _dtype(dtype)
+        n = int(np.prod(res))
+        if self._ops and dims != 3:
+            raise ValueError("vector modifiers need a 3D field")
+        f = np.ascontiguousarray(f.reshape(-1), dtype=npdt)
+        if f.size != n:
+            raise ValueError(f"Cannot reshape the pattern with shape {f.shape}")
+        if any(r < 2 for r in res):
+            raise ValueError("Shape of array too small to calculate a numerical gradient, at least 2 elements are "
+                             "required.")
+        lib = cabi.lib()
+        stride = (n + 3) // 4 * 4
+        keep = []
+        d_f, d_v = _DevBuf.upload(f, device), _DevBuf(3 * stride * f.itemsize, device)
+        keep += [d_f, d_v]
+        try:
+            g = cabi.make_grid((0.0, 0.0, 0.0), res + ((1,) if dims == 2 else ()))
+            cabi.check(lib.ab_fd_gradient(d_f.ptr, 0, C.byref(g), dims, code, 1, d_v.ptr, stride, device, None))
+            if self._ops:
+                ops = (cabi.ab_vec_op * len(self._ops))()
+                for k, (opcode, operands) in enumerate(self._ops):
+                    ops[k].opcode = opcode
+                    for j, (role, value) in enumerate(operands):
+                        kind, c, s, ptr, st = self._operand(role, value, n, npdt, device, keep)
+                        if j == 0:
+                            ops[k].kind0, ops[k].s0, ops[k].a0, ops[k].stride0 = kind, s, ptr, st
+                            ops[k].c = (C.c_double * 3)(*c)
+                        else:
+                            ops[k].kind1, ops[k].s1, ops[k].a1, ops[k].stride1 = kind, s, ptr, st
+                cabi.check(lib.ab_vec_apply(d_v.ptr, stride, n, ops, len(self._ops), code, device, None))
+            out = {}
+            if components:
+                d_c = _DevBuf(n * f.itemsize, device)
+                keep.append(d_c)
+                ids = {"x": cabi.AB_VC_X, "y": cabi.AB_VC_Y, "z": cabi.AB_VC_Z, "phi": cabi.AB_VC_PHI,
+                       "theta": cabi.AB_VC_THETA, "length": cabi.AB_VC_LENGTH}
+                for name in components:
+                    cabi.check(lib.ab_vec_component(d_v.ptr, stride, n, ids[name], code, d_c.ptr, device, None))
+                    out[name] = np.empty(n, dtype=npdt)
+                    d_c.download(out[name])
+            else:
+                vec = np.empty((dims, n), dtype=npdt)
+                for r in range(dims):
+                    d_v.download(vec[r], r * stride * f.itemsize)
+                out["vec"] = vec
+            cabi.check(lib.ab_stream_sync(device, None))
+        finally:
+            for b in keep:
+                b.close()
+        return out
+
+    def create(self, sdf_, *, dtype=None, device=0):
+        return self._run(sdf_, dtype, device)["vec"]
+
+    propagate = create
+
+    def x(self, sdf_, **kw):
+        return self._component("x", sdf_, **kw)
+
+    def y(self, sdf_, **kw):
+        return self._component("y", sdf_, **kw)
+
+    def z(self, sdf_, **kw):
+        return self._component("z", sdf_, **kw)
+
+    def phi(self, sdf_, **kw):
+        return self._component("phi", sdf_, **kw)
+
+    def theta(self, sdf_, **kw):
+        return self._component("theta", sdf_, **kw)
+
+    def length(self, sdf_, **kw):
+        return self._component("length", sdf_, **kw)
+
+    def _component(self, name, sdf_, *, dtype=None, device=0):
+        return self._run(sdf_, dtype, device, components=(name,))[name]
+
+    def components(self, sdf_, names=("x", "y", "z", "phi", "theta", "length"), *, dtype=None, device=0):
+        """Several scalar maps from ONE evaluation of the pipeline (the reference re-evaluates it per call)."""
+        return self._run(sdf_, dtype, device, components=tuple(names))
 
 
 # ---- point clouds ----------------------------------------------------------------------------------------------------------------

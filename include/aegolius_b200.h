@@ -203,6 +203,50 @@ int ab_nn_points(const void* cloud_dev, uint64_t m, int dim, const void* co, int
 int ab_cloud_upload(const double* points_host, uint64_t m, int dim, uint64_t row_stride, int dtype, int device,
                     void** out_dev);
 
+/* ---- whole-field kernels that follow the SDF evaluation in SPOMSO pipelines (device pointers, asynchronous) ---- */
+
+/* Replaces conv_averaging (post_processing.py:552-599): `iterations` passes of a box filter of ksize[3] samples over a
+ * C-ordered field of res[3] samples (2D fields: res[2] = ksize[2] = 1); scipy.ndimage.convolve placement, mode
+ * 'reflect'. field and out must not overlap. iterations == 0 copies. */
+int ab_box_filter(const void* field_dev, const uint32_t res[3], const uint32_t ksize[3], uint32_t iterations, int dtype,
+                  void* out_dev, int device, void* stream);
+/* Replaces conv_edge_detection (post_processing.py:602-623): 9u - (3x3 sum over the first two axes), 'reflect'. */
+int ab_edge_filter(const void* field_dev, const uint32_t res[3], int dtype, void* out_dev, int device, void* stream);
+
+/* Vector-field modifiers (vector_modification_functions.py:14-172; methods modifications.py:1712-1971). */
+#define AB_MAX_VEC_OPS 32
+typedef enum ab_vec_opcode {
+  AB_VOP_ADD = 1,       /* add_vectors        :23-28   operand 0: scalar | vec3 | (N,) | (3,N) */
+  AB_VOP_SUB = 2,       /* subtract_vectors   :31-36 */
+  AB_VOP_RESCALE = 3,   /* rescale_vectors    :39-41   operand 0: scalar | (N,) | (3,N) */
+  AB_VOP_ROT_Z = 4,     /* rotate_vectors_z_axis :104-113 and rotate_vectors_phi :44-52; operand 0: angle scalar | (N,) */
+  AB_VOP_ROT_THETA = 5, /* rotate_vectors_theta :55-69 */
+  AB_VOP_ROT_X = 6,     /* :72-81 */
+  AB_VOP_ROT_Y = 7,     /* :84-93 (the reference's sign convention) */
+  AB_VOP_ROT_AXIS = 8,  /* rotate_vectors_axis :116-131; operand 0: axis vec3 | (3,N); operand 1: angle scalar | (N,) */
+  AB_VOP_REVOLVE_X = 9, /* revolve_field_x :134-146; operand 0: coordinates (3,N) */
+  AB_VOP_REVOLVE_Y = 10,
+  AB_VOP_REVOLVE_Z = 11,
+  AB_VOP_NORMALIZE = 12 /* batch_normalize :14-20 */
+} ab_vec_opcode;
+typedef enum ab_vec_kind { AB_VK_NONE = 0, AB_VK_SCALAR = 1, AB_VK_VEC3 = 2, AB_VK_ARRAY = 3, AB_VK_VEC_ARRAY = 4 } ab_vec_kind;
+typedef struct ab_vec_op {
+  uint32_t opcode;
+  uint32_t kind0, kind1;
+  double c[3];        /* AB_VK_VEC3 operand */
+  double s0, s1;      /* AB_VK_SCALAR operands */
+  const void* a0;     /* DEVICE arrays of `dtype`: (N,) for AB_VK_ARRAY, (3, stride) for AB_VK_VEC_ARRAY */
+  const void* a1;
+  uint64_t stride0, stride1;
+} ab_vec_op;
+/* Applies ops[0..n_ops) in order to the (3, vec_stride) field in place, one pass over memory. */
+int ab_vec_apply(void* vec_dev, uint64_t vec_stride, uint64_t n, const ab_vec_op* ops, uint32_t n_ops, int dtype,
+                 int device, void* stream);
+typedef enum ab_vec_component_id { AB_VC_X = 0, AB_VC_Y = 1, AB_VC_Z = 2, AB_VC_PHI = 3, AB_VC_THETA = 4, AB_VC_LENGTH = 5 } ab_vec_component_id;
+/* VectorField.x/y/z/phi/theta/length (geom.py:262-362): phi = atan2(y, x), theta = acos(z), length = |v|. */
+int ab_vec_component(const void* vec_dev, uint64_t vec_stride, uint64_t n, int what, int dtype, void* out_dev,
+                     int device, void* stream);
+
 /* Replaces from_sdf (vector_functions.py:130-139): np.gradient of the reshaped field (unit spacing, 2nd-order
  * central inside, 1st-order one-sided on the faces) and, if normalize != 0, batch_normalize
  * (vector_modification_functions.py:14-20). field: DEVICE (points of the whole grid) of dtype; out: DEVICE
