@@ -918,6 +918,22 @@ static unsigned stream_grid(const DevInfo& di, uint64_t n, int nt) {
   return (unsigned)std::max<uint64_t>(1, std::min(want, cap));
 }
 
+// launch geometry of the stencil kernels: see Field3 in ab_fields.cuh (2D fields are viewed as (1, nx, ny))
+static int field_launch(const uint32_t res[3], bool allow_2d_view, Field3& f, dim3& grid, int& nt, int* is2d) {
+  const bool two_d = allow_2d_view && res[2] == 1;
+  f.n0 = two_d ? 1 : res[0];
+  f.n1 = two_d ? res[0] : res[1];
+  f.n2 = two_d ? res[1] : res[2];
+  if (is2d) *is2d = two_d ? 1 : 0;
+  if (f.n1 > 65535 || f.n0 > 65535) return fail(AB_ETOOLARGE, "field axis longer than 65535 samples");
+  // SPOMSO grids are odd (129, 513, 1025 ...): spread the warps of a row evenly over its CTAs instead of leaving a nearly
+  // empty last one (513 -> 3 x 192 threads, 1025 -> 5 x 224)
+  const uint32_t warps = (f.n2 + 31) / 32, ctas = (warps + 7) / 8;
+  nt = (int)((warps + ctas - 1) / ctas) * 32;
+  grid = dim3(ctas, f.n1, f.n0);
+  return AB_OK;
+}
+
 template <typename T>
 static int box_filter_t(const void* field, const uint32_t res[3], const uint32_t ksize[3], uint32_t iterations, void* out,
                         int device, cudaStream_t st) {
@@ -926,7 +942,11 @@ static int box_filter_t(const void* field, const uint32_t res[3], const uint32_t
   if (rc) return rc;
   const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
   const T norm = (T)((double)ksize[0] * ksize[1] * ksize[2]);
-  const unsigned grid = stream_grid(di, n, 256);
+  Field3 f;
+  dim3 grid;
+  int nt, is2d;
+  rc = field_launch(res, ksize[2] == 1, f, grid, nt, &is2d);
+  if (rc) return rc;
   int axes[3], n_axes = 0;
   for (int a = 0; a < 3; a++)
     if (ksize[a] > 1) axes[n_axes++] = a;
@@ -935,7 +955,7 @@ static int box_filter_t(const void* field, const uint32_t res[3], const uint32_t
     return AB_OK;
   }
   if (n_axes == 0) {  // a 1x1x1 kernel: u / 1
-    ab_scale_copy_kernel<T><<<grid, 256, 0, st>>>((const T*)field, (T*)out, n, norm);
+    ab_scale_copy_kernel<T><<<stream_grid(di, n, 256), 256, 0, st>>>((const T*)field, (T*)out, n, norm);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
     return AB_OK;
@@ -949,11 +969,9 @@ static int box_filter_t(const void* field, const uint32_t res[3], const uint32_t
     for (int ai = 0; ai < n_axes; ai++, p++) {
       const int a = axes[ai];
       T* dst = ((passes - 1 - p) & 1u) ? tmp : (T*)out;  // the last pass lands in `out`
-      const uint32_t n_axis = res[a];
-      const uint32_t n_inner = a == 0 ? res[1] * res[2] : (a == 1 ? res[2] : 1);
       const int k = (int)ksize[a];
       const int t0 = -((k & 1) ? k / 2 : k / 2 - 1);  // scipy.ndimage.convolve placement, see oracle/fields_np.py
-      ab_box_axis_kernel<T><<<grid, 256, 0, st>>>(src, dst, n, n_axis, n_inner, k, t0, norm, ai == n_axes - 1 ? 1 : 0);
+      ab_box_axis_kernel<T><<<grid, nt, 0, st>>>(src, dst, f, is2d ? a + 1 : a, k, t0, norm, ai == n_axes - 1 ? 1 : 0);
       src = dst;
     }
   }
@@ -990,13 +1008,13 @@ extern "C" int ab_edge_filter(const void* field_dev, const uint32_t res[3], int 
   rc = check_field_args(field_dev, res, out_dev);
   if (rc) return rc;
   if (field_dev == out_dev) return fail(AB_EINVAL, "edge filter cannot run in place");
-  DevInfo di;
-  rc = dev_info(device, di);
+  Field3 f;
+  dim3 grid;
+  int nt, is2d;
+  rc = field_launch(res, true, f, grid, nt, &is2d);
   if (rc) return rc;
-  const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
-  const unsigned grid = stream_grid(di, n, 256);
-  if (dtype == AB_F32) ab_edge_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)field_dev, (float*)out_dev, res[0], res[1], res[2]);
-  else if (dtype == AB_F64) ab_edge_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)field_dev, (double*)out_dev, res[0], res[1], res[2]);
+  if (dtype == AB_F32) ab_edge_kernel<float><<<grid, nt, 0, (cudaStream_t)stream>>>((const float*)field_dev, (float*)out_dev, f, is2d);
+  else if (dtype == AB_F64) ab_edge_kernel<double><<<grid, nt, 0, (cudaStream_t)stream>>>((const double*)field_dev, (double*)out_dev, f, is2d);
   else return fail(AB_EINVAL, "bad dtype %d", dtype);
   CUDA_TRY(cudaGetLastError());
   g_launches++;

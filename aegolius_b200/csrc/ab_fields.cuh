@@ -13,27 +13,41 @@ namespace ab {
 
 // scipy.ndimage 'reflect' (d c b a | a b c d | d c b a), valid for any offset
 AB_DEV int reflect_index(int i, int n) {
+  if ((unsigned)i < (unsigned)n) return i;  // the common case
   const int period = 2 * n;
   i %= period;
   if (i < 0) i += period;
   return i >= n ? period - 1 - i : i;
 }
 
-// one axis of the separable box filter over a C-ordered (n_outer, n_axis, n_inner) view: the sum of k taps starting at
-// offset t0; the last pass of an iteration also divides by the kernel volume (the reference's filter is ones / norm)
+// The stencil kernels see the field as a C-ordered (n0, n1, n2) array (2D fields arrive as (1, nx, ny)) and take their
+// coordinates from the launch grid: x = blockIdx.z, y = blockIdx.y, z = blockIdx.x * blockDim.x + threadIdx.x — no integer
+// division, loads coalesced along z.
+struct Field3 {
+  uint32_t n0, n1, n2;
+};
+
+// one axis of the separable box filter: the sum of k taps starting at offset t0 along `axis`; the last pass of an iteration
+// also divides by the kernel volume (the reference's filter is ones / norm)
 template <typename T>
-__global__ void ab_box_axis_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t n, uint32_t n_axis, uint32_t n_inner,
-                                   int k, int t0, T norm, int divide) {
-  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t row = e / n_inner;
-    const uint32_t j = (uint32_t)(e - row * n_inner);
-    const uint64_t o = row / n_axis;
-    const int i = (int)(row - o * n_axis);
-    const T* base = in + o * n_axis * (uint64_t)n_inner + j;
-    T s = T(0);
-    for (int t = 0; t < k; t++) s = s + base[(uint64_t)reflect_index(i + t0 + t, (int)n_axis) * n_inner];
-    out[e] = divide ? s / norm : s;
+__global__ void __launch_bounds__(256) ab_box_axis_kernel(const T* __restrict__ in, T* __restrict__ out, Field3 f, int axis, int k,
+                                                          int t0, T norm, int divide) {
+  const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, x = blockIdx.z;
+  if (z >= f.n2) return;
+  const uint64_t plane = (uint64_t)f.n1 * f.n2;
+  const uint64_t e = x * plane + (uint64_t)y * f.n2 + z;
+  T s = T(0);
+  if (axis == 2) {
+    const T* row = in + (e - z);
+    for (int t = 0; t < k; t++) s = s + row[reflect_index((int)z + t0 + t, (int)f.n2)];
+  } else if (axis == 1) {
+    const T* col = in + x * plane + z;
+    for (int t = 0; t < k; t++) s = s + col[(uint64_t)reflect_index((int)y + t0 + t, (int)f.n1) * f.n2];
+  } else {
+    const T* col = in + (uint64_t)y * f.n2 + z;
+    for (int t = 0; t < k; t++) s = s + col[(uint64_t)reflect_index((int)x + t0 + t, (int)f.n0) * plane];
   }
+  out[e] = divide ? s / norm : s;
 }
 
 template <typename T>
@@ -41,23 +55,30 @@ __global__ void ab_scale_copy_kernel(const T* __restrict__ in, T* __restrict__ o
   for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) out[e] = in[e] / norm;
 }
 
-// 9 u - sum of the 3x3 neighbourhood in the first two axes of a C-ordered (nx, ny, nz) field
+// 9 u - sum of the 3x3 neighbourhood over the two axes (ax, ay) = (0, 1) of a 3D field or (1, 2) of a 2D one
 template <typename T>
-__global__ void ab_edge_kernel(const T* __restrict__ in, T* __restrict__ out, uint32_t nx, uint32_t ny, uint32_t nz) {
-  const uint64_t n = (uint64_t)nx * ny * nz;
-  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t z = (uint32_t)(e % nz);
-    const uint64_t r = e / nz;
-    const int y = (int)(r % ny), x = (int)(r / ny);
-    T s = T(0);
+__global__ void __launch_bounds__(256) ab_edge_kernel(const T* __restrict__ in, T* __restrict__ out, Field3 f, int is2d) {
+  const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, x = blockIdx.z;
+  if (z >= f.n2) return;
+  const uint64_t plane = (uint64_t)f.n1 * f.n2;
+  const uint64_t e = x * plane + (uint64_t)y * f.n2 + z;
+  T s = T(0);
+  if (is2d) {  // (1, nx, ny): the stencil spans y (slow) and z (fast)
 #pragma unroll
-    for (int dx = -1; dx <= 1; dx++) {
-      const uint64_t xo = (uint64_t)reflect_index(x + dx, (int)nx) * ny;
+    for (int da = -1; da <= 1; da++) {
+      const T* row = in + (uint64_t)reflect_index((int)y + da, (int)f.n1) * f.n2;
 #pragma unroll
-      for (int dy = -1; dy <= 1; dy++) s = s + in[(xo + (uint64_t)reflect_index(y + dy, (int)ny)) * nz + z];
+      for (int db = -1; db <= 1; db++) s = s + row[reflect_index((int)z + db, (int)f.n2)];
     }
-    out[e] = T(9) * in[e] - s;
+  } else {
+#pragma unroll
+    for (int da = -1; da <= 1; da++) {
+      const T* pl = in + (uint64_t)reflect_index((int)x + da, (int)f.n0) * plane + z;
+#pragma unroll
+      for (int db = -1; db <= 1; db++) s = s + pl[(uint64_t)reflect_index((int)y + db, (int)f.n1) * f.n2];
+    }
   }
+  out[e] = T(9) * in[e] - s;
 }
 
 // ---- vector-field modifiers ----------------------------------------------------------------------------------------------

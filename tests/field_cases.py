@@ -2,7 +2,7 @@
 import numpy as np
 
 AVG_CASES = [((9, 7, 5), (5, 5, 1), 1), ((9, 7, 5), (3, 3, 3), 2), ((8, 6), (2, 4), 1), ((7, 9, 4), (4, 3, 2), 3),
-             ((5, 5), (7, 7), 1), ((6, 5, 3), (2, 2, 1), 1)]
+             ((5, 5), (7, 7), 1), ((6, 5, 3), (2, 2, 1), 1), ((6, 5, 1), (3, 2, 4), 2)]
 EDGE_CASES = [(9, 7), (6, 8, 3), (2, 2), (3, 3, 1)]
 RES = (11, 9, 7)
 

@@ -68,6 +68,45 @@ def main():
             print(json.dumps({"case": f"nn {spec.res} x 1M", "ms": ms, "Tpairs_per_s": pairs / ms / 1e9,
                               "Mqueries_per_s": spec.n_points / ms / 1e3}), flush=True)
             continue
+        if name == "fields":  # whole-field streaming kernels on a 513^3 fp32 field (device time, algorithmic bytes)
+            import ctypes as C
+            lib = cabi.lib()
+            res = (513, 513, 513)
+            n = res[0] * res[1] * res[2]
+            stride = (n + 3) // 4 * 4
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            f = torch.randn(n, dtype=torch.float32, device=dev)
+            o = torch.empty(n, dtype=torch.float32, device=dev)
+            v = torch.randn(3, stride, dtype=torch.float32, device=dev)
+            ang = torch.randn(n, dtype=torch.float32, device=dev)
+            r3 = (C.c_uint32 * 3)(*res)
+            k3 = (C.c_uint32 * 3)(5, 5, 1)
+            g = cabi.make_grid((0.0, 0.0, 0.0), res)
+            ops = (cabi.ab_vec_op * 2)()
+            ops[0].opcode, ops[0].kind0, ops[0].a0 = cabi.AB_VOP_ROT_Z, cabi.AB_VK_ARRAY, ang.data_ptr()
+            ops[1].opcode, ops[1].kind0, ops[1].kind1, ops[1].a1 = cabi.AB_VOP_ROT_AXIS, cabi.AB_VK_VEC3, cabi.AB_VK_ARRAY, ang.data_ptr()
+            ops[1].c = (C.c_double * 3)(1.0, 0.0, 0.0)
+            jobs = {
+                "box_filter_5x5x1 (2 passes: 16 B/pt)": (lambda: cabi.check(lib.ab_box_filter(f.data_ptr(), r3, k3, 1, cabi.AB_F32, o.data_ptr(), 0, st)), 16),
+                "edge_filter (8 B/pt)": (lambda: cabi.check(lib.ab_edge_filter(f.data_ptr(), r3, cabi.AB_F32, o.data_ptr(), 0, st)), 8),
+                "from_sdf (16 B/pt)": (lambda: cabi.check(lib.ab_fd_gradient(f.data_ptr(), 0, C.byref(g), 3, cabi.AB_F32, 1, v.data_ptr(), stride, 0, st)), 16),
+                "vec rotate_z+rotate_axis (32 B/pt)": (lambda: cabi.check(lib.ab_vec_apply(v.data_ptr(), stride, n, ops, 2, cabi.AB_F32, 0, st)), 32),
+                "vec component phi (12 B/pt)": (lambda: cabi.check(lib.ab_vec_component(v.data_ptr(), stride, n, cabi.AB_VC_PHI, cabi.AB_F32, o.data_ptr(), 0, st)), 12),
+            }
+            for jn, (fn, bpp) in jobs.items():
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(args.reps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); fn(); e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ms = float(np.median(ts))
+                print(json.dumps({"case": jn, "res": res, "ms": round(ms, 4), "GBps": round(bpp * n / ms / 1e6, 1),
+                                  "hbm_frac": round(bpp * n / ms / 1e6 / peak, 4)}), flush=True)
+            continue
         obj, spec, dt, grad = cases[name]
         prog = ab.flatten(obj)
         tdt = torch.float32 if dt == "f32" else torch.float64
