@@ -873,26 +873,32 @@ extern "C" int ab_nn_points(const void* cloud_dev, uint64_t m, int dim, const vo
 template <typename T>
 static int fd_t(const void* field, uint32_t plane0, const ab_grid* grid, int dims, int normalize, void* out,
                 uint64_t out_stride, int device, cudaStream_t st) {
-  DevInfo di;
-  int rc = dev_info(device, di);
-  if (rc) return rc;
   FDParams<T> kp{};
   kp.field = (const T*)field;
-  kp.plane0 = plane0;
-  for (int c = 0; c < 3; c++) kp.res[c] = grid->res[c];
-  kp.slab_begin = grid->slab_begin;
-  kp.slab_end = grid->slab_end;
-  kp.dims = dims;
+  const bool three = dims == 3;
+  // view: 3D (n0, n1, n2) = res; 2D (1, nx, ny). The slab runs over the first axis of the reference layout.
+  kp.n0 = three ? grid->res[0] : 1;
+  kp.n1 = three ? grid->res[1] : grid->res[0];
+  kp.n2 = three ? grid->res[2] : grid->res[1];
+  kp.o0 = three ? plane0 : 0;
+  kp.o1 = three ? 0 : plane0;
+  kp.b0 = three ? grid->slab_begin : 0;
+  kp.e0 = three ? grid->slab_end : 1;
+  kp.b1 = three ? 0 : grid->slab_begin;
+  kp.e1 = three ? grid->res[1] : grid->slab_end;
+  kp.has0 = three ? 1 : 0;
   kp.normalize = normalize;
+  kp.chunk = 32;
   kp.out = (T*)out;
   kp.out_stride = out_stride;
-  const uint64_t n = (uint64_t)(grid->slab_end - grid->slab_begin) * grid->res[1] * (dims == 3 ? grid->res[2] : 1);
+  const uint64_t n = (uint64_t)(kp.e0 - kp.b0) * (kp.e1 - kp.b1) * kp.n2;
   if (out_stride < n) return fail(AB_EINVAL, "out_stride < slab points");
-  constexpr int NT = 256;
-  uint64_t blocks = (n + NT - 1) / NT;
-  uint64_t cap = (uint64_t)di.sms * 16;
-  unsigned gridDim = (unsigned)(blocks < cap ? blocks : cap);
-  ab_fd_kernel<T, NT><<<gridDim, NT, 0, st>>>(kp);
+  const uint32_t rows = kp.e1 - kp.b1, chunks = (kp.e0 - kp.b0 + kp.chunk - 1) / kp.chunk;
+  if (rows > 65535 || chunks > 65535) return fail(AB_ETOOLARGE, "from_sdf: more than 65535 rows per plane");
+  // odd row lengths (129, 513, 1025 ...): spread the warps of a row evenly over its CTAs
+  const uint32_t warps = (kp.n2 + 31) / 32, ctas = (warps + 7) / 8;
+  const int nt = (int)((warps + ctas - 1) / ctas) * 32;
+  ab_fd_kernel<T><<<dim3(ctas, rows, chunks), nt, 0, st>>>(kp);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return AB_OK;

@@ -311,53 +311,75 @@ __global__ void ab_nn_finalize_kernel(float* out, uint64_t n) {
 }
 
 // ---- from_sdf -----------------------------------------------------------------------------------------------------------
+// The field is seen as a C-ordered (n0, n1, n2) array; a 2D (nx, ny) field arrives as (1, nx, ny) so that the fastest axis
+// is always the long one. Thread = one (i1, i2) column position (i2 from blockIdx.x/threadIdx.x: coalesced; i1 =
+// blockIdx.y), marching over a chunk of i0 planes (blockIdx.z) with the three i0-neighbours kept in registers, so every
+// field sample is fetched from DRAM once and there is no integer division anywhere.
 template <typename T>
 struct FDParams {
-  const T* field;        // planes [plane0, ...) of the whole grid
-  uint32_t plane0;
-  uint32_t res[3];
-  uint32_t slab_begin, slab_end;
-  int32_t dims;          // 2 or 3
+  const T* field;        // samples [o0.., o1.., 0..) of the whole grid: buffer origin (o0, o1)
+  uint32_t n0, n1, n2;   // whole-grid extents of the view
+  uint32_t o0, o1;       // first i0 / i1 held by `field`
+  uint32_t b0, e0, b1, e1;  // output range [b0, e0) x [b1, e1) x [0, n2)
+  int32_t has0;          // 1: 3D (three components, row 0 = d/di0); 0: 2D view (rows = d/di1, d/di2)
   int32_t normalize;
-  T* out;                // (dims, out_stride), indexed from the slab's first point
+  uint32_t chunk;        // i0 planes per CTA
+  T* out;                // (dims, out_stride), indexed from the first output sample
   uint64_t out_stride;
 };
 
+// np.gradient, unit spacing, edge_order=1, from the three samples along one axis
 template <typename T>
-AB_DEV T fd_axis(const T* f, uint64_t k, uint64_t stride, uint32_t i, uint32_t n) {
-  // np.gradient, unit spacing, edge_order=1
+AB_DEV T fd_three(T fm, T fc, T fp, uint32_t i, uint32_t n) {
   if (n < 2) return T(0);
-  if (i == 0) return f[k + stride] - f[k];
-  if (i == n - 1) return f[k] - f[k - stride];
-  return (f[k + stride] - f[k - stride]) * T(0.5);
+  if (i == 0) return fp - fc;
+  if (i == n - 1) return fc - fm;
+  return (fp - fm) * T(0.5);
 }
 
-template <typename T, int NT>
-__global__ void __launch_bounds__(NT) ab_fd_kernel(const __grid_constant__ FDParams<T> kp) {
-  const uint32_t n0 = kp.res[0], n1 = kp.res[1], n2 = kp.dims == 3 ? kp.res[2] : 1;
-  const uint64_t plane = (uint64_t)n1 * n2;
-  const uint64_t n = (uint64_t)(kp.slab_end - kp.slab_begin) * plane;
-  for (uint64_t l = (uint64_t)blockIdx.x * NT + threadIdx.x; l < n; l += (uint64_t)gridDim.x * NT) {
-    uint32_t i0 = (uint32_t)(l / plane);
-    uint32_t rem = (uint32_t)(l - (uint64_t)i0 * plane);
-    uint32_t i1 = rem / n2, i2 = rem - i1 * n2;
-    i0 += kp.slab_begin;
-    const uint64_t k = (uint64_t)(i0 - kp.plane0) * plane + rem;  // index into the field buffer
-    T g0 = fd_axis(kp.field, k, plane, i0, n0);
-    T g1 = fd_axis(kp.field, k, (uint64_t)n2, i1, n1);
-    T g2 = kp.dims == 3 ? fd_axis(kp.field, k, (uint64_t)1, i2, n2) : T(0);
+template <typename T>
+__global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDParams<T> kp) {
+  const uint32_t i2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i2 >= kp.n2) return;
+  const uint32_t i1 = kp.b1 + blockIdx.y;
+  const uint32_t x_begin = kp.b0 + blockIdx.z * kp.chunk;
+  const uint32_t x_end = x_begin + kp.chunk < kp.e0 ? x_begin + kp.chunk : kp.e0;
+  const uint32_t w1 = kp.e1 - kp.b1;                  // output rows per plane
+  const uint64_t fplane = (uint64_t)(kp.n1 - kp.o1) * kp.n2;  // the buffer holds rows [o1, n1) of every plane
+  const T* __restrict__ f = kp.field + (uint64_t)(i1 - kp.o1) * kp.n2 + i2;
+  auto at = [&](uint32_t i0) { return f[(uint64_t)(i0 - kp.o0) * fplane]; };
+  T fm = T(0), fc = at(x_begin), fp = T(0);
+  if (kp.has0 && x_begin > 0) fm = at(x_begin - 1);
+  for (uint32_t i0 = x_begin; i0 < x_end; i0++) {
+    if (kp.has0 && i0 + 1 < kp.n0) fp = at(i0 + 1);
+    const T* c = f + (uint64_t)(i0 - kp.o0) * fplane;
+    const T a1m = i1 > 0 ? c[-(int64_t)kp.n2] : T(0), a1p = i1 + 1 < kp.n1 ? c[kp.n2] : T(0);
+    const T a2m = i2 > 0 ? c[-1] : T(0), a2p = i2 + 1 < kp.n2 ? c[1] : T(0);
+    T g0 = kp.has0 ? fd_three(fm, fc, fp, i0, kp.n0) : T(0);
+    T g1 = fd_three(a1m, fc, a1p, i1, kp.n1);
+    T g2 = fd_three(a2m, fc, a2p, i2, kp.n2);
     if (kp.normalize) {
-      T m = s_sqrt(s_fma(g0, g0, s_fma(g1, g1, g2 * g2)));
+      // 3D: |(g0, g1, g2)|; 2D view: |(g1, g2)| — same nesting as np.linalg.norm's sum of squares is not needed, only
+      // the value to fp rounding (tests: <= 1e-13 fp64)
+      const T m = kp.has0 ? s_sqrt(s_fma(g0, g0, s_fma(g1, g1, g2 * g2))) : s_sqrt(s_fma(g1, g1, g2 * g2));
       if (m != T(0)) {
-        T im = T(1) / m;
+        const T im = T(1) / m;
         g0 *= im;
         g1 *= im;
         g2 *= im;
       }
     }
-    __stcs(kp.out + l, g0);
-    __stcs(kp.out + kp.out_stride + l, g1);
-    if (kp.dims == 3) __stcs(kp.out + 2 * kp.out_stride + l, g2);
+    const uint64_t l = ((uint64_t)(i0 - kp.b0) * w1 + (i1 - kp.b1)) * kp.n2 + i2;
+    if (kp.has0) {
+      __stcs(kp.out + l, g0);
+      __stcs(kp.out + kp.out_stride + l, g1);
+      __stcs(kp.out + 2 * kp.out_stride + l, g2);
+    } else {
+      __stcs(kp.out + l, g1);
+      __stcs(kp.out + kp.out_stride + l, g2);
+    }
+    fm = fc;
+    fc = fp;
   }
 }
 
