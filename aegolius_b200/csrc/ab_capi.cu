@@ -977,7 +977,25 @@ static int box_filter_t(const void* field, const uint32_t res[3], const uint32_t
       T* dst = ((passes - 1 - p) & 1u) ? tmp : (T*)out;  // the last pass lands in `out`
       const int k = (int)ksize[a];
       const int t0 = -((k & 1) ? k / 2 : k / 2 - 1);  // scipy.ndimage.convolve placement, see oracle/fields_np.py
-      ab_box_axis_kernel<T><<<grid, nt, 0, st>>>(src, dst, f, is2d ? a + 1 : a, k, t0, norm, ai == n_axes - 1 ? 1 : 0);
+      const int va = is2d ? a + 1 : a;  // axis in the (n0, n1, n2) view
+      const int divide = ai == n_axes - 1 ? 1 : 0;
+      bool done = false;
+      if (va < 2 && k <= 9) {  // slow axes, small windows: march along the axis with the window in registers
+        const uint32_t chunk = 32, n_axis = va == 0 ? f.n0 : f.n1;
+        const uint32_t chunks = (n_axis + chunk - 1) / chunk;
+        const dim3 mgrid = va == 0 ? dim3(grid.x, f.n1, chunks) : dim3(grid.x, chunks, f.n0);
+        switch (k) {
+#define AB_BOX_K(KK) case KK: ab_box_march_kernel<T, KK><<<mgrid, nt, 0, st>>>(src, dst, f, va, t0, norm, divide, chunk); done = true; break;
+          AB_BOX_K(2) AB_BOX_K(3) AB_BOX_K(4) AB_BOX_K(5) AB_BOX_K(6) AB_BOX_K(7) AB_BOX_K(8) AB_BOX_K(9)
+#undef AB_BOX_K
+          default: break;
+        }
+      }
+      if (!done) {
+        const uint32_t rows = 16;  // y rows one thread marches over
+        const dim3 bgrid(grid.x, (f.n1 + rows - 1) / rows, grid.z);
+        ab_box_axis_kernel<T><<<bgrid, nt, 0, st>>>(src, dst, f, va, k, t0, norm, divide, rows);
+      }
       src = dst;
     }
   }
@@ -1019,8 +1037,11 @@ extern "C" int ab_edge_filter(const void* field_dev, const uint32_t res[3], int 
   int nt, is2d;
   rc = field_launch(res, true, f, grid, nt, &is2d);
   if (rc) return rc;
-  if (dtype == AB_F32) ab_edge_kernel<float><<<grid, nt, 0, (cudaStream_t)stream>>>((const float*)field_dev, (float*)out_dev, f, is2d);
-  else if (dtype == AB_F64) ab_edge_kernel<double><<<grid, nt, 0, (cudaStream_t)stream>>>((const double*)field_dev, (double*)out_dev, f, is2d);
+  const uint32_t chunk = 32;
+  // 3D: (z chunks, y, x chunks); 2D view: (z chunks, y chunks, 1)
+  const dim3 egrid = is2d ? dim3(grid.x, (f.n1 + chunk - 1) / chunk, 1) : dim3(grid.x, f.n1, (f.n0 + chunk - 1) / chunk);
+  if (dtype == AB_F32) ab_edge_kernel<float><<<egrid, nt, 0, (cudaStream_t)stream>>>((const float*)field_dev, (float*)out_dev, f, is2d, chunk);
+  else if (dtype == AB_F64) ab_edge_kernel<double><<<egrid, nt, 0, (cudaStream_t)stream>>>((const double*)field_dev, (double*)out_dev, f, is2d, chunk);
   else return fail(AB_EINVAL, "bad dtype %d", dtype);
   CUDA_TRY(cudaGetLastError());
   g_launches++;

@@ -28,26 +28,87 @@ struct Field3 {
 };
 
 // one axis of the separable box filter: the sum of k taps starting at offset t0 along `axis`; the last pass of an iteration
-// also divides by the kernel volume (the reference's filter is ones / norm)
+// also divides by the kernel volume (the reference's filter is ones / norm). A thread owns one (x, z) and marches over
+// `rows` consecutive y, so the address arithmetic is a pointer increment per output and the taps are k loads that hit
+// L1 / L2 (x- and y-taps are whole rows apart, z-taps are neighbours in the same row).
 template <typename T>
 __global__ void __launch_bounds__(256) ab_box_axis_kernel(const T* __restrict__ in, T* __restrict__ out, Field3 f, int axis, int k,
-                                                          int t0, T norm, int divide) {
-  const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, x = blockIdx.z;
+                                                          int t0, T norm, int divide, uint32_t rows) {
+  const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.z;
+  if (z >= f.n2) return;
+  const uint32_t y0 = blockIdx.y * rows, y1 = y0 + rows < f.n1 ? y0 + rows : f.n1;
+  const uint64_t plane = (uint64_t)f.n1 * f.n2;
+  const T* src = in + x * plane + (uint64_t)y0 * f.n2 + z;
+  T* dst = out + x * plane + (uint64_t)y0 * f.n2 + z;
+  if (axis == 2) {
+    const bool inner = (int)z + t0 >= 0 && (int)z + t0 + k <= (int)f.n2;  // no reflection for this thread
+    for (uint32_t y = y0; y < y1; y++, src += f.n2, dst += f.n2) {
+      T s = T(0);
+      if (inner) {
+        for (int t = 0; t < k; t++) s = s + src[t0 + t];
+      } else {
+        const T* row = src - z;
+        for (int t = 0; t < k; t++) s = s + row[reflect_index((int)z + t0 + t, (int)f.n2)];
+      }
+      *dst = divide ? s / norm : s;
+    }
+  } else if (axis == 1) {
+    for (uint32_t y = y0; y < y1; y++, src += f.n2, dst += f.n2) {
+      T s = T(0);
+      if ((int)y + t0 >= 0 && (int)y + t0 + k <= (int)f.n1) {
+        const T* p = src + (int64_t)t0 * f.n2;
+        for (int t = 0; t < k; t++, p += f.n2) s = s + *p;
+      } else {
+        const T* col = in + x * plane + z;
+        for (int t = 0; t < k; t++) s = s + col[(uint64_t)reflect_index((int)y + t0 + t, (int)f.n1) * f.n2];
+      }
+      *dst = divide ? s / norm : s;
+    }
+  } else {
+    const bool inner = (int)x + t0 >= 0 && (int)x + t0 + k <= (int)f.n0;
+    for (uint32_t y = y0; y < y1; y++, src += f.n2, dst += f.n2) {
+      T s = T(0);
+      if (inner) {
+        const T* p = src + (int64_t)t0 * (int64_t)plane;
+        for (int t = 0; t < k; t++, p += plane) s = s + *p;
+      } else {
+        const T* col = in + (uint64_t)y * f.n2 + z;
+        for (int t = 0; t < k; t++) s = s + col[(uint64_t)reflect_index((int)x + t0 + t, (int)f.n0) * plane];
+      }
+      *dst = divide ? s / norm : s;
+    }
+  }
+}
+
+// The same pass for the two slow axes with the window in registers: a thread marches ALONG the filter axis over `chunk`
+// outputs, keeps the last K samples and adds them in tap order (the same order as the generic kernel and the oracle, so
+// the bits agree), i.e. one load per output instead of K.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) ab_box_march_kernel(const T* __restrict__ in, T* __restrict__ out, Field3 f, int axis, int t0,
+                                                           T norm, int divide, uint32_t chunk) {
+  const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= f.n2) return;
   const uint64_t plane = (uint64_t)f.n1 * f.n2;
-  const uint64_t e = x * plane + (uint64_t)y * f.n2 + z;
-  T s = T(0);
-  if (axis == 2) {
-    const T* row = in + (e - z);
-    for (int t = 0; t < k; t++) s = s + row[reflect_index((int)z + t0 + t, (int)f.n2)];
-  } else if (axis == 1) {
-    const T* col = in + x * plane + z;
-    for (int t = 0; t < k; t++) s = s + col[(uint64_t)reflect_index((int)y + t0 + t, (int)f.n1) * f.n2];
-  } else {
-    const T* col = in + (uint64_t)y * f.n2 + z;
-    for (int t = 0; t < k; t++) s = s + col[(uint64_t)reflect_index((int)x + t0 + t, (int)f.n0) * plane];
+  // axis 0: fixed y = blockIdx.y, march x over chunk blockIdx.z; axis 1: fixed x = blockIdx.z, march y over chunk blockIdx.y
+  const uint32_t n_axis = axis == 0 ? f.n0 : f.n1;
+  const uint64_t stride = axis == 0 ? plane : (uint64_t)f.n2;
+  const uint32_t a0 = (axis == 0 ? blockIdx.z : blockIdx.y) * chunk;
+  const uint32_t a1 = a0 + chunk < n_axis ? a0 + chunk : n_axis;
+  const uint64_t base = axis == 0 ? (uint64_t)blockIdx.y * f.n2 + z : (uint64_t)blockIdx.z * plane + z;
+  const T* col = in + base;
+  T* dst = out + base + (uint64_t)a0 * stride;
+  T w[K];
+#pragma unroll
+  for (int t = 0; t < K - 1; t++) w[t + 1] = col[(uint64_t)reflect_index((int)a0 + t0 + t, (int)n_axis) * stride];
+  for (uint32_t a = a0; a < a1; a++, dst += stride) {
+#pragma unroll
+    for (int t = 0; t < K - 1; t++) w[t] = w[t + 1];
+    w[K - 1] = col[(uint64_t)reflect_index((int)a + t0 + K - 1, (int)n_axis) * stride];
+    T s = T(0);
+#pragma unroll
+    for (int t = 0; t < K; t++) s = s + w[t];
+    *dst = divide ? s / norm : s;
   }
-  out[e] = divide ? s / norm : s;
 }
 
 template <typename T>
@@ -55,30 +116,48 @@ __global__ void ab_scale_copy_kernel(const T* __restrict__ in, T* __restrict__ o
   for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) out[e] = in[e] / norm;
 }
 
-// 9 u - sum of the 3x3 neighbourhood over the two axes (ax, ay) = (0, 1) of a 3D field or (1, 2) of a 2D one
+// 9 u - sum of the 3x3 neighbourhood over the two axes (0, 1) of a 3D field or (1, 2) of the (1, nx, ny) view of a 2D one.
+// A thread marches along the first stencil axis over `chunk` outputs with the 3x3 window in registers: three loads per
+// output. The sum runs in the oracle's order (first axis outer, second inner).
 template <typename T>
-__global__ void __launch_bounds__(256) ab_edge_kernel(const T* __restrict__ in, T* __restrict__ out, Field3 f, int is2d) {
-  const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, x = blockIdx.z;
+__global__ void __launch_bounds__(256) ab_edge_kernel(const T* __restrict__ in, T* __restrict__ out, Field3 f, int is2d, uint32_t chunk) {
+  const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= f.n2) return;
   const uint64_t plane = (uint64_t)f.n1 * f.n2;
-  const uint64_t e = x * plane + (uint64_t)y * f.n2 + z;
-  T s = T(0);
-  if (is2d) {  // (1, nx, ny): the stencil spans y (slow) and z (fast)
+  // march axis A / cross axis B: 3D (x, y) with y = blockIdx.y fixed; 2D view (y, z) with z fixed
+  const uint32_t nA = is2d ? f.n1 : f.n0, nB = is2d ? f.n2 : f.n1;
+  const uint64_t sA = is2d ? (uint64_t)f.n2 : plane, sB = is2d ? 1 : (uint64_t)f.n2;
+  const uint32_t bpos = is2d ? z : blockIdx.y;
+  const uint32_t a0 = (is2d ? blockIdx.y : blockIdx.z) * chunk;
+  const uint32_t a1 = a0 + chunk < nA ? a0 + chunk : nA;
+  // offsets of the three cross-axis taps relative to the column of this thread
+  const int64_t ob[3] = {((int64_t)reflect_index((int)bpos - 1, (int)nB) - (int64_t)bpos) * (int64_t)sB, 0,
+                         ((int64_t)reflect_index((int)bpos + 1, (int)nB) - (int64_t)bpos) * (int64_t)sB};
+  const T* col = in + (is2d ? (uint64_t)z : (uint64_t)blockIdx.y * f.n2 + z);
+  T* dst = out + (is2d ? (uint64_t)z : (uint64_t)blockIdx.y * f.n2 + z) + (uint64_t)a0 * sA;
+  T w[3][3];
 #pragma unroll
-    for (int da = -1; da <= 1; da++) {
-      const T* row = in + (uint64_t)reflect_index((int)y + da, (int)f.n1) * f.n2;
+  for (int da = 0; da < 2; da++) {
+    const T* p = col + (uint64_t)reflect_index((int)a0 - 1 + da, (int)nA) * sA;
 #pragma unroll
-      for (int db = -1; db <= 1; db++) s = s + row[reflect_index((int)z + db, (int)f.n2)];
-    }
-  } else {
-#pragma unroll
-    for (int da = -1; da <= 1; da++) {
-      const T* pl = in + (uint64_t)reflect_index((int)x + da, (int)f.n0) * plane + z;
-#pragma unroll
-      for (int db = -1; db <= 1; db++) s = s + pl[(uint64_t)reflect_index((int)y + db, (int)f.n1) * f.n2];
-    }
+    for (int db = 0; db < 3; db++) w[da + 1][db] = p[ob[db]];
   }
-  out[e] = T(9) * in[e] - s;
+  for (uint32_t a = a0; a < a1; a++, dst += sA) {
+#pragma unroll
+    for (int db = 0; db < 3; db++) {
+      w[0][db] = w[1][db];
+      w[1][db] = w[2][db];
+    }
+    const T* p = col + (uint64_t)reflect_index((int)a + 1, (int)nA) * sA;
+#pragma unroll
+    for (int db = 0; db < 3; db++) w[2][db] = p[ob[db]];
+    T s = T(0);
+#pragma unroll
+    for (int da = 0; da < 3; da++)
+#pragma unroll
+      for (int db = 0; db < 3; db++) s = s + w[da][db];
+    *dst = T(9) * w[1][1] - s;
+  }
 }
 
 // ---- vector-field modifiers ----------------------------------------------------------------------------------------------
