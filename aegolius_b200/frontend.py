@@ -43,7 +43,8 @@ _LEAF_NAMES = [
     "sdf_triangle_2d", "sdf_arc", "sdf_sector", "sdf_inf_sector", "sdf_ngon", "sdf_segmented_line_2d",
     "sdf_point_cloud_2d", "sdf_closed_segmented_line_2d", "sdf_closed_segmented_line_3d", "sdf_polygon_2d",
     "sdf_parametric_curve_2d", "sdf_parametric_curve_3d", "sdf_closed_parametric_curve_2d",
-    "sdf_closed_parametric_curve_3d",
+    "sdf_closed_parametric_curve_3d", "sdf_segmented_curve_2d", "sdf_segmented_curve_3d",
+    "sdf_closed_segmented_curve_2d", "sdf_closed_segmented_curve_3d",
 ]
 LEAVES = {n: LeafSDF(n) for n in _LEAF_NAMES}
 globals().update(LEAVES)
@@ -601,6 +602,55 @@ class ParametricCurve3D(GenericGeometry):
     @property
     def closed(self):
         return self._closed
+
+
+class _SegmentedParametricBase(GenericGeometry):
+    """Polyline through `points`, sampled at parameters ts (point v = floor(t), fraction u = t - v): distance to the
+    nearest SAMPLE (sdf_2D.py:180-188, sdf_3D.py:253-261), plus the closing segment when closed."""
+    _dim = 2
+
+    def __init__(self, points, t_range, closed=False):
+        self._points = _as_rows(points)
+        self._t_range = t_range
+        self._closed = closed
+        name = f"sdf_closed_segmented_curve_{self._dim}d" if closed else f"sdf_segmented_curve_{self._dim}d"
+        GenericGeometry.__init__(self, _leaf(name), self._points, self.ts)
+
+    @property
+    def steps(self):
+        return self._t_range[2]
+
+    @property
+    def t_start(self):
+        return self._t_range[0]
+
+    @property
+    def t_end(self):
+        return self._t_range[1]
+
+    @property
+    def closed(self):
+        return self._closed
+
+
+class SegmentedParametricCurve(_SegmentedParametricBase):
+    """geom_2d.py:460-528 (without .polygon(), which needs a grid-wide test)."""
+    _dim = 2
+
+    @property
+    def ts(self):  # geom_2d.py:519-523
+        tt = np.linspace(self._t_range[0], self._t_range[1] - 1, self._t_range[2])
+        return np.clip(tt, 0, self._points.shape[1] - 1.0001)
+
+
+class SegmentedParametricCurve3D(_SegmentedParametricBase):
+    """geom_3d.py:651-714."""
+    _dim = 3
+
+    @property
+    def ts(self):  # geom_3d.py:704-708: unlike the 2D class the start value is subtracted
+        tt = np.linspace(self._t_range[0], self._t_range[1] - 1, self._t_range[2]) - self._t_range[0]
+        return np.clip(tt, 0, self._points.shape[1] - 1.0001)
 
 
 class PointCloud3D(GenericGeometry):

@@ -96,6 +96,12 @@ def to_frontend(obj, _stack=()):
             node.leaf = "sdf_closed_parametric_curve_2d" if qn.startswith("ParametricCurve.") else \
                 "sdf_closed_parametric_curve_3d"
             node._geo_parameters = tuple(getattr(obj, "_geo_parameters", ()))
+        elif qn in ("SegmentedParametricCurve.sdf_closed_curve.<locals>.new_geo_object",
+                    "SegmentedParametricCurve3D.sdf_closed_curve.<locals>.new_geo_object"):
+            node = _blank("leaf")
+            node.leaf = "sdf_closed_segmented_curve_3d" if qn.startswith("SegmentedParametricCurve3D.") else \
+                "sdf_closed_segmented_curve_2d"
+            node._geo_parameters = tuple(getattr(obj, "_geo_parameters", ()))
         elif inspect.isfunction(fn) and fn.__name__ in fe.LEAVES and "<locals>" not in qn:
             node = _blank("leaf")
             node.leaf = fn.__name__

@@ -522,6 +522,23 @@ class _Builder:
                 else:
                     self.leaf("sdf_segment_2d", (p0[:2], p1[:2]))
                 e(oc.C_UNION, a=slot)
+        elif name in ("sdf_segmented_curve_2d", "sdf_segmented_curve_3d", "sdf_closed_segmented_curve_2d",
+                      "sdf_closed_segmented_curve_3d"):
+            # nearest SAMPLE of the polyline, interpolated on the host exactly as sdf_2D.py:180-188 / sdf_3D.py:253-261
+            pts, ts = np.asarray(params[0], dtype=np.float64), np.asarray(params[1], dtype=np.float64)
+            dim = 3 if name.endswith("3d") else 2
+            if pts.ndim != 2 or pts.shape[0] < dim:
+                raise ValueError(f"points must have shape ({dim}, M)")
+            v = np.floor(ts).astype(int)
+            u = ts - v
+            fval = pts[:dim, v + 1] * u + pts[:dim, v] * (1 - u)
+            self.leaf(f"sdf_point_cloud_{dim}d", (fval,))
+            if name.startswith("sdf_closed"):  # min(f1, segment(first, last)), geom_2d.py:491-496 / geom_3d.py:677-682
+                slot = self.cur_vd
+                self.use_v(slot)
+                e(oc.PUSH_V, a=slot)
+                self.leaf(f"sdf_segment_{dim}d", (pts[:dim, 0], pts[:dim, -1]))
+                e(oc.C_UNION, a=slot)
         elif name in ("sdf_point_cloud_3d", "sdf_point_cloud_2d"):
             pts = np.asarray(params[0], dtype=np.float64)
             dim = 3 if name.endswith("3d") else 2

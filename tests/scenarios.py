@@ -122,6 +122,15 @@ PRIMS2.update({
     "parametric_curve": lambda ns: ns.ParametricCurve(lissajous, (1.6, 1.1), (0, 1, 57)),
     "parametric_curve_closed": lambda ns: ns.ParametricCurve(lissajous, (1.6, 1.1), (0, 0.8, 41), closed=True),
 })
+_SPC2 = np.array([[-2.0, -0.6, 0.4, 1.9, 1.2, -0.9], [-1.1, 1.3, -0.7, 0.5, 1.6, 1.4]])
+_SPC3 = np.array([[-1.5, -0.4, 0.8, 1.6, 0.3], [-1.0, 1.2, 0.9, -0.8, -1.4], [-0.9, 0.2, 1.1, 0.4, -0.7]])
+PRIMS2["segmented_parametric_curve"] = lambda ns: ns.SegmentedParametricCurve(_SPC2, (0, 6, 64))
+PRIMS2["segmented_parametric_curve_closed"] = lambda ns: ns.SegmentedParametricCurve(_SPC2.T, (1, 6, 37), closed=True)
+PRIMS3["segmented_parametric_curve3d"] = lambda ns: ns.SegmentedParametricCurve3D(_SPC3, (0, 5, 48))
+PRIMS3["segmented_parametric_curve3d_closed"] = lambda ns: ns.SegmentedParametricCurve3D(_SPC3, (1, 5, 29), closed=True)
+scenario("prim3_segmented_parametric_curve3d", *G3)(lambda ns: _xf(PRIMS3["segmented_parametric_curve3d"](ns), 3))
+scenario("prim3_segmented_parametric_curve3d_closed", *G3)(
+    lambda ns: _xf(PRIMS3["segmented_parametric_curve3d_closed"](ns), 0))
 PRIMS3["parametric_curve3d"] = lambda ns: ns.ParametricCurve3D(helix, (0.8, 1.6), (0, 1, 49))
 PRIMS3["parametric_curve3d_closed"] = lambda ns: ns.ParametricCurve3D(helix, (0.8, 1.6), (0, 1, 33), closed=True)
 scenario("prim3_parametric_curve3d", *G3)(lambda ns: _xf(PRIMS3["parametric_curve3d"](ns), 1))
