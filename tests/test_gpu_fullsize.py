@@ -105,3 +105,58 @@ def test_c4_terrain_fixture_cloud_grid():
     assert np.max(np.abs(got - exp)) <= 1e-5 * 2.5
     got64 = ab.point_cloud_sdf(spec, pts, dtype="f64")
     assert np.max(np.abs(got64 - exp)) <= 1e-12 * 2.5
+
+
+def test_c4_full_size_octree_against_kdtree_sample():
+    """C4 as BASELINE.json states it: 257^3 queries x 1 000 000 cloud points. Checked on a seeded sample of the queries
+    against scipy's cKDTree (what the reference calls), plus two properties: the field is >= 0 and 1-Lipschitz along z."""
+    import aegolius_b200 as ab
+    cfg = ab.workloads.CONFIGS["C4"]
+    pts = cfg["cloud"]()
+    spec = ab.GridSpec(cfg["size"], cfg["res"])
+    assert spec.res == (257, 257, 257) and pts.shape == (3, 1_000_000)
+    got = ab.point_cloud_sdf(spec, pts, dtype="f32")
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, spec.n_points, size=200_000)
+    nx, ny, nz = spec.res
+    iz, iy, ix = k % nz, (k // nz) % ny, k // (nz * ny)
+    ax = [np.linspace(-spec.size[i] / 2, spec.size[i] / 2, spec.res[i]) for i in range(3)]
+    co = np.stack([ax[0][ix], ax[1][iy], ax[2][iz]])
+    exp = interp_np.point_cloud_distance_kdtree(co, pts)
+    assert np.max(np.abs(got[k] - exp)) <= 1e-5 * 2.5
+    g = got.reshape(spec.res)
+    assert g.min() >= 0.0
+    hz = spec.size[2] / (nz - 1)
+    assert np.max(np.abs(np.diff(g, axis=2))) <= hz * (1 + 1e-4)
+    got64 = ab.point_cloud_sdf(spec, pts, dtype="f64", slab=(100, 110))
+    k2 = k[(ix >= 100) & (ix < 110)]
+    sel = (ix >= 100) & (ix < 110)
+    assert np.max(np.abs(got64[k2 - 100 * ny * nz] - exp[sel])) <= 1e-12 * 2.5
+
+
+def test_more_than_2_to_31_points_is_split_into_launches():
+    """A 1301^3 grid (2.2e9 samples) exceeds the kernels' 32-bit point index: the C ABI splits it into launches on plane
+    boundaries. Sampled against the oracle, with extra samples on the planes next to the split."""
+    import torch
+    import aegolius_b200 as ab
+    from aegolius_b200 import engine
+    cfg = ab.workloads.CONFIGS["C1"]
+    spec = ab.GridSpec(cfg["size"], (1300, 1300, 1300))
+    assert spec.n_points > 2 ** 31
+    prog = ab.flatten(cfg["build"]())
+    field = engine.create_torch(prog, spec, dtype="f32")
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(11)
+    nx, ny, nz = spec.res
+    plane = ny * nz
+    split = (0x7fffffff - 4096) // plane  # first plane of the second launch (see run_program in ab_capi.cu)
+    ix = np.concatenate([rng.integers(0, nx, 150_000), np.repeat(np.arange(split - 2, split + 2), 20_000), [0, nx - 1]])
+    iy, iz = rng.integers(0, ny, ix.size), rng.integers(0, nz, ix.size)
+    ax = [np.linspace(-spec.size[i] / 2, spec.size[i] / 2, spec.res[i]) for i in range(3)]
+    co = np.stack([ax[0][ix], ax[1][iy], ax[2][iz]])
+    exp = interp_np.run(prog, co)
+    k = torch.as_tensor(ix.astype(np.int64) * plane + iy * nz + iz, device=field.device)
+    got = field[k].cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(got - exp)) <= 1e-5 * 4
+    del field
+    torch.cuda.empty_cache()
