@@ -68,6 +68,8 @@ _SIGNATURES = {
                                C.c_uint64, C.c_int, C.c_void_p]),
     "ab_eval_points": (C.c_int, [C.POINTER(ab_program), C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "ab_eval_grid_loss": (C.c_int, [C.POINTER(ab_program), C.POINTER(ab_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p]),
     "ab_eval_grid_host": (C.c_int, [C.POINTER(ab_program), C.POINTER(ab_grid), C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.c_int]),
     "ab_eval_points_host": (C.c_int, [C.POINTER(ab_program), C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,

@@ -290,6 +290,8 @@ struct EvalTarget {
   T* out;
   T* grad;
   uint64_t grad_stride;
+  const T* target;     // loss mode (ab_eval_grid_loss): no per-point outputs
+  double* loss_accum;
 };
 
 template <typename S, typename T>
@@ -334,10 +336,11 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   int rc = validate(prog);
   if (rc) return rc;
   if (tg.n == 0) return AB_OK;
-  if (!tg.out) return fail(AB_EINVAL, "null output pointer");
+  const bool loss_mode = tg.loss_accum != nullptr;
+  if (!loss_mode && !tg.out) return fail(AB_EINVAL, "null output pointer");
   if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL && grad_mode != AB_GRAD_PARAM)
     return fail(AB_EINVAL, "bad grad_mode %d", grad_mode);
-  if (grad_mode != AB_GRAD_NONE && (!tg.grad || tg.grad_stride < tg.n))
+  if (!loss_mode && grad_mode != AB_GRAD_NONE && (!tg.grad || tg.grad_stride < tg.n))
     return fail(AB_EINVAL, "gradient output missing or grad_stride < n");
   if (grad_mode == AB_GRAD_PARAM && !prog->dargs) return fail(AB_EINVAL, "AB_GRAD_PARAM needs ab_program.dargs");
 
@@ -448,8 +451,10 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
       }
     }
     kp.n = chunk;
-    kp.out = tg.out + done;
+    kp.out = tg.out ? tg.out + done : nullptr;
     kp.grad = tg.grad ? tg.grad + done : nullptr;
+    kp.target = tg.target ? tg.target + done : nullptr;
+    kp.loss_accum = tg.loss_accum;
     if (tg.grid_mode) {
       if (tg.g.is2d) kp.g.i1_begin = tg.g.i1_begin + (uint32_t)(done / tg.g.n2);
       else kp.g.i0_begin = tg.g.i0_begin + (uint32_t)(done / tg.g.plane);
@@ -488,6 +493,29 @@ static int eval_grid_t(const ab_program* prog, const ab_grid* grid, int grad_mod
   tg.grad = (T*)out_grad;
   tg.grad_stride = grad_stride;
   return run_program<T>(prog, tg, grad_mode, device, st);
+}
+
+template <typename T>
+static int eval_grid_loss_t(const ab_program* prog, const ab_grid* grid, const void* target, double* accum, int device,
+                            cudaStream_t st) {
+  EvalTarget<T> tg{};
+  int rc = make_gridk(grid, tg.g, &tg.n);
+  if (rc) return rc;
+  tg.grid_mode = 1;
+  tg.target = (const T*)target;
+  tg.loss_accum = accum;
+  CUDA_TRY(cudaMemsetAsync(accum, 0, 2 * sizeof(double), st));
+  return run_program<T>(prog, tg, AB_GRAD_PARAM, device, st);
+}
+
+extern "C" int ab_eval_grid_loss(const ab_program* prog, const ab_grid* grid, int dtype, const void* target_dev,
+                                 double* accum_dev, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (!target_dev || !accum_dev) return fail(AB_EINVAL, "null pointer");
+  if (dtype == AB_F32) return eval_grid_loss_t<float>(prog, grid, target_dev, accum_dev, device, (cudaStream_t)stream);
+  if (dtype == AB_F64) return eval_grid_loss_t<double>(prog, grid, target_dev, accum_dev, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
 }
 
 extern "C" int ab_eval_grid(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out,

@@ -109,6 +109,10 @@ struct KParams {
   const void* blob[AB_MAX_BLOBS];  // (x, y, z, 0) records of T
   uint32_t blob_count[AB_MAX_BLOBS];
   const void* blob_tree[AB_MAX_BLOBS];  // device TreeRef<T> of the blob (large clouds) or nullptr: scan the blob
+  // AB_GRAD_PARAM loss mode (ab_eval_grid_loss): instead of storing F and dF/dtheta the kernel accumulates
+  // loss_accum[0] += sum (F - target)^2, loss_accum[1] += sum 2 (F - target) dF/dtheta   (target indexed like out)
+  const T* target;
+  double* loss_accum;
   uint2 ops[AB_MAX_OPS];  // kernel-side encoding: x = dense opcode (a full word), y = argument offset | a << 16 | b << 24
   T args[AB_MAX_ARGS];
 };
@@ -269,6 +273,21 @@ AB_DEV void emit(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint32_t 
   for (int k = 0; k < K; k++) store_pack(kp.grad + (uint64_t)k * kp.grad_stride, acc.d[k], idx, kp.n, ga);
 }
 
+// loss mode of the parameter-tangent kernel: r = F - target, sums of r^2 and 2 r dF/dtheta in double
+template <typename T, int W, int K>
+AB_DEV void accumulate_loss(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint32_t idx, double& loss, double& dloss) {
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    if (idx + j < kp.n) {
+      const double r = (double)(acc.v.v[j] - kp.target[idx + j]);
+      loss += r * r;
+      dloss += 2.0 * r * (double)acc.d[0].v[j];
+    }
+  }
+}
+template <typename T, int W>
+AB_DEV void accumulate_loss(const KParams<T>&, const Pack<T, W>&, uint32_t, double&, double&) {}
+
 // nearest cloud point inside the interpreter (sdf_3D.py:283-286), for a cloud that sits anywhere in a tree: queries arrive
 // already warped by the ops above the leaf. Large clouds come with an octree (built by the host per call, ab_tree.cuh) and
 // every lane walks it; small ones are scanned with uniform (broadcast) loads. Same (q-p)^2 expression either way, so the
@@ -399,6 +418,7 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
     b2 = rem - b1 * kp.g.n2;
   }
 
+  double loss_sum = 0.0, dloss_sum = 0.0;  // loss mode only (PARAM kernels)
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t idx = tile * tile_pts + threadIdx.x * W;  // first local point of this thread
     P cx, cy, cz;
@@ -723,8 +743,27 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
         default: break;  // unknown opcodes are rejected on the host (AB_EUNSUPPORTED_OP)
       }
     }
+    if constexpr (PARAM) {
+      if (kp.loss_accum) {  // fused least-squares reduction: nothing is written per point
+        accumulate_loss(kp, acc, idx, loss_sum, dloss_sum);
+        continue;
+      }
+    }
     const bool aligned = ((reinterpret_cast<uintptr_t>(kp.out) & 15) == 0);
     emit(kp, acc, idx, aligned);
+  }
+  if constexpr (PARAM) {
+    if (kp.loss_accum) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        loss_sum += __shfl_xor_sync(0xffffffffu, loss_sum, off);
+        dloss_sum += __shfl_xor_sync(0xffffffffu, dloss_sum, off);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(kp.loss_accum, loss_sum);
+        atomicAdd(kp.loss_accum + 1, dloss_sum);
+      }
+    }
   }
 }
 

@@ -198,8 +198,9 @@ def value_and_grad(geometry, spec, target, *, dtype="f32", device=0, post=None):
     least-squares objective used there: loss(params) = sum((F(params) - target)^2), F = field of geometry(*params) on the
     grid `spec`. Returns f(params) -> (loss, d loss / d params).
 
-    Everything stays on the device: one AB_GRAD_PARAM launch per parameter gives (F, dF/dtheta_k) as torch tensors and the
-    sums  sum(r^2), sum(2 r dF/dtheta_k)  are torch reductions (K forward-mode passes; K is a handful of shape parameters).
+    One AB_GRAD_PARAM launch per parameter (K forward-mode passes; K is a handful of shape parameters). Without `post`
+    the sums  sum(r^2), sum(2 r dF/dtheta_k)  are reduced inside the kernel (ab_eval_grid_loss: no per-point stores, two
+    doubles come back); with `post` the launch returns (F, dF/dtheta_k) as torch tensors and the sums are torch reductions.
     `target` is a torch CUDA tensor or array of N values; `post(F, dF)` may map the field before the residual (e.g. a
     falloff) and must return the transformed pair."""
     import torch
@@ -207,15 +208,29 @@ def value_and_grad(geometry, spec, target, *, dtype="f32", device=0, post=None):
     tdt = torch.float32 if _dtype(dtype)[0] == cabi.AB_F32 else torch.float64
     tgt = torch.as_tensor(np.asarray(target) if not torch.is_tensor(target) else target, dtype=tdt, device=dev)
 
+    code = _dtype(dtype)[0]
+    accum = torch.zeros(2, dtype=torch.float64, device=dev)
+
     def f(params):
         params = [float(v) for v in params]
         grads, loss = [], None
         for k in range(len(params)):
             prog = program_tangent(geometry, params, k)
+            if post is None:
+                # fused: the kernel reduces sum r^2 and sum 2 r dF/dtheta_k itself (ab_eval_grid_loss), nothing is stored
+                cp = cabi.CProgram(prog)
+                g = cabi.make_grid(spec.size, spec.res)
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                cabi.check(cabi.lib().ab_eval_grid_loss(cp.ref(), C.byref(g), code, tgt.data_ptr(), accum.data_ptr(), device,
+                                                        C.c_void_p(stream)))
+                both = accum.cpu()
+                if loss is None:
+                    loss = float(both[0])
+                grads.append(float(both[1]))
+                continue
             field, dfield = create_torch(prog, spec, dtype=dtype, grad="param", device=device)
             dfield = dfield[0]
-            if post is not None:
-                field, dfield = post(field, dfield)
+            field, dfield = post(field, dfield)
             r = field - tgt
             if loss is None:
                 loss = float(torch.sum(r * r))

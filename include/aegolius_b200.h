@@ -181,6 +181,14 @@ int ab_eval_grid(const ab_program* prog, const ab_grid* grid, int dtype, int gra
 int ab_eval_points(const ab_program* prog, const void* co, int co_dtype, uint64_t co_stride, uint64_t n, int dtype,
                    int grad_mode, void* out, void* out_grad, uint64_t grad_stride, int device, void* stream);
 
+/* Fused least-squares objective for shape optimisation, the device counterpart of jax.value_and_grad(worker) in
+ * Code/examples/autodiff/position_optimization.py:101-179: one AB_GRAD_PARAM evaluation (prog->dargs holds d args / d theta)
+ * whose per-point results are not stored but reduced in the kernel:
+ *   accum_dev[0] = sum_k (F_k - target_k)^2,   accum_dev[1] = sum_k 2 (F_k - target_k) dF_k/dtheta     (doubles, DEVICE)
+ * target_dev: DEVICE array of `dtype`, one value per grid point of the slab. accum_dev is zeroed by the call. */
+int ab_eval_grid_loss(const ab_program* prog, const ab_grid* grid, int dtype, const void* target_dev, double* accum_dev,
+                      int device, void* stream);
+
 /* Host-buffer variants (what the Python drop-in calls when the user wants a NumPy array back): allocate/reuse
  * device scratch, run, copy the result to `out_host` (pinned or pageable), synchronise. */
 int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out_host,

@@ -227,6 +227,51 @@ def test_position_optimisation_converges_like_the_jax_example():
     assert loss < 1e-2 * loss0 and np.max(np.abs(params - np.array(target_xy))) < 0.05
 
 
+def test_fused_loss_reduction_matches_unfused_and_oracle():
+    """ab_eval_grid_loss (sums reduced inside the AB_GRAD_PARAM kernel) against the same sums formed from the stored
+    (F, dF/dtheta) maps and against the fp64 oracle's field; 3D tree, both precisions."""
+    import torch
+    import aegolius_b200 as ab
+    from aegolius_b200 import engine
+    spec = ab.GridSpec((4, 4, 4), (48, 40, 36))
+
+    def geometry(r, w, x0):
+        s = ab.Sphere(r)
+        s.move((x0, 0.1, -0.2))
+        b = ab.Box(1.5, 1.0, 0.8)
+        b.rotate(0.6, (0, 0, 1))
+        return ab.CombineGeometry("SMOOTH_UNION2").combine_parametric(s, b, parameters=w)
+
+    params = [0.9, 0.3, 0.4]
+    rng = np.random.default_rng(4)
+    target64 = interp_np.run_grid(ab.flatten(geometry(1.0, 0.25, 0.5)), spec.size, spec.res) + 0.01 * rng.normal(size=spec.n_points)
+    exp_field = interp_np.run_grid(ab.flatten(geometry(*params)), spec.size, spec.res)
+    exp_loss = float(np.sum((exp_field - target64) ** 2))
+    for dt, rtol in (("f64", 1e-11), ("f32", 2e-5)):
+        loss, grads = ab.value_and_grad(geometry, spec, target64, dtype=dt)(params)
+        assert abs(loss - exp_loss) <= rtol * exp_loss
+        # the unfused path: identity `post` makes value_and_grad store the maps and reduce them with torch
+        loss_u, grads_u = ab.value_and_grad(geometry, spec, target64, dtype=dt, post=lambda f, d: (f, d))(params)
+        assert abs(loss - loss_u) <= 10 * rtol * abs(loss_u)
+        assert np.allclose(grads, grads_u, rtol=50 * rtol, atol=50 * rtol * np.max(np.abs(grads_u)))
+    # slabs add up: two half-grid calls through the C ABI
+    import ctypes as C
+    from aegolius_b200 import cabi
+    prog = engine.program_tangent(geometry, params, 0)
+    cp = cabi.CProgram(prog)
+    tgt = torch.as_tensor(target64, dtype=torch.float64, device="cuda")
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    total = np.zeros(2)
+    plane = spec.res[1] * spec.res[2]
+    for x0, x1 in ((0, 20), (20, spec.res[0])):
+        g = cabi.make_grid(spec.size, spec.res, (x0, x1))
+        cabi.check(cabi.lib().ab_eval_grid_loss(cp.ref(), C.byref(g), cabi.AB_F64, tgt.data_ptr() + 8 * x0 * plane,
+                                                acc.data_ptr(), 0, None))
+        total += acc.cpu().numpy()
+    full, gfull = ab.value_and_grad(geometry, spec, target64, dtype="f64")(params)
+    assert abs(total[0] - full) <= 1e-11 * full and abs(total[1] - gfull[0]) <= 1e-9 * abs(gfull[0])
+
+
 def _cloud_cases():
     rng = np.random.default_rng(1)
     from aegolius_b200 import workloads
