@@ -140,8 +140,15 @@ class CProgram:
         self._blob_arrays = [np.ascontiguousarray(b, dtype=np.float64) for b in prog.blobs]
         n_blobs = len(self._blob_arrays)
         self._blobs = (ab_blob * max(1, n_blobs))()
+        fields = {st["blob"] for st in getattr(prog, "stages", ())}  # P_FIELD inputs: device arrays, one value per point
         for i, b in enumerate(self._blob_arrays):
-            if device_blobs is not None and device_blobs[i] is not None:
+            if i in fields:
+                if device_blobs is None or device_blobs[i] is None:
+                    raise ValueError("this program has grid-stencil stages: evaluate it through aegolius_b200.create "
+                                     "on a whole grid (the stages need the full field)")
+                ptr, count = device_blobs[i]
+                self._blobs[i] = ab_blob(ptr, count, 1, 1)
+            elif device_blobs is not None and device_blobs[i] is not None:
                 self._blobs[i] = ab_blob(device_blobs[i], b.shape[1], 3, 1)
             else:
                 self._blobs[i] = ab_blob(b.ctypes.data, b.shape[1], 3, 0)

@@ -90,7 +90,7 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
     case AB_OP_END: case AB_OP_SAVE_P: case AB_OP_LOAD_P: case AB_OP_PUSH_V: case AB_OP_SYMMETRY: case AB_OP_ZERO_Z:
     case AB_OP_ABS: case AB_OP_NEG: case AB_OP_SIGN: case AB_OP_EXTRUDE_END: case AB_OP_C_UNION: case AB_OP_C_INTERSECT:
     case AB_OP_NEXT_LOAD:
-    case AB_OP_C_SUBTRACT: case AB_OP_C_SUM: case AB_OP_C_DIFF: case AB_OP_P_POINT_CLOUD:
+    case AB_OP_C_SUBTRACT: case AB_OP_C_SUM: case AB_OP_C_DIFF: case AB_OP_P_POINT_CLOUD: case AB_OP_P_FIELD:
       n = 0; break;
     case AB_OP_SCALE_P: case AB_OP_TWIST: case AB_OP_ABSX_SUB: case AB_OP_REVOLVE: case AB_OP_ROUND: case AB_OP_ONION:
     case AB_OP_CONCENTRIC: case AB_OP_SCALE_V: case AB_OP_EXTRUDE_BEGIN: case AB_OP_PP_HARD_BIN: case AB_OP_PP_RELU:
@@ -166,6 +166,11 @@ static int validate(const ab_program* prog) {
         if (op.a != 2 && op.a != 3) return fail(AB_EINVAL, "op %u: point cloud dim must be 2 or 3", i);
         if (prog->blobs[op.b].count == 0 || prog->blobs[op.b].count > 0xffffffffull)
           return fail(AB_EINVAL, "op %u: point cloud size out of range", i);
+        break;
+      case AB_OP_P_FIELD:
+        if (op.b >= prog->n_blobs || !prog->blobs) return fail(AB_EINVAL, "op %u: blob %u missing", i, op.b);
+        if (prog->blobs[op.b].dim != 1 || !prog->blobs[op.b].on_device || !prog->blobs[op.b].data)
+          return fail(AB_EINVAL, "op %u: P_FIELD needs a device blob with dim = 1", i);
         break;
       case AB_OP_SYMMETRY: case AB_OP_P_AXIS:
         if (op.a > 2) return fail(AB_EINVAL, "op %u: axis %u", i, op.a);
@@ -393,13 +398,27 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   kp.dargs_off = grad_mode == AB_GRAD_PARAM ? kParamHalf : 0;
 
   std::vector<void*> temp_blobs;
+  const char* field_base[AB_MAX_BLOBS] = {nullptr, nullptr, nullptr, nullptr};
+  static_assert(AB_MAX_BLOBS == 4, "field_base initialiser");
   for (uint32_t b = 0; b < AB_MAX_BLOBS; b++) {
     kp.blob[b] = nullptr;
     kp.blob_count[b] = 0;
     kp.blob_tree[b] = nullptr;
   }
+  bool blob_used[AB_MAX_BLOBS] = {false, false, false, false};
+  for (uint32_t i = 0; i < prog->n_ops; i++)
+    if (prog->ops[i].opcode == AB_OP_P_POINT_CLOUD || prog->ops[i].opcode == AB_OP_P_FIELD) blob_used[prog->ops[i].b] = true;
   for (uint32_t b = 0; b < prog->n_blobs; b++) {
     const ab_blob& bl = prog->blobs[b];
+    if (!blob_used[b]) continue;  // e.g. the not-yet-computed field of a later stencil stage in a prefix program
+    if (bl.dim == 1) {  // a per-point field (P_FIELD): used in place, advanced with the output pointer per launch
+      if (!bl.data || !bl.on_device || bl.count < tg.n) return fail(AB_EINVAL, "field blob %u must be a device array of >= %llu values", b, (unsigned long long)tg.n);
+      if (grad_mode != AB_GRAD_NONE) return fail(AB_EUNSUPPORTED_OP, "no derivative passes through a grid stencil (P_FIELD, blob %u)", b);
+      field_base[b] = (const char*)bl.data;
+      kp.blob[b] = bl.data;
+      kp.blob_count[b] = 0;
+      continue;
+    }
     if (!bl.data || bl.count == 0 || bl.count > 0xffffffffull) return fail(AB_EINVAL, "blob %u empty or too large", b);
     if (bl.on_device) {
       kp.blob[b] = bl.data;
@@ -455,6 +474,8 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
     kp.grad = tg.grad ? tg.grad + done : nullptr;
     kp.target = tg.target ? tg.target + done : nullptr;
     kp.loss_accum = tg.loss_accum;
+    for (uint32_t b = 0; b < AB_MAX_BLOBS; b++)
+      if (field_base[b]) kp.blob[b] = field_base[b] + done * sizeof(T);
     if (tg.grid_mode) {
       if (tg.g.is2d) kp.g.i1_begin = tg.g.i1_begin + (uint32_t)(done / tg.g.n2);
       else kp.g.i0_begin = tg.g.i0_begin + (uint32_t)(done / tg.g.plane);

@@ -56,7 +56,7 @@ AB_DEV void divmod_small(uint32_t t, uint32_t n, uint32_t magic, uint32_t& q, ui
   X(PP_GAUSS_BOUNDARY) X(PP_GAUSS_FALLOFF) X(C_UNION) X(C_INTERSECT) X(C_SUBTRACT) X(C_SUM) X(C_DIFF) X(C_SMIN2)       \
   X(C_SMIN3) X(C_SMAX3) X(C_SSUB3) X(C_BOLTZ_INT) X(C_BOLTZ_SUB) X(P_SPHERE) X(P_CYLINDER) X(P_BOX) X(P_TORUS)         \
   X(P_CHAINLINK) X(P_BRAID) X(P_ARC3D) X(P_PLANE) X(P_UPLANE) X(P_SEGMENT) X(P_CONE) X(P_OINF_CONE) X(P_INF_CONE)      \
-  X(P_SOLID_ANGLE) X(P_TRIANGLE3D) X(P_QUAD3D) X(P_SEGLINE) X(P_AXIS) X(P_POINT_CLOUD) X(P_CIRCLE) X(P_NEU_CIRCLE)     \
+  X(P_SOLID_ANGLE) X(P_TRIANGLE3D) X(P_QUAD3D) X(P_SEGLINE) X(P_AXIS) X(P_POINT_CLOUD) X(P_FIELD) X(P_CIRCLE) X(P_NEU_CIRCLE)     \
   X(P_BOX2D) X(P_SEGMENT2D) X(P_RBOX2D) X(P_TRIANGLE2D) X(P_ARC) X(P_SECTOR) X(P_INF_SECTOR) X(P_NGON) X(P_SEGLINE2D) \
   X(P_POLYGON2D)
 enum DenseOp : uint16_t {
@@ -271,6 +271,20 @@ AB_DEV void emit(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint32_t 
   const bool ga = aligned && (kp.grad_stride % W == 0);
 #pragma unroll
   for (int k = 0; k < K; k++) store_pack(kp.grad + (uint64_t)k * kp.grad_stride, acc.d[k], idx, kp.n, ga);
+}
+
+// P_FIELD: the value of a precomputed per-point field (the output of a grid stencil), indexed like `out`
+template <typename T, int W>
+AB_DEV void load_field(const void* field, uint32_t idx, uint64_t n, Pack<T, W>& out) {
+  const T* f = reinterpret_cast<const T*>(field);
+#pragma unroll
+  for (int j = 0; j < W; j++) out.v[j] = f[idx + j < n ? idx + j : n - 1];
+}
+template <typename T, int W, int K>
+AB_DEV void load_field(const void* field, uint32_t idx, uint64_t n, Dual<Pack<T, W>, K>& out) {
+  Pack<T, W> v;
+  load_field(field, idx, n, v);
+  out = Dual<Pack<T, W>, K>(v);  // zero tangents (rejected on the host for the gradient modes anyway)
 }
 
 // loss mode of the parameter-tangent kernel: r = F - target, sums of r^2 and 2 r dF/dtheta in double
@@ -667,6 +681,7 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
 #endif
         // 3D primitives
         case D_P_SPHERE: acc = prim_sphere(p, a); break;
+        case D_P_FIELD: load_field(kp.blob[sb], idx, kp.n, acc); break;
         case D_P_CYLINDER: acc = prim_cylinder(p, a); break;
         case D_P_BOX: acc = prim_box(p, a); break;
         case D_P_TORUS: acc = prim_torus(p, a); break;
@@ -788,7 +803,7 @@ inline bool is_lite_op(int ab_opcode) {
     case AB_OP_C_SMIN2: case AB_OP_C_SMIN3: case AB_OP_C_SMAX3: case AB_OP_C_SSUB3: case AB_OP_P_SPHERE:
     case AB_OP_P_CYLINDER: case AB_OP_P_BOX: case AB_OP_P_TORUS: case AB_OP_P_CHAINLINK: case AB_OP_P_PLANE:
     case AB_OP_P_UPLANE: case AB_OP_P_SEGMENT: case AB_OP_P_AXIS: case AB_OP_P_CIRCLE: case AB_OP_P_BOX2D:
-    case AB_OP_P_SEGMENT2D:
+    case AB_OP_P_SEGMENT2D: case AB_OP_P_FIELD:
       return true;
     default: return false;
   }

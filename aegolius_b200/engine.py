@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import cabi
-from .grid import GridSpec, detect_grid
+from .grid import resolution_conversion, GridSpec, detect_grid
 from .program import Program, flatten
 from . import opcodes as oc
 
@@ -100,6 +100,15 @@ def create(obj, co, *, dtype="f32", grad=None, device=0, out=None, out_grad=None
     code, npdt = _dtype(dtype)
     gmode, rows = _grad_mode(grad)
     spec = detect_grid(co)
+    if prog.stages:
+        if spec is None or slab is not None or rows:
+            raise NotImplementedError("programs with grid stencils (conv_averaging / conv_edge_detection modifications) are "
+                                      "evaluated on whole grids only, without gradients")
+        field = _create_staged(prog, spec, code, npdt, device)
+        if out is not None:
+            out[...] = field
+            return out
+        return field
     cp = cabi.CProgram(prog)
     lib = cabi.lib()
     if spec is not None:
@@ -132,6 +141,46 @@ def create(obj, co, *, dtype="f32", grad=None, device=0, out=None, out_grad=None
         cabi.check(lib.ab_eval_points_host(cp.ref(), co.ctypes.data, n, n, code, gmode, field.ctypes.data, gptr,
                                            gstride, device))
     return (field, g_arr) if rows else field
+
+
+def _create_staged(prog, spec, code, npdt, device):
+    """Programs with grid-stencil stages: for every stage, in program order, the prefix program ops[:k] is evaluated over the
+    whole grid on the device, filtered by ab_box_filter / ab_edge_filter, and bound to the P_FIELD op that replaced the
+    modification; the full program then runs once with all fields bound. Nothing but the result leaves the device."""
+    lib = cabi.lib()
+    n = spec.n_points
+    item = np.dtype(npdt).itemsize
+    g = cabi.make_grid(spec.size, spec.res)
+    res3 = (C.c_uint32 * 3)(*spec.res)
+    bound = [None] * len(prog.blobs)
+    bufs = []
+    try:
+        for st in sorted(prog.stages, key=prog.stage_op_index):
+            want = tuple(resolution_conversion(int(r)) for r in st["res"] if r)
+            if want != tuple(spec.res[:len(want)]) or (len(want) == 2 and spec.res[2] != 1):
+                raise ValueError(f"Cannot reshape the pattern with shape ({n},)")  # what smarter_reshape raises
+            pre = prog.prefix(prog.stage_op_index(st))
+            d_in, d_out = _DevBuf(n * item, device), _DevBuf(n * item, device)
+            bufs += [d_in, d_out]
+            cp = cabi.CProgram(pre, device_blobs=bound)
+            cabi.check(lib.ab_eval_grid(cp.ref(), C.byref(g), code, cabi.AB_GRAD_NONE, d_in.ptr, None, 0, device, None))
+            if st["kind"] == 0:
+                ks = (C.c_uint32 * 3)(*st["ksize"])
+                cabi.check(lib.ab_box_filter(d_in.ptr, res3, ks, st["iterations"], code, d_out.ptr, device, None))
+            else:
+                cabi.check(lib.ab_edge_filter(d_in.ptr, res3, code, d_out.ptr, device, None))
+            bound[st["blob"]] = (d_out.ptr.value, n)
+        d_res = _DevBuf(n * item, device)
+        bufs.append(d_res)
+        cp = cabi.CProgram(prog, device_blobs=bound)
+        cabi.check(lib.ab_eval_grid(cp.ref(), C.byref(g), code, cabi.AB_GRAD_NONE, d_res.ptr, None, 0, device, None))
+        field = np.empty(n, dtype=npdt)
+        d_res.download(field)
+        cabi.check(lib.ab_stream_sync(device, None))
+    finally:
+        for b in bufs:
+            b.close()
+    return field
 
 
 def create_with_gradient(obj, co, **kw):

@@ -355,11 +355,12 @@ class ModifyObject:
     def signed(self, *a, **k):
         self._unsupported("signed")
 
-    def conv_averaging(self, *a, **k):
-        self._unsupported("conv_averaging")
+    # grid stencils (modifications.py:1586-1637): evaluated by separate kernels between two interpreter launches
+    def conv_averaging(self, kernel_size, iterations, co_resolution):
+        return self._add("conv_averaging", kernel_size=kernel_size, iterations=iterations, co_resolution=co_resolution)
 
-    def conv_edge_detection(self, *a, **k):
-        self._unsupported("conv_edge_detection")
+    def conv_edge_detection(self, co_resolution):
+        return self._add("conv_edge_detection", co_resolution=co_resolution)
 
 
 # ----------------------------------------------------------------------------------------------------------------

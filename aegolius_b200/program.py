@@ -25,13 +25,16 @@ class FlattenError(NotImplementedError):
 
 
 class Program:
-    def __init__(self, ops, args, blobs, n_pslots, n_vslots):
+    def __init__(self, ops, args, blobs, n_pslots, n_vslots, stages=()):
         self.ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
         self.args = np.ascontiguousarray(args, dtype=np.float64)
         self.blobs = [np.ascontiguousarray(b, dtype=np.float64) for b in blobs]
         self.n_pslots = int(n_pslots)
         self.n_vslots = int(n_vslots)
         self.dargs = None
+        # grid-stencil stages (conv_averaging / conv_edge_detection used as modifications): each entry names the P_FIELD
+        # blob it feeds and the stencil to run on the field accumulated by ops[:op_index] (see engine._create_staged)
+        self.stages = [dict(st) for st in stages]
 
     @property
     def n_ops(self):
@@ -58,14 +61,36 @@ class Program:
              prefix + "slots": np.array([self.n_pslots, self.n_vslots, len(self.blobs)], dtype=np.int64)}
         for i, b in enumerate(self.blobs):
             d[f"{prefix}blob{i}"] = b
+        if self.stages:
+            d[prefix + "stages"] = np.array([[st["blob"], st["kind"], *st["ksize"], st["iterations"], *st["res"]]
+                                             for st in self.stages], dtype=np.int64)
         return d
+
+    def stage_op_index(self, st):
+        """Position of the P_FIELD op fed by stage `st`."""
+        hit = np.nonzero((self.ops["opcode"] == oc.P_FIELD) & (self.ops["b"] == st["blob"]))[0]
+        if hit.size != 1:
+            raise ValueError("stage without a unique P_FIELD op")
+        return int(hit[0])
+
+    def prefix(self, op_index):
+        """The program that stops right before ops[op_index]: its result is the field a stencil stage consumes."""
+        ops = np.concatenate([self.ops[:op_index], np.array([(oc.END, 0, 0, 0)], dtype=OP_DTYPE)])
+        pre = Program(ops, self.args, self.blobs, self.n_pslots, self.n_vslots,
+                      [st for st in self.stages if self.stage_op_index(st) < op_index])
+        return pre
 
     @classmethod
     def from_arrays(cls, d, prefix="prog_"):
         ops = np.ascontiguousarray(d[prefix + "ops"]).view(OP_DTYPE).reshape(-1)
         slots = d[prefix + "slots"]
         blobs = [d[f"{prefix}blob{i}"] for i in range(int(slots[2]))]
-        return cls(ops, d[prefix + "args"], blobs, int(slots[0]), int(slots[1]))
+        stages = []
+        if prefix + "stages" in d:
+            for row in np.asarray(d[prefix + "stages"]).reshape(-1, 9):
+                stages.append(dict(blob=int(row[0]), kind=int(row[1]), ksize=tuple(int(v) for v in row[2:5]),
+                                   iterations=int(row[5]), res=tuple(int(v) for v in row[6:9])))
+        return cls(ops, d[prefix + "args"], blobs, int(slots[0]), int(slots[1]), stages)
 
 
 def _vec3(v, what):
@@ -132,6 +157,7 @@ class _Builder:
         self.ops = []
         self.args = []
         self.blobs = []
+        self.stages = []
         self.max_p = 0
         self.max_v = 0
         self.p_alias = None  # P-slot known to hold exactly the current coordinates (lets nested combines share it)
@@ -197,7 +223,10 @@ class _Builder:
 
         for post in reversed(posts):
             for (code, a, args) in post:
-                self.emit(code, a=a, args=args)
+                if code == oc.P_FIELD:
+                    self.emit(code, b=a)
+                else:
+                    self.emit(code, a=a, args=args)
         if s != 1.0:
             self.emit(oc.SCALE_V, args=[s])
 
@@ -369,6 +398,29 @@ class _Builder:
             post.append((oc.PP_GAUSS_BOUNDARY, 0, [p["amplitude"], p["width"]]))
         elif name == "gaussian_falloff":
             post.append((oc.PP_GAUSS_FALLOFF, 0, [p["amplitude"], p["width"]]))
+        elif name in ("conv_averaging", "conv_edge_detection"):
+            # grid stencils (modifications.py:1586-1637): the field accumulated so far is filtered over the whole grid by
+            # a separate kernel and comes back through a P_FIELD op; engine.create runs the stages in order
+            res = tuple(int(r) for r in np.asarray(p["co_resolution"]).reshape(-1))
+            if len(res) not in (2, 3):
+                raise FlattenError(f"{name}: co_resolution must have 2 or 3 entries")
+            if name == "conv_averaging":
+                ks = p["kernel_size"]
+                ks = (int(ks),) * len(res) if isinstance(ks, (int, np.integer)) else tuple(int(k) for k in np.asarray(ks).reshape(-1))
+                if len(ks) != len(res):
+                    raise ValueError("Dimension of the kernel and the field must match!")
+                its = int(p["iterations"])
+            else:
+                ks, its = (3, 3) + ((1,) if len(res) == 3 else ()), 1
+            if len(self.blobs) >= oc.MAX_BLOBS:
+                raise FlattenError(f"more than {oc.MAX_BLOBS} blobs (point clouds + stencil stages) in one tree")
+            if not (name == "conv_averaging" and its == 0):  # iterations == 0 returns the field untouched
+                self.blobs.append(np.zeros((1, 0)))
+                b = len(self.blobs) - 1
+                self.stages.append(dict(blob=b, kind=0 if name == "conv_averaging" else 1,
+                                        ksize=tuple(ks) + (1,) * (3 - len(ks)), iterations=its,
+                                        res=tuple(res) + (0,) * (3 - len(res))))
+                post.append((oc.P_FIELD, b, []))
         else:
             raise FlattenError(f"modification '{name}' cannot enter the GPU op list")
         return post, vd
@@ -723,4 +775,6 @@ def flatten(obj, optimize=True) -> Program:
         raise FlattenError(f"program too large: {len(ops)} ops / {len(args)} args "
                            f"(limits {oc.MAX_OPS} / {oc.MAX_ARGS})")
     arr = np.array(ops, dtype=OP_DTYPE)
-    return Program(arr, np.asarray(args, dtype=np.float64), b.blobs, max(b.max_p, 1), max(b.max_v, 1))
+    prog = Program(arr, np.asarray(args, dtype=np.float64), b.blobs, max(b.max_p, 1), max(b.max_v, 1), b.stages)
+    prog.stages.sort(key=prog.stage_op_index)  # evaluation order (modifications are visited outermost first)
+    return prog

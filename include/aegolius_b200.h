@@ -123,7 +123,11 @@ typedef enum ab_opcode {
   AB_OP_P_BRAID = 101, AB_OP_P_ARC3D = 102, AB_OP_P_PLANE = 103, AB_OP_P_UPLANE = 104, AB_OP_P_SEGMENT = 105,
   AB_OP_P_CONE = 106, AB_OP_P_OINF_CONE = 107, AB_OP_P_INF_CONE = 108, AB_OP_P_SOLID_ANGLE = 109,
   AB_OP_P_TRIANGLE3D = 110, AB_OP_P_QUAD3D = 111, AB_OP_P_SEGLINE = 112, AB_OP_P_AXIS = 113,
-  AB_OP_P_POINT_CLOUD = 114, /* a = dim (2|3), b = blob index: brute-force min distance (sdf_3D.py:283-286) */
+  AB_OP_P_POINT_CLOUD = 114, /* a = dim (2|3), b = blob index: nearest-point distance (sdf_3D.py:283-286) */
+  AB_OP_P_FIELD = 115,       /* b = blob index of a DEVICE field (blob.dim = 1, one value of the evaluation dtype per point
+                                of the call, indexed like `out`): value = field[point]. Carries the output of a grid
+                                stencil (conv_averaging / conv_edge_detection as a modification,
+                                modifications.py:1586-1637) back into the op list; no derivative passes through it */
   /* --- 2D primitives (sdf_2D.py), evaluated on (x,y) --- */
   AB_OP_P_CIRCLE = 128, AB_OP_P_NEU_CIRCLE = 129, AB_OP_P_BOX2D = 130, AB_OP_P_SEGMENT2D = 131,
   AB_OP_P_RBOX2D = 132, AB_OP_P_TRIANGLE2D = 133, AB_OP_P_ARC = 134, AB_OP_P_SECTOR = 135,

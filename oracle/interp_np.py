@@ -28,6 +28,7 @@ import numpy as np
  C_BOLTZ_SUB) = range(64, 75)
 (P_SPHERE, P_CYLINDER, P_BOX, P_TORUS, P_CHAINLINK, P_BRAID, P_ARC3D, P_PLANE, P_UPLANE, P_SEGMENT, P_CONE,
  P_OINF_CONE, P_INF_CONE, P_SOLID_ANGLE, P_TRIANGLE3D, P_QUAD3D, P_SEGLINE, P_AXIS, P_POINT_CLOUD) = range(96, 115)
+P_FIELD = 115  # output of a grid-stencil stage (conv_averaging / conv_edge_detection as modifications)
 (P_CIRCLE, P_NEU_CIRCLE, P_BOX2D, P_SEGMENT2D, P_RBOX2D, P_TRIANGLE2D, P_ARC, P_SECTOR, P_INF_SECTOR, P_NGON,
  P_SEGLINE2D, P_POLYGON2D) = range(128, 140)
 
@@ -85,7 +86,7 @@ def _tri_edge_sq(co_v, s, ss):  # one edge term of sdf_3D.py:203-206
     return sum(x * x for x in t)
 
 
-def run(prog, co, return_state=False, return_margin=False):
+def run(prog, co, return_state=False, return_margin=False, fields=None):
     """Evaluates the program on fp64 coordinates co (3,N); returns the field (N,) float64.
     Follows apply_ec_transforms (transformations.py:232-242) + the closure chain semantics (see program.py).
 
@@ -388,6 +389,10 @@ def run(prog, co, return_state=False, return_margin=False):
                 acc = out
             elif code == P_AXIS:  # :13-22
                 acc = (x, y, z)[a] - A[o]
+            elif code == P_FIELD:  # modifications.py:1586-1637: the filtered field of an earlier stage, same point order
+                acc = np.asarray(fields[b], dtype=np.float64)
+                if acc.shape != x.shape:
+                    raise ValueError("P_FIELD: the bound field does not match the evaluation points")
             elif code == P_POINT_CLOUD:  # sdf_3D.py:283-286 / sdf_2D.py:221-224 (exact NN distance)
                 from scipy.spatial import cKDTree
                 cloud = prog.blobs[b]
@@ -493,6 +498,8 @@ def run_grid(prog, size, res, x0=None, x1=None, chunk_planes=None, return_margin
     that 513^3 / 1025^3 fit in host RAM (pointwise ops make slabbing exactly equivalent)."""
     dims = 3 if res[2] > 1 or size[2] != 0 else 2
     axes = [np.linspace(-size[i] / 2, size[i] / 2, res[i]) for i in range(dims)]
+    if getattr(prog, "stages", None):
+        return _run_grid_staged(prog, size, res, dims, axes, x0, x1, return_margin)
     x0 = 0 if x0 is None else x0
     x1 = res[0] if x1 is None else x1
     per_plane = res[1] * res[2]
@@ -514,6 +521,36 @@ def run_grid(prog, size, res, x0=None, x1=None, chunk_planes=None, return_margin
         else:
             out[sl] = run(prog, co)
     return (out, mar) if return_margin else out
+
+
+def _run_grid_staged(prog, size, res, dims, axes, x0, x1, return_margin):
+    """Grid-stencil modifications (modifications.py:1586-1637: u = inner(co); u = smarter_reshape(u, res); stencil; flatten)
+    restated over the op list: every stage filters the field accumulated by the ops before its P_FIELD op."""
+    from . import fields_np
+    if x0 not in (None, 0) or x1 not in (None, res[0]):
+        raise ValueError("grid stencils need the whole grid")
+    if dims == 3:
+        co = np.asarray(np.meshgrid(axes[0], axes[1], axes[2], indexing="ij")).reshape(3, -1)
+    else:
+        c2 = np.asarray(np.meshgrid(axes[0], axes[1], indexing="ij")).reshape(2, -1)
+        co = np.zeros((3, c2.shape[1]))
+        co[:2] = c2
+    shape = tuple(int(r) for r in res[:dims])
+    fields = {}
+    margin = np.full(co.shape[1], np.inf)
+    for st in sorted(prog.stages, key=prog.stage_op_index):
+        pre = prog.prefix(prog.stage_op_index(st))
+        u, m = run(pre, co, return_margin=True, fields=fields)
+        margin = np.minimum(margin, m)
+        u = u.reshape(shape)
+        if st["kind"] == 0:
+            u = fields_np.conv_averaging(u, tuple(st["ksize"][:dims]), st["iterations"])
+        else:
+            u = fields_np.conv_edge_detection(u)
+        fields[st["blob"]] = u.reshape(-1)
+    out, m = run(prog, co, return_margin=True, fields=fields)
+    margin = np.minimum(margin, m)
+    return (out, margin) if return_margin else out
 
 
 def from_sdf(field, res, normalize=True):

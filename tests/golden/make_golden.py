@@ -31,7 +31,7 @@ def main():
     for name, sc in SCENARIOS.items():
         co, res = generate_grid(sc["size"], sc["res"])
         obj = sc["build"](ns)
-        expected = obj.create(co.copy())
+        expected = np.asarray(obj.create(co.copy())).reshape(-1)  # conv_edge_detection returns the N-D array
         prog = flatten(obj)
         out.update(prog.to_arrays(prefix=f"{name}/prog_"))
         out[f"{name}/expected"] = expected

@@ -138,6 +138,42 @@ scenario("prim3_parametric_curve3d_closed", *G3)(lambda ns: _xf(PRIMS3["parametr
 for _i, (_n, _b) in enumerate(PRIMS2.items()):
     scenario("prim2_" + _n, *G2)(lambda ns, _b=_b, _i=_i: _xf2(_b(ns), _i % 4))
 
+# grid stencils used as modifications (modifications.py:1586-1637); co_resolution = the scenario's requested resolution
+def _stencil_cloud2d(ns):  # surface_reconstruction_2D.py:132 pattern: a sparse 2D cloud smoothed by repeated averaging
+    rng = np.random.default_rng(12)
+    t = rng.uniform(0, 2 * np.pi, 60)
+    pc = ns.PointCloud2D(np.stack([2.2 * np.cos(t), 1.6 * np.sin(t)]))
+    pc.conv_averaging((5, 5), 4, G2[1])
+    pc.onion(0.2)
+    return pc
+
+
+def _stencil_tree3d(ns):  # a stencil inside one branch of a union, even-sized kernel, then more ops on top
+    s = ns.Sphere(1.1)
+    s.move((0.4, -0.2, 0.3))
+    s.conv_averaging((2, 3, 4), 2, G3[1])
+    s.rounding(0.05)
+    b = ns.Box(1.6, 1.0, 2.0)
+    b.rotate(0.5, (0, 1, 0))
+    u = ns.CombineGeometry("SMOOTH_UNION2").combine_parametric(s, b, parameters=0.3)
+    u.conv_averaging(3, 1, G3[1])
+    return u
+
+
+def _stencil_edge2d(ns):
+    c = ns.Circle(1.8)
+    c.move((0.6, -0.3, 0))
+    r = ns.Rectangle(2.5, 1.2)
+    u = ns.CombineGeometry("UNION2").combine(c, r)
+    u.hard_binarization(0.0)
+    u.conv_edge_detection(G2[1])
+    return u
+
+
+scenario("stencil_conv_averaging_cloud2d", *G2)(_stencil_cloud2d)
+scenario("stencil_conv_averaging_tree3d", *G3)(_stencil_tree3d)
+scenario("stencil_conv_edge_detection_2d", *G2)(_stencil_edge2d)
+
 # ---------------------------------------------------------------------------------------------------------------
 # modifications, one per scenario
 

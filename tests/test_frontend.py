@@ -69,11 +69,38 @@ def test_combine_api_errors_match_the_reference():
 
 def test_unflattenable_trees_raise_not_implemented_naming_the_culprit():
     s = ab.Sphere(1.0)
-    for name in ("custom_modification", "displacement", "define_volume", "signed", "conv_averaging"):
+    for name in ("custom_modification", "displacement", "define_volume", "signed", "custom_post_process"):
         with pytest.raises(NotImplementedError, match=name):
             getattr(s, name)(lambda *a: 0, ())
     with pytest.raises(NotImplementedError):
         ab.GenericGeometry(lambda co: co[0])
+
+
+def test_grid_stencil_modifications_become_stages():
+    """conv_averaging / conv_edge_detection as modifications: a P_FIELD op in the list + a stage record; the prefix
+    program of a stage ends right before its P_FIELD; programs with stages survive serialisation."""
+    s = ab.Sphere(1.0)
+    s.conv_averaging((3, 3, 3), 2, (16, 12, 20))
+    s.rounding(0.1)
+    s.conv_edge_detection((16, 12, 20))
+    prog = ab.flatten(s)
+    names = [oc.NAMES[int(o["opcode"])] for o in prog.ops]
+    assert names == ["P_SPHERE", "P_FIELD", "ROUND", "P_FIELD", "END"]
+    assert [st["kind"] for st in prog.stages] == [0, 1] and prog.stages[0]["ksize"] == (3, 3, 3)
+    assert prog.stages[0]["iterations"] == 2 and prog.stages[1]["res"] == (16, 12, 20)
+    pre = prog.prefix(prog.stage_op_index(prog.stages[1]))
+    assert [oc.NAMES[int(o["opcode"])] for o in pre.ops] == ["P_SPHERE", "P_FIELD", "ROUND", "END"]
+    assert len(pre.stages) == 1
+    back = ab.Program.from_arrays(prog.to_arrays())
+    assert back.stages == prog.stages and np.array_equal(back.ops, prog.ops)
+    # zero iterations leave the field untouched (post_processing.py:573-574): no stage at all
+    z = ab.Sphere(1.0)
+    z.conv_averaging(3, 0, (8, 8, 8))
+    assert not ab.flatten(z).stages
+    with pytest.raises(ValueError):
+        bad = ab.Sphere(1.0)
+        bad.conv_averaging((3, 3), 1, (8, 8, 8))
+        ab.flatten(bad)
 
 
 def test_late_binding_of_children_like_the_reference_closures():
