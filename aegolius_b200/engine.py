@@ -109,6 +109,12 @@ def create(obj, co, *, dtype="f32", grad=None, device=0, out=None, out_grad=None
             out[...] = field
             return out
         return field
+    if (spec is not None and not rows and out is None and prog.n_ops == 2
+            and int(prog.ops[0]["opcode"]) == oc.P_POINT_CLOUD):
+        # a bare, untransformed cloud on a grid (PointCloud3D(points).create(coor)): the dedicated nearest-neighbour
+        # path walks its octree once per warp of samples instead of once per sample
+        dim = int(prog.ops[0]["a"])
+        return point_cloud_sdf(spec, prog.blobs[int(prog.ops[0]["b"])][:dim], dim=dim, dtype=dtype, device=device, slab=slab)
     cp = cabi.CProgram(prog)
     lib = cabi.lib()
     if spec is not None:

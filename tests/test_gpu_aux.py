@@ -62,6 +62,24 @@ def test_point_cloud_leaf_inside_a_tree_matches_oracle(m):
     assert np.max(np.abs(nrm - 1.0)) <= 1e-9
 
 
+def test_bare_point_cloud_object_takes_the_dedicated_path():
+    """PointCloud3D(points).create(grid) with no transform or modification is routed to ab_nn_grid (packet walk);
+    same field as the interpreter leaf to fp32 rounding, and identical to point_cloud_sdf."""
+    import aegolius_b200 as ab
+    pts = _cloud(30000, seed=2)
+    spec = ab.GridSpec((2.5, 2.5, 1.5), (24, 20, 16))
+    bare = ab.PointCloud3D(pts)
+    assert ab.flatten(bare).n_ops == 2
+    a = ab.create(bare, spec, dtype="f32")
+    assert np.array_equal(a, ab.point_cloud_sdf(spec, pts, dtype="f32"))
+    moved = ab.PointCloud3D(pts)
+    moved.move((0.0, 0.0, 1e-300))  # a no-op translation keeps the interpreter path (3 ops)
+    b = ab.create(moved, spec, dtype="f32")
+    assert np.max(np.abs(a - b)) <= 1e-6 * 2.5
+    exp = interp_np.point_cloud_distance_kdtree(spec.materialize(), pts)
+    assert np.max(np.abs(a - exp)) <= 1e-5 * 2.5
+
+
 def test_point_cloud_2d_leaf_with_octree_matches_oracle():
     import aegolius_b200 as ab
     rng = np.random.default_rng(3)
