@@ -385,9 +385,18 @@ template <typename S>
 struct IsDual { static constexpr bool value = false; };
 template <typename P, int K>
 struct IsDual<Dual<P, K>> { static constexpr bool value = true; };
+// resident CTAs per SM the kernels are compiled for (register cap 65536 / (128 n)); measured on B200: the mid duals are
+// best at 7 (72 registers, no spills; 8 costs C3+gradient 15 %), the lite kernels at 8 (64 registers)
+#ifndef AB_MID_CTAS
+#define AB_MID_CTAS 7
+#endif
+#ifndef AB_LITE_CTAS
+#define AB_LITE_CTAS 8
+#endif
 template <typename S, int TIER>
 __host__ __device__ constexpr int min_ctas() {  // the wide lite dual kernel (4 points x 4 components) needs ~3x the registers
-  return (IsDual<S>::value && S::width >= 4) ? 3 : (TIER <= 1 ? 6 : 4);
+  if (sizeof(typename S::scalar) == 8) return TIER <= 1 ? 6 : 4;  // fp64 values take two registers: keep the 80-register cap
+  return (IsDual<S>::value && S::width >= 4) ? 3 : (TIER == 0 ? AB_LITE_CTAS : (TIER == 1 ? AB_MID_CTAS : 4));
 }
 
 #ifndef AB_BIG_CTA
