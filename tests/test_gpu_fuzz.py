@@ -155,3 +155,75 @@ def test_random_tree_gradient_and_points_mode(seed):
     assert ok.mean() > 0.6
     err = np.max(np.abs(grad[:, ok] - fd[:, ok]))
     assert err < 1e-4 * scale, f"seed {seed}: gradient off by {err:.2e}\\n{prog.disassemble()}"
+
+
+def _leaf2(ab, rng):
+    u = rng.uniform
+    k = rng.integers(0, 9)
+    if k == 0:
+        return ab.Circle(u(0.3, 1.2))
+    if k == 1:
+        return ab.Rectangle(u(0.5, 2.0), u(0.4, 1.5))
+    if k == 2:
+        return ab.RoundedRectangle(u(1.0, 2.0), u(0.8, 1.5), tuple(u(0.05, 0.3, 4)))
+    if k == 3:
+        return ab.NGon(u(0.5, 1.2), int(rng.integers(3, 9)))
+    if k == 4:
+        return ab.Triangle(tuple(u(-1.2, 1.2, 2)), tuple(u(-1.2, 1.2, 2)), tuple(u(-1.2, 1.2, 2)))
+    if k == 5:
+        return ab.Sector(u(0.6, 1.5), u(0.1, 0.8), u(1.0, 2.6))
+    if k == 6:
+        return ab.Arc(u(0.6, 1.3), u(0.1, 0.3), u(1.2, 2.8))
+    if k == 7:
+        return ab.Segment(tuple(u(-1.5, 1.5, 2)), tuple(u(-1.5, 1.5, 2)))
+    return ab.NEUCircle(u(0.5, 1.2), float(rng.choice([1.0, 3.0, 4.0])))
+
+
+def _tree2(ab, rng, depth):
+    u = rng.uniform
+
+    def place(o):
+        for _ in range(int(rng.integers(0, 2))):
+            j = rng.integers(0, 4)
+            if j == 0:
+                o.rounding(u(0.02, 0.15))
+            elif j == 1:
+                o.onion(u(0.03, 0.1))
+            elif j == 2:
+                o.symmetry(int(rng.integers(0, 2)))
+            else:
+                o.boundary()
+        o.rotate(u(0, 2 * np.pi), (0, 0, 1))
+        if rng.random() < 0.5:
+            o.rescale(u(0.6, 1.6))
+        o.move((u(-2.0, 2.0), u(-2.0, 2.0), 0.0))
+        return o
+    if depth == 0 or rng.random() < 0.2:
+        return place(_leaf2(ab, rng))
+    if rng.random() < 0.5:
+        op = NONPARAM[rng.integers(0, len(NONPARAM))]
+        n = int(rng.integers(2, 6)) if op in ("UNION", "INTERSECT") else 2
+        node = ab.CombineGeometry(op).combine(*[_tree2(ab, rng, depth - 1) for _ in range(n)])
+    else:
+        op = PARAM[rng.integers(0, len(PARAM))]
+        node = ab.CombineGeometry(op).combine_parametric(_tree2(ab, rng, depth - 1), _tree2(ab, rng, depth - 1),
+                                                         parameters=float(u(0.15, 0.5)))
+    return place(node) if rng.random() < 0.5 else node
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_random_2d_tree_matches_oracle(seed):
+    import aegolius_b200 as ab
+    rng = np.random.default_rng(5000 + seed)
+    prog = ab.flatten(_tree2(ab, rng, 3))
+    spec = ab.GridSpec((8.0, 8.0), (70, 58))
+    exp, margin = interp_np.run_grid(prog, spec.size + (0.0,), spec.res, return_margin=True)
+    ok = np.isfinite(exp)
+    assert ok.mean() > 0.99
+    scale = max(1.0, float(np.max(np.abs(exp[ok]))))
+    for dt, tol, band in (("f64", 1e-11, 1e-9), ("f32", 3e-5, 2e-6)):
+        got = ab.create(prog, spec, dtype=dt).astype(np.float64)
+        keep = ok & (margin > band * 8.0)
+        assert keep.mean() > 0.9
+        err = np.max(np.abs(got[keep] - exp[keep]))
+        assert err <= tol * 8.0 * scale, f"seed {seed} {dt}: max |cuda - oracle| = {err:.3e}\\n{prog.disassemble()}"
