@@ -59,6 +59,30 @@ def slab_ranges(n_planes: int, parts: int):
     return out
 
 
+def bind_to_device_numa(device=0):
+    """Pins the calling process to the CPUs NVML reports as local to `device` (same PCIe root / NUMA node), so that
+    page-locked buffers allocated afterwards land in memory next to the GPU and the D2H leg does not cross sockets.
+    Returns the CPU set, or None when NVML / affinity control is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # honour CUDA_VISIBLE_DEVICES: NVML enumerates physical devices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else device
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class PinnedArray:
     """Page-locked host buffer exposed as a numpy array (for the D2H leg of create())."""
 

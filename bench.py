@@ -258,6 +258,7 @@ def run_gpu(args):
     value = n_total / (ms_per_step * 1e-3)
 
     # ---- e2e: public API, host buffers, D2H inside the timed region ----
+    numa_cpus = None if os.environ.get("AB_NO_NUMA_BIND") else engine.bind_to_device_numa(local)
     pf = engine.PinnedArray((n_local,), np.float32)
     pg = engine.PinnedArray((3, n_local), np.float32)
     e2e_steps = max(1, min(args.steps, 3))
@@ -347,7 +348,8 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": n_total / e2e_s, "unit": "points/s", "h2d_bytes_per_step": prog.nbytes(),
                     "d2h_bytes_per_step": 16 * n_local, "ms_per_step": e2e_s * 1e3,
-                    "note": "aegolius_b200.create(obj, grid, grad='spatial') into pinned host arrays (per rank)"},
+                    "note": "aegolius_b200.create(obj, grid, grad='spatial') into pinned host arrays (per rank)",
+                    "numa_bound_cpus": len(numa_cpus) if numa_cpus else 0},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(n_local), "peak_source": peak_src,
