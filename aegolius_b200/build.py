@@ -59,6 +59,38 @@ def _compile(unit, extra_flags, force):
     return obj, "built"
 
 
+SPEC_DIR = os.path.join(HERE, "spec")
+
+
+def build_specialized(enabled_ops, kind, verbose=True):
+    """Compiles csrc/ab_interp_spec.cu with only `enabled_ops` (names as in opcodes.NAMES) into
+    aegolius_b200/spec/spec_<digest>.so and returns its path (cached: the digest covers the sources, the flags and the op
+    set). kind: 0 fp32 values, 1 fp32 + spatial gradient, 2 fp64 values, 3 fp64 + spatial gradient."""
+    from . import opcodes as oc
+    names = sorted(set(oc.NAMES.values()))
+    enabled = sorted(set(enabled_ops) | {"END"})
+    unknown = [n for n in enabled if n not in names]
+    if unknown:
+        raise ValueError(f"unknown ops {unknown}")
+    flags = [f"-DAB_SPEC_KIND={int(kind)}", f"-DAB_SPEC_MIN_CTAS={7 if kind < 2 else 6}"]
+    flags += [f"-DAB_SPEC_{n}=0" for n in names if n not in enabled]
+    dig = hashlib.sha256((_digest("ab_interp_spec.cu", flags) + ",".join(enabled)).encode()).hexdigest()[:20]
+    os.makedirs(SPEC_DIR, exist_ok=True)
+    out = os.path.join(SPEC_DIR, f"spec_{dig}.so")
+    if os.path.exists(out):
+        return out
+    tmp = out + f".tmp{os.getpid()}"
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + flags + [
+        "-Xcompiler", "-fvisibility=hidden", "-shared", "-o", tmp, os.path.join(CSRC, "ab_interp_spec.cu"), "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for the specialised kernel:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, out)
+    if verbose:
+        print(f"[aegolius_b200.build] specialised kernel ({len(enabled)} ops, kind {kind}): {out}")
+    return out
+
+
 def build(force=False, extra_flags=(), verbose=True):
     os.makedirs(BUILD, exist_ok=True)
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:

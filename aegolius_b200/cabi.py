@@ -70,6 +70,10 @@ _SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "ab_eval_grid_loss": (C.c_int, [C.POINTER(ab_program), C.POINTER(ab_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_void_p]),
+    "ab_spec_register": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "ab_spec_clear": (C.c_int, []),
+    "ab_op_tier": (C.c_int, [C.c_int]),
+    "ab_spec_hits": (C.c_uint64, []),
     "ab_eval_grid_host": (C.c_int, [C.POINTER(ab_program), C.POINTER(ab_grid), C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.c_int]),
     "ab_eval_points_host": (C.c_int, [C.POINTER(ab_program), C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,

@@ -322,6 +322,66 @@ static int dispatch_nt(const KParams<T>& kp, int device, cudaStream_t st) {
   return AB_OK;
 }
 
+// ---- program-specialised kernels (ab_interp_spec.cu, built on request) ------------------------------------------------------
+typedef int (*ab_spec_fn)(const void*, int, unsigned long long, void*, int*);
+struct SpecEntry {
+  int dtype, grad_mode;
+  uint8_t mask[AB_OP__COUNT];  // ops compiled into the kernel
+  ab_spec_fn fn;
+};
+static std::vector<SpecEntry> g_specs;
+static std::mutex g_spec_mu;
+static std::atomic<uint64_t> g_spec_hits{0};
+
+extern "C" int ab_spec_register(int dtype, int grad_mode, const uint8_t* op_mask, uint32_t mask_len, void* launch_fn,
+                                uint64_t kparams_size) {
+  if (!op_mask || !launch_fn || mask_len != AB_OP__COUNT) return fail(AB_EINVAL, "bad specialisation descriptor");
+  if (dtype != AB_F32 && dtype != AB_F64) return fail(AB_EINVAL, "bad dtype %d", dtype);
+  if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL) return fail(AB_EINVAL, "specialised kernels exist for values and spatial gradients only");
+  const uint64_t want = dtype == AB_F32 ? sizeof(KParams<float>) : sizeof(KParams<double>);
+  if (kparams_size != want) return fail(AB_EINVAL, "specialised kernel built against another library version (KParams %llu != %llu bytes)", (unsigned long long)kparams_size, (unsigned long long)want);
+  SpecEntry e{};
+  e.dtype = dtype;
+  e.grad_mode = grad_mode;
+  memcpy(e.mask, op_mask, AB_OP__COUNT);
+  e.fn = (ab_spec_fn)launch_fn;
+  std::lock_guard<std::mutex> lk(g_spec_mu);
+  g_specs.insert(g_specs.begin(), e);  // newest first
+  return AB_OK;
+}
+extern "C" int ab_op_tier(int opcode) { return (opcode < 0 || opcode >= AB_OP__COUNT) ? -1 : op_tier(opcode); }
+extern "C" int ab_spec_clear(void) {
+  std::lock_guard<std::mutex> lk(g_spec_mu);
+  g_specs.clear();
+  return AB_OK;
+}
+extern "C" uint64_t ab_spec_hits(void) { return g_spec_hits.load(); }
+
+static ab_spec_fn find_spec(const ab_program* prog, int dtype, int grad_mode) {
+  std::lock_guard<std::mutex> lk(g_spec_mu);
+  for (const SpecEntry& e : g_specs) {
+    if (e.dtype != dtype || e.grad_mode != grad_mode) continue;
+    bool ok = true;
+    for (uint32_t i = 0; i < prog->n_ops && ok; i++) ok = prog->ops[i].opcode < AB_OP__COUNT && e.mask[prog->ops[i].opcode];
+    if (ok) return e.fn;
+  }
+  return nullptr;
+}
+
+template <typename T>
+static int dispatch_spec(ab_spec_fn fn, const KParams<T>& kp, int device, cudaStream_t st) {
+  DevInfo di;
+  int rc = dev_info(device, di);
+  if (rc) return rc;
+  int status = AB_OK;
+  const cudaError_t e = (cudaError_t)fn(&kp, di.sms, (unsigned long long)di.smem_optin, st, &status);
+  if (e != cudaSuccess) return fail(AB_ECUDA, "specialised interpreter launch: %s", cudaGetErrorString(e));
+  if (status != AB_OK) return fail(status, "interpreter stacks (%u P, %u V slots) do not fit in shared memory", kp.n_pslots, kp.n_vslots);
+  g_launches++;
+  g_spec_hits++;
+  return AB_OK;
+}
+
 template <typename S, typename T, int TIER, bool PARAM = false>
 static int dispatch_fixed(const KParams<T>& kp, int device, cudaStream_t st) {
   DevInfo di;
@@ -450,6 +510,9 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
     }
   }
 
+  // a registered program-specialised kernel that covers every op of this program takes precedence over the tiers
+  const ab_spec_fn spec = (grad_mode == AB_GRAD_PARAM || loss_mode) ? nullptr
+                                                                      : find_spec(prog, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode);
   constexpr int WV = sizeof(T) == 4 ? 4 : 2;  // one 128-bit store per thread
   constexpr int WG = sizeof(T) == 4 ? 2 : 1;  // dual numbers carry 4x the state: halve the points per thread
   // the kernel indexes points with 32 bits: split big jobs into launches of < 2^31 points (whole planes in grid mode)
@@ -482,7 +545,8 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
     } else {
       kp.co = (const char*)tg.co + done * (tg.co_is_f64 ? 8 : 4);
     }
-    if (grad_mode == AB_GRAD_NONE) {
+    if (spec) rc = dispatch_spec<T>(spec, kp, device, st);
+    else if (grad_mode == AB_GRAD_NONE) {
       if constexpr (sizeof(T) == 4) {
         // lite programs are cheap per op, so 8 points per thread (two 128-bit stores) halve the per-point dispatch and
         // index overhead at still < 100 registers

@@ -87,6 +87,7 @@ struct Vec4<double> {
 };
 
 }  // namespace ab
+#include "ab_spec_default.h"
 #include "ab_tree.cuh"
 namespace ab {
 
@@ -395,6 +396,9 @@ struct IsDual<Dual<P, K>> { static constexpr bool value = true; };
 #endif
 template <typename S, int TIER>
 __host__ __device__ constexpr int min_ctas() {  // the wide lite dual kernel (4 points x 4 components) needs ~3x the registers
+#ifdef AB_SPEC_MIN_CTAS
+  return AB_SPEC_MIN_CTAS;  // specialised build: the caller knows which op set it compiled
+#endif
   if (sizeof(typename S::scalar) == 8) return TIER <= 1 ? 6 : 4;  // fp64 values take two registers: keep the 80-register cap
   return (IsDual<S>::value && S::width >= 4) ? 3 : (TIER == 0 ? AB_LITE_CTAS : (TIER == 1 ? AB_MID_CTAS : 4));
 }
@@ -565,7 +569,9 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
           p.y = SK::ld(pstack, sa * 3 + 1, NT);
           p.z = SK::ld(pstack, sa * 3 + 2, NT);
           break;
+#if AB_SPEC_PUSH_V
         case D_PUSH_V: SK::st(vstack, sa, NT, acc); break;
+#endif
         // fused [PUSH_V] + LOAD_P + transform (program.py::_fuse): one dispatch per child of a combine chain
         case D_NEXT_AFFINE:
         case D_NEXT_TRANSLATE:
@@ -578,56 +584,104 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
           else if (code == D_NEXT_TRANSLATE) op_translate(p, a);
           break;
         // coordinate ops
+#if AB_SPEC_AFFINE
         case D_AFFINE: op_affine(p, a); break;
+#endif
+#if AB_SPEC_TRANSLATE
         case D_TRANSLATE: op_translate(p, a); break;
+#endif
+#if AB_SPEC_SCALE_P
         case D_SCALE_P: op_scale_p(p, a); break;
+#endif
+#if AB_SPEC_ELONGATE
         case D_ELONGATE: op_elongate(p, a); break;
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_TWIST
         case D_TWIST: op_twist(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_BEND
         case D_BEND: op_bend(p, a); break;
 #endif
+#endif
+#if AB_SPEC_ABSX_SUB
         case D_ABSX_SUB: op_absx_sub(p, a); break;
+#endif
         case D_SYMMETRY:
           if (sa == 0) p.x = abs_(p.x);
           else if (sa == 1) p.y = abs_(p.y);
           else p.z = abs_(p.z);
           break;
 #if AB_TIER_FULL
+#if AB_SPEC_ROTSYM
         case D_ROTSYM: op_rotsym(p, a); break;
 #endif
+#endif
+#if AB_SPEC_REVOLVE
         case D_REVOLVE: op_revolve(p, a); break;
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_AXIS_REVOLVE
         case D_AXIS_REVOLVE: op_axis_revolve(p, a); break;
 #endif
+#endif
+#if AB_SPEC_REP_INF
         case D_REP_INF: op_rep_inf(p, a); break;
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_REP_FIN
         case D_REP_FIN: op_rep_fin(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_LIN_INST
         case D_LIN_INST: op_lin_inst(p, a, sa); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_CURVE_INST
         case D_CURVE_INST: op_curve_inst(p, a, sa); break;
 #endif
+#endif
+#if AB_SPEC_ZERO_Z
         case D_ZERO_Z: p.z = constant_like(p.z, T(0)); break;
+#endif
         // value ops
+#if AB_SPEC_ROUND
         case D_ROUND: acc = acc - a[0]; break;
+#endif
+#if AB_SPEC_ABS
         case D_ABS: acc = abs_(acc); break;
+#endif
+#if AB_SPEC_NEG
         case D_NEG: acc = -acc; break;
+#endif
+#if AB_SPEC_SIGN
         case D_SIGN: acc = sign_(acc); break;
+#endif
+#if AB_SPEC_ONION
         case D_ONION: acc = abs_(acc) - a[0]; break;
+#endif
+#if AB_SPEC_CONCENTRIC
         case D_CONCENTRIC: acc = abs_(acc - a[0]); break;
+#endif
+#if AB_SPEC_SCALE_V
         case D_SCALE_V: acc = acc * a[0]; break;
+#endif
         case D_EXTRUDE_BEGIN:
           SK::st(vstack, sa, NT, abs_(p.z) - a[0]);
           p.z = constant_like(p.z, T(0));
           break;
+#if AB_SPEC_EXTRUDE_END
         case D_EXTRUDE_END: acc = op_extrude_end<S, T>(acc, SK::ld(vstack, sa, NT)); break;
+#endif
         // post-processing (post_processing.py:380-560)
 #if AB_TIER_FULL
+#if AB_SPEC_PP_SIGMOID
         case D_PP_SIGMOID: acc = div_(constant_like(acc, a[0]), exp_(acc * (T(4) * rcp_arg(a[1]))) + T(1)); break;
+#endif
 #endif
 #if AB_TIER_FULL
         case D_PP_POS_SIGMOID:
@@ -635,7 +689,9 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
           break;
 #endif
 #if AB_TIER_FULL
+#if AB_SPEC_PP_CAPPED_EXP
         case D_PP_CAPPED_EXP: acc = min_(exp_(acc * (T(-4) * rcp_arg(a[1]))), T(1)) * a[0]; break;
+#endif
 #endif
 #if AB_TIER_FULL
         case D_PP_HARD_BIN:
@@ -643,10 +699,14 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
           break;
 #endif
 #if AB_TIER_FULL
+#if AB_SPEC_PP_LINEAR
         case D_PP_LINEAR: acc = clamp_(T(1) - acc * rcp_arg(a[1]), T(0), T(1)) * a[0]; break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_PP_RELU
         case D_PP_RELU: acc = max_(acc * rcp_arg(a[0]), T(0)); break;
+#endif
 #endif
 #if AB_TIER_FULL
         case D_PP_SMOOTH_RELU: {
@@ -673,57 +733,115 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
         } break;
 #endif
         // combine: acc = f(V[a], acc)
+#if AB_SPEC_C_UNION
         case D_C_UNION: acc = min_(SK::ld(vstack, sa, NT), acc); AB_CPUSH; break;
+#endif
+#if AB_SPEC_C_INTERSECT
         case D_C_INTERSECT: acc = max_(SK::ld(vstack, sa, NT), acc); AB_CPUSH; break;
+#endif
+#if AB_SPEC_C_SUBTRACT
         case D_C_SUBTRACT: acc = max_(SK::ld(vstack, sa, NT), -acc); AB_CPUSH; break;
+#endif
+#if AB_SPEC_C_SUM
         case D_C_SUM: acc = SK::ld(vstack, sa, NT) + acc; AB_CPUSH; break;
+#endif
+#if AB_SPEC_C_DIFF
         case D_C_DIFF: acc = SK::ld(vstack, sa, NT) - acc; AB_CPUSH; break;
+#endif
+#if AB_SPEC_C_SMIN2
         case D_C_SMIN2: acc = smin_poly2(SK::ld(vstack, sa, NT), acc, a[0]); AB_CPUSH; break;
+#endif
+#if AB_SPEC_C_SMIN3
         case D_C_SMIN3: acc = smin_poly3(SK::ld(vstack, sa, NT), acc, a[0]); AB_CPUSH; break;
+#endif
+#if AB_SPEC_C_SMAX3
         case D_C_SMAX3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), -acc, a[0]); AB_CPUSH; break;
+#endif
+#if AB_SPEC_C_SSUB3
         case D_C_SSUB3: acc = -smin_poly3(-SK::ld(vstack, sa, NT), acc, a[0]); AB_CPUSH; break;
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_C_BOLTZ_INT
         case D_C_BOLTZ_INT: acc = smax_boltz(SK::ld(vstack, sa, NT), acc, a[0]); AB_CPUSH; break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_C_BOLTZ_SUB
         case D_C_BOLTZ_SUB: acc = smax_boltz(SK::ld(vstack, sa, NT), -acc, a[0]); AB_CPUSH; break;
 #endif
+#endif
         // 3D primitives
+#if AB_SPEC_P_SPHERE
         case D_P_SPHERE: acc = prim_sphere(p, a); break;
+#endif
+#if AB_SPEC_P_FIELD
         case D_P_FIELD: load_field(kp.blob[sb], idx, kp.n, acc); break;
+#endif
+#if AB_SPEC_P_CYLINDER
         case D_P_CYLINDER: acc = prim_cylinder(p, a); break;
+#endif
+#if AB_SPEC_P_BOX
         case D_P_BOX: acc = prim_box(p, a); break;
+#endif
+#if AB_SPEC_P_TORUS
         case D_P_TORUS: acc = prim_torus(p, a); break;
+#endif
+#if AB_SPEC_P_CHAINLINK
         case D_P_CHAINLINK: acc = prim_chainlink(p, a); break;
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_BRAID
         case D_P_BRAID: acc = prim_braid(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_ARC3D
         case D_P_ARC3D: acc = prim_arc3d(p, a); break;
 #endif
+#endif
+#if AB_SPEC_P_PLANE
         case D_P_PLANE: acc = prim_plane(p, a); break;
+#endif
+#if AB_SPEC_P_UPLANE
         case D_P_UPLANE: acc = prim_uplane(p, a); break;
+#endif
+#if AB_SPEC_P_SEGMENT
         case D_P_SEGMENT: acc = prim_segment(p, a); break;
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_CONE
         case D_P_CONE: acc = prim_cone(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_OINF_CONE
         case D_P_OINF_CONE: acc = prim_inf_cone(p, a, true); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_INF_CONE
         case D_P_INF_CONE: acc = prim_inf_cone(p, a, false); break;
 #endif
+#endif
 #if AB_TIER_FULL >= 2
+#if AB_SPEC_P_SOLID_ANGLE
         case D_P_SOLID_ANGLE: acc = prim_solid_angle(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL >= 2
+#if AB_SPEC_P_TRIANGLE3D
         case D_P_TRIANGLE3D: acc = prim_triangle3d(p, a); break;
 #endif
-#if AB_TIER_FULL >= 2
-        case D_P_QUAD3D: acc = prim_quad3d(p, a); break;
 #endif
 #if AB_TIER_FULL >= 2
+#if AB_SPEC_P_QUAD3D
+        case D_P_QUAD3D: acc = prim_quad3d(p, a); break;
+#endif
+#endif
+#if AB_TIER_FULL >= 2
+#if AB_SPEC_P_SEGLINE
         case D_P_SEGLINE: acc = prim_segline(p, a, 3); break;
+#endif
 #endif
         case D_P_AXIS:
           if (sa == 0) acc = p.x - a[0];
@@ -731,38 +849,64 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
           else acc = p.z - a[0];
           break;
 #if AB_TIER_FULL >= 2
+#if AB_SPEC_P_POINT_CLOUD
         case D_P_POINT_CLOUD: acc = prim_point_cloud<S, T>(p, kp.blob[sb], kp.blob_count[sb], sa, kp.blob_tree[sb]); break;
 #endif
+#endif
         // 2D primitives
+#if AB_SPEC_P_CIRCLE
         case D_P_CIRCLE: acc = prim_circle(p, a); break;
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_NEU_CIRCLE
         case D_P_NEU_CIRCLE: acc = prim_neu_circle(p, a); break;
 #endif
+#endif
+#if AB_SPEC_P_BOX2D
         case D_P_BOX2D: acc = prim_box2d(p, a); break;
+#endif
+#if AB_SPEC_P_SEGMENT2D
         case D_P_SEGMENT2D: acc = prim_segment2d(p, a); break;
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_RBOX2D
         case D_P_RBOX2D: acc = prim_rbox2d(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_TRIANGLE2D
         case D_P_TRIANGLE2D: acc = prim_triangle2d(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_ARC
         case D_P_ARC: acc = prim_arc(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_SECTOR
         case D_P_SECTOR: acc = prim_sector(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_INF_SECTOR
         case D_P_INF_SECTOR: acc = prim_inf_sector(p, a); break;
 #endif
+#endif
 #if AB_TIER_FULL
+#if AB_SPEC_P_NGON
         case D_P_NGON: acc = prim_ngon(p, a); break;
 #endif
-#if AB_TIER_FULL >= 2
-        case D_P_SEGLINE2D: acc = prim_segline(p, a, 2); break;
 #endif
 #if AB_TIER_FULL >= 2
+#if AB_SPEC_P_SEGLINE2D
+        case D_P_SEGLINE2D: acc = prim_segline(p, a, 2); break;
+#endif
+#endif
+#if AB_TIER_FULL >= 2
+#if AB_SPEC_P_POLYGON2D
         case D_P_POLYGON2D: acc = prim_polygon2d(p, a); break;
+#endif
 #endif
         default: break;  // unknown opcodes are rejected on the host (AB_EUNSUPPORTED_OP)
       }

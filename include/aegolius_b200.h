@@ -193,6 +193,17 @@ int ab_eval_points(const ab_program* prog, const void* co, int co_dtype, uint64_
 int ab_eval_grid_loss(const ab_program* prog, const ab_grid* grid, int dtype, const void* target_dev, double* accum_dev,
                       int device, void* stream);
 
+/* Program-specialised kernels (optional). aegolius_b200/build.py can compile the interpreter with only the ops of one
+ * program (csrc/ab_interp_spec.cu -> its own shared object exporting ab_spec_launch); registering that launcher here makes
+ * every later evaluation whose ops are all in `op_mask` (AB_OP__COUNT bytes, 1 = compiled in) with the same dtype and
+ * grad_mode (AB_GRAD_NONE | AB_GRAD_SPATIAL) use it instead of the general tiers. Same results, smaller kernel. */
+int ab_spec_register(int dtype, int grad_mode, const uint8_t* op_mask, uint32_t mask_len, void* launch_fn,
+                     uint64_t kparams_size);
+int ab_spec_clear(void);
+/* Kernel tier an op needs: 0 lite, 1 mid, 2 full (the library runs a program on the smallest tier covering its ops). */
+int ab_op_tier(int opcode);
+uint64_t ab_spec_hits(void);
+
 /* Host-buffer variants (what the Python drop-in calls when the user wants a NumPy array back): allocate/reuse
  * device scratch, run, copy the result to `out_host` (pinned or pageable), synchronise. */
 int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out_host,

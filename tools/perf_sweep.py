@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--cases", default="sphere,c1,c3,c3g,c2,c1_64,c3_64,nn")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--nn-res", type=int, default=128)
+    ap.add_argument("--spec", action="store_true", help="register a program-specialised kernel (engine.specialize) first")
     args = ap.parse_args()
     peak = 6452.8
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -109,6 +110,9 @@ def main():
             continue
         obj, spec, dt, grad = cases[name]
         prog = ab.flatten(obj)
+        if args.spec:
+            cabi.lib().ab_spec_clear()
+            engine.specialize(prog, dtype=dt, grad=grad)
         tdt = torch.float32 if dt == "f32" else torch.float64
         n = spec.n_points
         field = torch.empty(n, dtype=tdt, device=dev)
