@@ -337,7 +337,7 @@ extern "C" int ab_spec_register(int dtype, int grad_mode, const uint8_t* op_mask
                                 uint64_t kparams_size) {
   if (!op_mask || !launch_fn || mask_len != AB_OP__COUNT) return fail(AB_EINVAL, "bad specialisation descriptor");
   if (dtype != AB_F32 && dtype != AB_F64) return fail(AB_EINVAL, "bad dtype %d", dtype);
-  if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL) return fail(AB_EINVAL, "specialised kernels exist for values and spatial gradients only");
+  if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL && grad_mode != AB_GRAD_PARAM) return fail(AB_EINVAL, "bad grad_mode %d", grad_mode);
   const uint64_t want = dtype == AB_F32 ? sizeof(KParams<float>) : sizeof(KParams<double>);
   if (kparams_size != want) return fail(AB_EINVAL, "specialised kernel built against another library version (KParams %llu != %llu bytes)", (unsigned long long)kparams_size, (unsigned long long)want);
   SpecEntry e{};
@@ -511,8 +511,7 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   }
 
   // a registered program-specialised kernel that covers every op of this program takes precedence over the tiers
-  const ab_spec_fn spec = (grad_mode == AB_GRAD_PARAM || loss_mode) ? nullptr
-                                                                      : find_spec(prog, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode);
+  const ab_spec_fn spec = find_spec(prog, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode);
   constexpr int WV = sizeof(T) == 4 ? 4 : 2;  // one 128-bit store per thread
   constexpr int WG = sizeof(T) == 4 ? 2 : 1;  // dual numbers carry 4x the state: halve the points per thread
   // the kernel indexes points with 32 bits: split big jobs into launches of < 2^31 points (whole planes in grid mode)

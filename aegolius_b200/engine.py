@@ -73,10 +73,11 @@ def specialize(obj, *, dtype="f32", grad=None, verbose=False):
     prog = _as_program(obj)
     code, _ = _dtype(dtype)
     gmode, _ = _grad_mode(grad)
-    if gmode not in (cabi.AB_GRAD_NONE, cabi.AB_GRAD_SPATIAL):
-        raise ValueError("specialised kernels exist for values and spatial gradients")
-    kind = (0 if code == cabi.AB_F32 else 2) + (1 if gmode == cabi.AB_GRAD_SPATIAL else 0)
-    if max(cabi.lib().ab_op_tier(int(o)) for o in prog.ops["opcode"]) == 0:
+    if gmode == cabi.AB_GRAD_PARAM:
+        kind = 4 if code == cabi.AB_F32 else 5
+    else:
+        kind = (0 if code == cabi.AB_F32 else 2) + (1 if gmode == cabi.AB_GRAD_SPATIAL else 0)
+    if gmode != cabi.AB_GRAD_PARAM and max(cabi.lib().ab_op_tier(int(o)) for o in prog.ops["opcode"]) == 0:
         # lite programs already run on a 23 KB kernel with twice the points per thread; a specialised build at the
         # standard width is slower (C1 at 1025^3: 3.0 -> 3.9 ms)
         return None
@@ -309,7 +310,7 @@ def jacfwd(geometry, argnums=0, *, mode="dual", dtype="f64", rel_step=1e-6, devi
     raise ValueError("mode must be 'dual' or 'fd'")
 
 
-def value_and_grad(geometry, spec, target, *, dtype="f32", device=0, post=None):
+def value_and_grad(geometry, spec, target, *, dtype="f32", device=0, post=None, specialized=False):
     """Counterpart of jax.value_and_grad(worker)(params) in Code/examples/autodiff/position_optimization.py:101-179 for the
     least-squares objective used there: loss(params) = sum((F(params) - target)^2), F = field of geometry(*params) on the
     grid `spec`. Returns f(params) -> (loss, d loss / d params).
@@ -318,7 +319,8 @@ def value_and_grad(geometry, spec, target, *, dtype="f32", device=0, post=None):
     the sums  sum(r^2), sum(2 r dF/dtheta_k)  are reduced inside the kernel (ab_eval_grid_loss: no per-point stores, two
     doubles come back); with `post` the launch returns (F, dF/dtheta_k) as torch tensors and the sums are torch reductions.
     `target` is a torch CUDA tensor or array of N values; `post(F, dF)` may map the field before the residual (e.g. a
-    falloff) and must return the transformed pair."""
+    falloff) and must return the transformed pair. specialized=True runs the loop on a program-specialised build of the
+    tangent kernel (engine.specialize, needs nvcc once)."""
     import torch
     dev = torch.device("cuda", device)
     tdt = torch.float32 if _dtype(dtype)[0] == cabi.AB_F32 else torch.float64
@@ -332,6 +334,8 @@ def value_and_grad(geometry, spec, target, *, dtype="f32", device=0, post=None):
         grads, loss = [], None
         for k in range(len(params)):
             prog = program_tangent(geometry, params, k)
+            if specialized:  # one compilation per op set (cached); later steps of the optimisation loop reuse it
+                specialize(prog, dtype=dtype, grad="param")
             if post is None:
                 # fused: the kernel reduces sum r^2 and sum 2 r dF/dtheta_k itself (ab_eval_grid_loss), nothing is stored
                 cp = cabi.CProgram(prog)

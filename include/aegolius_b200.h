@@ -196,7 +196,8 @@ int ab_eval_grid_loss(const ab_program* prog, const ab_grid* grid, int dtype, co
 /* Program-specialised kernels (optional). aegolius_b200/build.py can compile the interpreter with only the ops of one
  * program (csrc/ab_interp_spec.cu -> its own shared object exporting ab_spec_launch); registering that launcher here makes
  * every later evaluation whose ops are all in `op_mask` (AB_OP__COUNT bytes, 1 = compiled in) with the same dtype and
- * grad_mode (AB_GRAD_NONE | AB_GRAD_SPATIAL) use it instead of the general tiers. Same results, smaller kernel. */
+ * grad_mode use it instead of the general tiers (AB_GRAD_PARAM kernels also serve ab_eval_grid_loss). Same results,
+ * smaller kernel. */
 int ab_spec_register(int dtype, int grad_mode, const uint8_t* op_mask, uint32_t mask_len, void* launch_fn,
                      uint64_t kparams_size);
 int ab_spec_clear(void);

@@ -51,6 +51,30 @@ def test_specialised_kernel_is_bit_identical_and_selected_by_coverage():
     assert np.array_equal(f64[0], g64[0]) and np.array_equal(f64[1], g64[1])
 
 
+def test_specialised_tangent_kernel_in_the_optimisation_loop():
+    """value_and_grad(..., specialized=True): the fused loss reduction on a specialised AB_GRAD_PARAM kernel gives the same
+    loss and gradient as the general kernel."""
+    import aegolius_b200 as ab
+    from aegolius_b200 import cabi
+    lib = cabi.lib()
+    lib.ab_spec_clear()
+    spec = ab.GridSpec((4, 4, 4), (40, 36, 32))
+
+    def geometry(r, w):
+        s = ab.Sphere(r)
+        s.twist(0.4)
+        b = ab.Box(1.5, 1.0, 0.8)
+        return ab.CombineGeometry("SMOOTH_UNION2").combine_parametric(s, b, parameters=w)
+
+    target = ab.create(geometry(1.0, 0.25), spec, dtype="f32")
+    l0, g0 = ab.value_and_grad(geometry, spec, target)([0.8, 0.3])
+    hits = lib.ab_spec_hits()
+    l1, g1 = ab.value_and_grad(geometry, spec, target, specialized=True)([0.8, 0.3])
+    assert lib.ab_spec_hits() >= hits + 2
+    assert abs(l0 - l1) <= 1e-9 * abs(l0) and np.allclose(g0, g1, rtol=1e-9, atol=0)
+    lib.ab_spec_clear()
+
+
 def test_specialisation_registry_rejects_foreign_layouts():
     from aegolius_b200 import cabi, opcodes as oc
     lib = cabi.lib()
@@ -58,5 +82,5 @@ def test_specialisation_registry_rejects_foreign_layouts():
     fn = C.cast(lib.ab_version, C.c_void_p)
     assert lib.ab_spec_register(cabi.AB_F32, cabi.AB_GRAD_NONE, mask, oc.OP_COUNT, fn, 12345) == -1
     assert b"KParams" in lib.ab_last_error()
-    assert lib.ab_spec_register(cabi.AB_F32, cabi.AB_GRAD_PARAM, mask, oc.OP_COUNT, fn, 12345) == -1
+    assert lib.ab_spec_register(cabi.AB_F32, 7, mask, oc.OP_COUNT, fn, 12345) == -1
     assert lib.ab_spec_register(cabi.AB_F32, cabi.AB_GRAD_NONE, mask, 7, fn, 12345) == -1
