@@ -313,8 +313,9 @@ template <typename T>
 AB_DEV uint32_t cloud_nearest_tree(const TreeRef<T>& t, T x, T y, T z, int dim) {
   T best;
   uint32_t bi;
-  if (dim == 3) tree_nearest<T, 3, 0, true>(t, x, y, z, best, bi);
-  else tree_nearest<T, 2, 0, true>(t, x, y, T(0), best, bi);
+  // every lane of the warp is here with a neighbouring sample (the op stream is warp-uniform): walk the tree once for all
+  if (dim == 3) tree_nearest_packet<T, 3, 0, true>(t, x, y, z, best, bi);
+  else tree_nearest_packet<T, 2, 0, true>(t, x, y, T(0), best, bi);
   return bi;
 }
 

@@ -153,4 +153,90 @@ AB_DEV void tree_nearest(const TreeRef<T>& t, T qx, T qy, T qz, T& best, uint32_
   }
 }
 
+// The same walk for a whole warp at once (all 32 lanes must call it together): node state, child order (from lane 0's
+// query) and the stack are warp-uniform, every lane tests its own query against the child's box and a child is entered when
+// any lane still needs it; leaf points are fetched once per warp. For queries that are close together (grid samples) the
+// lanes need nearly the same nodes, so little is wasted and nothing diverges.
+template <typename T, int DIM, int FORM, bool TRACK>
+AB_DEV void tree_nearest_packet(const TreeRef<T>& t, T qx, T qy, T qz, T& best, uint32_t& best_i) {
+  typedef typename Vec4<T>::type V4;
+  constexpr int B = DIM;
+  constexpr uint32_t NC = 1u << B;
+  constexpr uint32_t kFull = 0xffffffffu;
+  const int L = t.levels;
+  const uint32_t* __restrict__ start = t.start;
+  const uint8_t* __restrict__ occ = t.occ;
+  const V4* __restrict__ pts = t.pts;
+  const T rx = qx - t.geom.org[0], ry = qy - t.geom.org[1], rz = DIM == 3 ? qz - t.geom.org[2] : T(0);
+  const T slack = t.geom.slack + T(sizeof(T) == 4 ? 4.8e-7 : 8.9e-16) * (s_abs(rx) + s_abs(ry) + s_abs(rz));
+  const T ux = __shfl_sync(kFull, rx, 0), uy = __shfl_sync(kFull, ry, 0), uz = __shfl_sync(kFull, rz, 0);
+  best = T(3.0e38);
+  best_i = 0;
+  uint32_t ix = 0, iy = 0, iz = 0, code = 0;
+  uint64_t stack = 0;
+  int l = 0;
+  uint32_t todo = 0;
+  bool fresh = true;
+  while (true) {
+    const T cs = t.geom.cell * (T)(1u << (L - l - 1));
+    const T css = cs + slack;
+    T ax0, ax1, ay0, ay1, az0 = T(0), az1 = T(0);
+    uint32_t hx, hy, hz = 0;
+    half_distances(rx, ix, cs, css, slack, ax0, ax1, hx);
+    half_distances(ry, iy, cs, css, slack, ay0, ay1, hy);
+    if constexpr (DIM == 3) half_distances(rz, iz, cs, css, slack, az0, az1, hz);
+    (void)hx, (void)hy, (void)hz;
+    uint32_t pref = (ux >= (T)(2 * ix + 1) * cs ? 1u : 0u) | (uy >= (T)(2 * iy + 1) * cs ? 2u : 0u);
+    if constexpr (DIM == 3) pref |= uz >= (T)(2 * iz + 1) * cs ? 4u : 0u;
+    if (fresh) todo = xor_permute<DIM>(occ[level_offset<DIM>(l) + code], pref);
+    bool descended = false;
+    while (todo) {
+      const uint32_t c = (uint32_t)(__ffs((int)todo) - 1) ^ pref;
+      todo &= todo - 1u;
+      const T bx = (c & 1u) ? ax1 : ax0, by = (c & 2u) ? ay1 : ay0, bz = (c & 4u) ? az1 : az0;
+      if (!__any_sync(kFull, tree_d2<FORM>(bx, by, bz) < best)) continue;
+      const uint32_t ccode = (code << B) | c;
+      const int shift = B * (L - l - 1);
+      const uint32_t s = start[(size_t)ccode << shift], e = start[(size_t)(ccode + 1) << shift];
+      if (shift == 0 || e - s <= t.leaf) {
+        for (uint32_t i = s; i < e; i++) {
+          const V4 p = pts[i];
+          const T dx = qx - p.x, dy = qy - p.y, dz = DIM == 3 ? qz - p.z : T(0);
+          const T d2 = tree_d2<FORM>(dx, dy, dz);
+          if constexpr (TRACK) {
+            if (d2 < best) {
+              best = d2;
+              best_i = i;
+            }
+          } else {
+            best = s_min(best, d2);
+          }
+        }
+        continue;
+      }
+      stack = (stack << NC) | todo;
+      l++;
+      ix = 2 * ix + (c & 1u);
+      iy = 2 * iy + ((c >> 1) & 1u);
+      if constexpr (DIM == 3) iz = 2 * iz + (c >> 2);
+      code = ccode;
+      descended = true;
+      break;
+    }
+    if (descended) {
+      fresh = true;
+      continue;
+    }
+    if (l == 0) break;
+    l--;
+    ix >>= 1;
+    iy >>= 1;
+    iz >>= 1;
+    code >>= B;
+    todo = (uint32_t)(stack & (uint64_t)((1u << NC) - 1u));
+    stack >>= NC;
+    fresh = false;
+  }
+}
+
 }  // namespace ab
