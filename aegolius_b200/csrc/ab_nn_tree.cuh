@@ -296,17 +296,7 @@ __global__ void __launch_bounds__(NT) ab_nn_tree_kernel(const __grid_constant__ 
 // need almost the same nodes, so the votes waste little and nothing diverges.
 template <typename T, int DIM, int NT>
 __global__ void __launch_bounds__(NT) ab_nn_tree_packet_kernel(const __grid_constant__ TreeParams<T> tp) {
-  typedef typename Vec4<T>::type V4;
-  constexpr int B = DIM;
-  constexpr uint32_t NC = 1u << B;
-  constexpr uint32_t kFull = 0xffffffffu;
   const TreeRef<T> tr = *tp.tree;
-  const uint32_t kLeaf = tr.leaf;
-  const TreeGeom<T> g = tr.geom;
-  const int L = tr.levels;
-  const uint32_t* __restrict__ start = tr.start;
-  const uint8_t* __restrict__ occ = tr.occ;
-  const V4* __restrict__ pts = tr.pts;
 
   const GridK& gk = tp.q.g;
   const uint32_t n0 = (uint32_t)(tp.q.n / gk.plane), n1 = gk.n1, n2 = gk.n2;
@@ -327,79 +317,10 @@ __global__ void __launch_bounds__(NT) ab_nn_tree_packet_kernel(const __grid_cons
   i1 = i1 < n1 ? i1 : n1 - 1;
   i2 = i2 < n2 ? i2 : n2 - 1;
   const uint64_t k = (i0 * n1 + i1) * n2 + i2;
-  T qx, qy, qz;
+  T qx, qy, qz, best;
+  uint32_t bi;
   nn_query_point(tp.q, k, qx, qy, qz);
-  const T rx = qx - g.org[0], ry = qy - g.org[1], rz = qz - g.org[2];
-  const T slack = g.slack + T(sizeof(T) == 4 ? 4.8e-7 : 8.9e-16) * (s_abs(rx) + s_abs(ry) + s_abs(rz));
-  // the packet's reference position orders the children
-  const T ux = __shfl_sync(kFull, rx, 0), uy = __shfl_sync(kFull, ry, 0), uz = __shfl_sync(kFull, rz, 0);
-  T best = T(3.0e38);
-  uint32_t ix = 0, iy = 0, iz = 0, code = 0;
-  uint64_t stack = 0;
-  int l = 0;
-  uint32_t todo = 0;
-  bool fresh = true;
-  while (true) {
-    const T cs = g.cell * (T)(1u << (L - l - 1));
-    const T css = cs + slack;
-    T ax0, ax1, ay0, ay1, az0 = T(0), az1 = T(0);
-    uint32_t hx, hy, hz = 0;
-    half_distances(rx, ix, cs, css, slack, ax0, ax1, hx);
-    half_distances(ry, iy, cs, css, slack, ay0, ay1, hy);
-    if constexpr (DIM == 3) half_distances(rz, iz, cs, css, slack, az0, az1, hz);
-    uint32_t pref = (ux >= (T)(2 * ix + 1) * cs ? 1u : 0u) | (uy >= (T)(2 * iy + 1) * cs ? 2u : 0u);
-    if constexpr (DIM == 3) pref |= uz >= (T)(2 * iz + 1) * cs ? 4u : 0u;
-    (void)hx, (void)hy, (void)hz;
-    if (fresh) todo = xor_permute<DIM>(occ[level_offset<DIM>(l) + code], pref);
-    bool descended = false;
-    while (todo) {
-      const uint32_t c = (uint32_t)(__ffs((int)todo) - 1) ^ pref;
-      todo &= todo - 1u;
-      const T bx = (c & 1u) ? ax1 : ax0, by = (c & 2u) ? ay1 : ay0, bz = (c & 4u) ? az1 : az0;
-      if (!__any_sync(kFull, tree_d2<1>(bx, by, bz) < best)) continue;
-      const uint32_t ccode = (code << B) | c;
-      const int shift = B * (L - l - 1);
-      const uint32_t s = start[(size_t)ccode << shift], e = start[(size_t)(ccode + 1) << shift];
-      if (shift == 0 || e - s <= kLeaf) {
-        for (uint32_t i = s; i < e; i++) {
-          const V4 p = pts[i];
-          T dx, dy, dz;
-          if constexpr (sizeof(T) == 4) {
-            dx = qx + (-p.x);
-            dy = qy + (-p.y);
-            dz = qz + (-p.z);
-          } else {
-            dx = qx - p.x;
-            dy = qy - p.y;
-            dz = qz - p.z;
-          }
-          best = s_min(best, tree_d2<1>(dx, dy, dz));
-        }
-        continue;
-      }
-      stack = (stack << NC) | todo;
-      l++;
-      ix = 2 * ix + (c & 1u);
-      iy = 2 * iy + ((c >> 1) & 1u);
-      if constexpr (DIM == 3) iz = 2 * iz + (c >> 2);
-      code = ccode;
-      descended = true;
-      break;
-    }
-    if (descended) {
-      fresh = true;
-      continue;
-    }
-    if (l == 0) break;
-    l--;
-    ix >>= 1;
-    iy >>= 1;
-    iz >>= 1;
-    code >>= B;
-    todo = (uint32_t)(stack & (uint64_t)((1u << NC) - 1u));
-    stack >>= NC;
-    fresh = false;
-  }
+  tree_nearest_packet<T, DIM, 1, false>(tr, qx, qy, qz, best, bi);
   if (valid) __stcs(tp.q.out + k, s_sqrt(best));
 }
 
