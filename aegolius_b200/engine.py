@@ -97,6 +97,45 @@ def specialize(obj, *, dtype="f32", grad=None, verbose=False):
     return path
 
 
+_AUTO_SPEC = {"on": False, "pending": {}, "lock": None}
+
+
+def set_auto_specialize(enable=True):
+    """Opt-in: every evaluation of a program that has no specialised kernel yet starts ONE background compilation for its
+    (op set, dtype, gradient mode); evaluations keep running on the general kernels until the build is registered, then
+    switch to it. Off by default (it launches nvcc on the host)."""
+    import threading
+    _AUTO_SPEC["on"] = bool(enable)
+    if _AUTO_SPEC["lock"] is None:
+        _AUTO_SPEC["lock"] = threading.Lock()
+
+
+def wait_for_specializations(timeout=None):
+    """Blocks until the background builds started so far are registered (tests, benchmarks)."""
+    for th in list(_AUTO_SPEC["pending"].values()):
+        th.join(timeout)
+
+
+def _auto_specialize(prog, dtype, grad):
+    if not _AUTO_SPEC["on"] or prog.stages:
+        return
+    import threading
+    key = (tuple(sorted({int(o) for o in prog.ops["opcode"]})), str(dtype), str(grad))
+    with _AUTO_SPEC["lock"]:
+        if key in _AUTO_SPEC["pending"]:
+            return
+
+        def work():
+            try:
+                specialize(prog, dtype=dtype, grad=grad)
+            except Exception:  # no nvcc / compile error: stay on the general kernels
+                pass
+
+        th = threading.Thread(target=work, name="aegolius-specialize", daemon=True)
+        _AUTO_SPEC["pending"][key] = th
+        th.start()
+
+
 def bind_to_device_numa(device=0):
     """Pins the calling process to the CPUs NVML reports as local to `device` (same PCIe root / NUMA node), so that
     page-locked buffers allocated afterwards land in memory next to the GPU and the D2H leg does not cross sockets.
@@ -171,6 +210,7 @@ def create(obj, co, *, dtype="f32", grad=None, device=0, out=None, out_grad=None
             out[...] = field
             return out
         return field
+    _auto_specialize(prog, dtype, grad)
     if (spec is not None and not rows and out is None and prog.n_ops == 2
             and int(prog.ops[0]["opcode"]) == oc.P_POINT_CLOUD):
         # a bare, untransformed cloud on a grid (PointCloud3D(points).create(coor)): the dedicated nearest-neighbour
@@ -368,6 +408,7 @@ def create_torch(obj, spec: GridSpec, *, dtype="f32", grad=None, device=0, slab=
     (and gradient (3,N) view of a row-padded buffer)."""
     import torch
     prog = _as_program(obj)
+    _auto_specialize(prog, dtype, grad)
     code, npdt = _dtype(dtype)
     tdt = torch.float32 if code == cabi.AB_F32 else torch.float64
     gmode, rows = _grad_mode(grad)

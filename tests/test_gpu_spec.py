@@ -75,6 +75,26 @@ def test_specialised_tangent_kernel_in_the_optimisation_loop():
     lib.ab_spec_clear()
 
 
+def test_auto_specialisation_switches_over_in_the_background():
+    import aegolius_b200 as ab
+    from aegolius_b200 import cabi
+    lib = cabi.lib()
+    lib.ab_spec_clear()
+    tree = ab.workloads.build_c2()
+    spec = ab.GridSpec((8, 8), (300, 260))
+    ab.set_auto_specialize(True)
+    try:
+        a = ab.create(tree, spec, dtype="f32")          # general kernel; the build starts in the background
+        ab.wait_for_specializations(timeout=300)
+        hits = lib.ab_spec_hits()
+        b = ab.create(tree, spec, dtype="f32")          # specialised kernel from now on
+        assert lib.ab_spec_hits() > hits
+        assert np.array_equal(a, b)
+    finally:
+        ab.set_auto_specialize(False)
+        lib.ab_spec_clear()
+
+
 def test_specialisation_registry_rejects_foreign_layouts():
     from aegolius_b200 import cabi, opcodes as oc
     lib = cabi.lib()
