@@ -348,38 +348,55 @@ __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDPa
   const uint64_t fplane = (uint64_t)(kp.n1 - kp.o1) * kp.n2;  // the buffer holds rows [o1, n1) of every plane
   const T* __restrict__ f = kp.field + (uint64_t)(i1 - kp.o1) * kp.n2 + i2;
   auto at = [&](uint32_t i0) { return f[(uint64_t)(i0 - kp.o0) * fplane]; };
-  T fm = T(0), fc = at(x_begin), fp = T(0);
+  // four planes per step with all their loads issued up front: the march is latency-bound otherwise (one DRAM load in
+  // flight per thread); U centre values ahead + 4 in-plane neighbours each = 20 independent loads per thread
+  constexpr int U = 4;
+  T fm = T(0), fc = at(x_begin);
   if (kp.has0 && x_begin > 0) fm = at(x_begin - 1);
-  for (uint32_t i0 = x_begin; i0 < x_end; i0++) {
-    if (kp.has0 && i0 + 1 < kp.n0) fp = at(i0 + 1);
-    const T* c = f + (uint64_t)(i0 - kp.o0) * fplane;
-    const T a1m = i1 > 0 ? c[-(int64_t)kp.n2] : T(0), a1p = i1 + 1 < kp.n1 ? c[kp.n2] : T(0);
-    const T a2m = i2 > 0 ? c[-1] : T(0), a2p = i2 + 1 < kp.n2 ? c[1] : T(0);
-    T g0 = kp.has0 ? fd_three(fm, fc, fp, i0, kp.n0) : T(0);
-    T g1 = fd_three(a1m, fc, a1p, i1, kp.n1);
-    T g2 = fd_three(a2m, fc, a2p, i2, kp.n2);
-    if (kp.normalize) {
-      // 3D: |(g0, g1, g2)|; 2D view: |(g1, g2)| — same nesting as np.linalg.norm's sum of squares is not needed, only
-      // the value to fp rounding (tests: <= 1e-13 fp64)
-      const T m = kp.has0 ? s_sqrt(s_fma(g0, g0, s_fma(g1, g1, g2 * g2))) : s_sqrt(s_fma(g1, g1, g2 * g2));
-      if (m != T(0)) {
-        const T im = T(1) / m;
-        g0 *= im;
-        g1 *= im;
-        g2 *= im;
+  for (uint32_t i0 = x_begin; i0 < x_end; i0 += U) {
+    T c[U + 2];  // planes i0-1 .. i0+U
+    c[0] = fm;
+    c[1] = fc;
+    T a1m[U], a1p[U], a2m[U], a2p[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t x = i0 + u;
+      c[u + 2] = (x + 1 < kp.n0 && x < x_end) ? at(x + 1) : T(0);
+      const bool live = x < x_end;
+      const T* p = f + (uint64_t)((live ? x : x_begin) - kp.o0) * fplane;
+      a1m[u] = (live && i1 > 0) ? p[-(int64_t)kp.n2] : T(0);
+      a1p[u] = (live && i1 + 1 < kp.n1) ? p[kp.n2] : T(0);
+      a2m[u] = (live && i2 > 0) ? p[-1] : T(0);
+      a2p[u] = (live && i2 + 1 < kp.n2) ? p[1] : T(0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t x = i0 + u;
+      if (x >= x_end) break;
+      T g0 = kp.has0 ? fd_three(c[u], c[u + 1], c[u + 2], x, kp.n0) : T(0);
+      T g1 = fd_three(a1m[u], c[u + 1], a1p[u], i1, kp.n1);
+      T g2 = fd_three(a2m[u], c[u + 1], a2p[u], i2, kp.n2);
+      if (kp.normalize) {
+        const T m = kp.has0 ? s_sqrt(s_fma(g0, g0, s_fma(g1, g1, g2 * g2))) : s_sqrt(s_fma(g1, g1, g2 * g2));
+        if (m != T(0)) {
+          const T im = T(1) / m;
+          g0 *= im;
+          g1 *= im;
+          g2 *= im;
+        }
+      }
+      const uint64_t l = ((uint64_t)(x - kp.b0) * w1 + (i1 - kp.b1)) * kp.n2 + i2;
+      if (kp.has0) {
+        __stcs(kp.out + l, g0);
+        __stcs(kp.out + kp.out_stride + l, g1);
+        __stcs(kp.out + 2 * kp.out_stride + l, g2);
+      } else {
+        __stcs(kp.out + l, g1);
+        __stcs(kp.out + kp.out_stride + l, g2);
       }
     }
-    const uint64_t l = ((uint64_t)(i0 - kp.b0) * w1 + (i1 - kp.b1)) * kp.n2 + i2;
-    if (kp.has0) {
-      __stcs(kp.out + l, g0);
-      __stcs(kp.out + kp.out_stride + l, g1);
-      __stcs(kp.out + 2 * kp.out_stride + l, g2);
-    } else {
-      __stcs(kp.out + l, g1);
-      __stcs(kp.out + kp.out_stride + l, g2);
-    }
-    fm = fc;
-    fc = fp;
+    fm = c[U];
+    fc = c[U + 1];
   }
 }
 
