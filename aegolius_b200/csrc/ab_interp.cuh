@@ -381,7 +381,7 @@ __host__ __device__ inline size_t prog_args_bytes(uint32_t n_args) { return ((si
 // primitives): 40 registers instead of ~120, so 3x the resident warps, and a 23 KB body instead of 170 KB. The host
 // picks the smallest tier that covers the program (op_tier below). TIER 1 adds every op with one transcendental or a
 // small table (twist, bend, rotational symmetry, instancing, Boltzmann combines, post-processing maps, cones, arcs,
-// n-gons, 2D triangles and sectors ...) at 72 registers; TIER 2 adds the widest primitives (3D triangles, quads, solid angles, polylines, polygons, point clouds).
+// n-gons ...) at 72 registers; TIER 2 adds the widest primitives (triangles, quads, sectors, solid angles, polylines, polygons, point clouds).
 // minimum resident CTAs per SM asked of the register allocator, per tier (128-thread CTAs): lite 6, mid 5, full 4
 template <typename S>
 struct IsDual { static constexpr bool value = false; };
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
         case D_P_RBOX2D: acc = prim_rbox2d(p, a); break;
 #endif
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
 #if AB_SPEC_P_TRIANGLE2D
         case D_P_TRIANGLE2D: acc = prim_triangle2d(p, a); break;
 #endif
@@ -884,7 +884,7 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
         case D_P_ARC: acc = prim_arc(p, a); break;
 #endif
 #endif
-#if AB_TIER_FULL
+#if AB_TIER_FULL >= 2
 #if AB_SPEC_P_SECTOR
         case D_P_SECTOR: acc = prim_sector(p, a); break;
 #endif
@@ -966,8 +966,8 @@ inline bool is_lite_op(int ab_opcode) {
 inline int op_tier(int ab_opcode) {
   if (is_lite_op(ab_opcode)) return 0;
   switch (ab_opcode) {
-    case AB_OP_P_SOLID_ANGLE: case AB_OP_P_TRIANGLE3D: case AB_OP_P_QUAD3D: case AB_OP_P_SEGLINE:
-    case AB_OP_P_SEGLINE2D: case AB_OP_P_POINT_CLOUD: case AB_OP_P_POLYGON2D:
+    case AB_OP_P_SOLID_ANGLE: case AB_OP_P_SECTOR: case AB_OP_P_TRIANGLE3D: case AB_OP_P_QUAD3D: case AB_OP_P_SEGLINE:
+    case AB_OP_P_SEGLINE2D: case AB_OP_P_POINT_CLOUD: case AB_OP_P_TRIANGLE2D: case AB_OP_P_POLYGON2D:
       return 2;
     default: return 1;
   }
