@@ -395,13 +395,16 @@ struct IsDual<Dual<P, K>> { static constexpr bool value = true; };
 #ifndef AB_LITE_CTAS
 #define AB_LITE_CTAS 8
 #endif
+#ifndef AB_FULL_CTAS
+#define AB_FULL_CTAS 4
+#endif
 template <typename S, int TIER>
 __host__ __device__ constexpr int min_ctas() {  // the wide lite dual kernel (4 points x 4 components) needs ~3x the registers
 #ifdef AB_SPEC_MIN_CTAS
   return AB_SPEC_MIN_CTAS;  // specialised build: the caller knows which op set it compiled
 #endif
   if (sizeof(typename S::scalar) == 8) return TIER <= 1 ? 6 : 4;  // fp64 values take two registers: keep the 80-register cap
-  return (IsDual<S>::value && S::width >= 4) ? 3 : (TIER == 0 ? AB_LITE_CTAS : (TIER == 1 ? AB_MID_CTAS : 4));
+  return (IsDual<S>::value && S::width >= 4) ? 3 : (TIER == 0 ? AB_LITE_CTAS : (TIER == 1 ? AB_MID_CTAS : AB_FULL_CTAS));
 }
 
 #ifndef AB_BIG_CTA
