@@ -100,14 +100,24 @@ __global__ void __launch_bounds__(256) ab_box_march_kernel(const T* __restrict__
   T w[K];
 #pragma unroll
   for (int t = 0; t < K - 1; t++) w[t + 1] = col[(uint64_t)reflect_index((int)a0 + t0 + t, (int)n_axis) * stride];
-  for (uint32_t a = a0; a < a1; a++, dst += stride) {
+  constexpr int U = 4;  // outputs per step: their loads are issued together (the march is latency-bound otherwise)
+  for (uint32_t a = a0; a < a1; a += U) {
+    T nw[U];
 #pragma unroll
-    for (int t = 0; t < K - 1; t++) w[t] = w[t + 1];
-    w[K - 1] = col[(uint64_t)reflect_index((int)a + t0 + K - 1, (int)n_axis) * stride];
-    T s = T(0);
+    for (int u = 0; u < U; u++)
+      nw[u] = a + u < a1 ? col[(uint64_t)reflect_index((int)(a + u) + t0 + K - 1, (int)n_axis) * stride] : T(0);
 #pragma unroll
-    for (int t = 0; t < K; t++) s = s + w[t];
-    *dst = divide ? s / norm : s;
+    for (int u = 0; u < U; u++) {
+      if (a + u >= a1) break;
+#pragma unroll
+      for (int t = 0; t < K - 1; t++) w[t] = w[t + 1];
+      w[K - 1] = nw[u];
+      T s = T(0);
+#pragma unroll
+      for (int t = 0; t < K; t++) s = s + w[t];
+      *dst = divide ? s / norm : s;
+      dst += stride;
+    }
   }
 }
 
@@ -142,21 +152,32 @@ __global__ void __launch_bounds__(256) ab_edge_kernel(const T* __restrict__ in, 
 #pragma unroll
     for (int db = 0; db < 3; db++) w[da + 1][db] = p[ob[db]];
   }
-  for (uint32_t a = a0; a < a1; a++, dst += sA) {
+  constexpr int U = 4;  // outputs per step, loads issued together (latency-bound otherwise)
+  for (uint32_t a = a0; a < a1; a += U) {
+    T nw[U][3];
 #pragma unroll
-    for (int db = 0; db < 3; db++) {
-      w[0][db] = w[1][db];
-      w[1][db] = w[2][db];
+    for (int u = 0; u < U; u++) {
+      const T* p = col + (uint64_t)reflect_index((int)(a + u) + 1, (int)nA) * sA;
+#pragma unroll
+      for (int db = 0; db < 3; db++) nw[u][db] = a + u < a1 ? p[ob[db]] : T(0);
     }
-    const T* p = col + (uint64_t)reflect_index((int)a + 1, (int)nA) * sA;
 #pragma unroll
-    for (int db = 0; db < 3; db++) w[2][db] = p[ob[db]];
-    T s = T(0);
+    for (int u = 0; u < U; u++) {
+      if (a + u >= a1) break;
 #pragma unroll
-    for (int da = 0; da < 3; da++)
+      for (int db = 0; db < 3; db++) {
+        w[0][db] = w[1][db];
+        w[1][db] = w[2][db];
+        w[2][db] = nw[u][db];
+      }
+      T s = T(0);
 #pragma unroll
-      for (int db = 0; db < 3; db++) s = s + w[da][db];
-    *dst = T(9) * w[1][1] - s;
+      for (int da = 0; da < 3; da++)
+#pragma unroll
+        for (int db = 0; db < 3; db++) s = s + w[da][db];
+      *dst = T(9) * w[1][1] - s;
+      dst += sA;
+    }
   }
 }
 
