@@ -308,18 +308,33 @@ __global__ void __launch_bounds__(256) ab_vec_kernel(const __grid_constant__ Vec
 
 template <typename T>
 __global__ void ab_vec_component_kernel(const T* __restrict__ vec, uint64_t stride, uint64_t n, int what, T* __restrict__ out) {
-  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-    const T v0 = vec[e], v1 = vec[stride + e], v2 = vec[2 * stride + e];
-    T r;
-    switch (what) {
-      case AB_VC_X: r = v0; break;
-      case AB_VC_Y: r = v1; break;
-      case AB_VC_Z: r = v2; break;
-      case AB_VC_PHI: r = atan2_(v1, v0); break;
-      case AB_VC_THETA: r = sizeof(T) == 4 ? (T)acosf((float)v2) : (T)acos((double)v2); break;
-      default: r = s_sqrt(v0 * v0 + v1 * v1 + v2 * v2); break;
+  constexpr int U = 4;  // elements per thread and step, loads issued together
+  const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += step * U) {
+    T v0[U], v1[U], v2[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t e = e0 + u * step;
+      const bool live = e < n;
+      v0[u] = live && what != AB_VC_Y && what != AB_VC_Z ? vec[e] : T(0);
+      v1[u] = live && what != AB_VC_X && what != AB_VC_Z ? vec[stride + e] : T(0);
+      v2[u] = live && what != AB_VC_X && what != AB_VC_Y && what != AB_VC_PHI ? vec[2 * stride + e] : T(0);
     }
-    out[e] = r;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t e = e0 + u * step;
+      if (e >= n) break;
+      T r;
+      switch (what) {
+        case AB_VC_X: r = v0[u]; break;
+        case AB_VC_Y: r = v1[u]; break;
+        case AB_VC_Z: r = v2[u]; break;
+        case AB_VC_PHI: r = atan2_(v1[u], v0[u]); break;
+        case AB_VC_THETA: r = sizeof(T) == 4 ? (T)acosf((float)v2[u]) : (T)acos((double)v2[u]); break;
+        default: r = s_sqrt(v0[u] * v0[u] + v1[u] * v1[u] + v2[u] * v2[u]); break;
+      }
+      out[e] = r;
+    }
   }
 }
 
