@@ -72,6 +72,12 @@ _SIGNATURES = {
                                     C.c_void_p]),
     "ab_spec_register": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
     "ab_spec_clear": (C.c_int, []),
+    "ab_prog_register": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64]),
+    "ab_prog_clear": (C.c_int, []),
+    "ab_prog_hits": (C.c_uint64, []),
+    "ab_prog_enable": (C.c_int, [C.c_int]),
+    "ab_prog_signature_hash": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_int, C.c_int]),
+    "ab_prog_arg_layout": (C.c_int, [C.POINTER(ab_program), C.c_void_p, C.POINTER(C.c_uint32)]),
     "ab_op_tier": (C.c_int, [C.c_int]),
     "ab_spec_hits": (C.c_uint64, []),
     "ab_eval_grid_host": (C.c_int, [C.POINTER(ab_program), C.POINTER(ab_grid), C.c_int, C.c_int, C.c_void_p,

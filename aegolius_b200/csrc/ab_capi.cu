@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "ab_kernels_aux.cuh"
@@ -270,7 +271,6 @@ static int build_tree(const typename Vec4<T>::type* cloud, uint32_t m, int dim, 
                       void** buf_out, const TreeRef<T>** ref_out);
 
 // ---- interpreter launch ----------------------------------------------------------------------------------------------------
-static const uint32_t kParamHalf = (AB_MAX_ARGS / 2) & ~3u;
 
 // arguments that the kernels read as plain tables (no tangent): see raw_args() uses in ab_ops.cuh
 static bool structural_arg(int opcode, int k) {
@@ -332,6 +332,7 @@ struct SpecEntry {
 static std::vector<SpecEntry> g_specs;
 static std::mutex g_spec_mu;
 static std::atomic<uint64_t> g_spec_hits{0};
+static std::atomic<uint64_t> g_prog_hits{0};
 
 extern "C" int ab_spec_register(int dtype, int grad_mode, const uint8_t* op_mask, uint32_t mask_len, void* launch_fn,
                                 uint64_t kparams_size) {
@@ -369,7 +370,7 @@ static ab_spec_fn find_spec(const ab_program* prog, int dtype, int grad_mode) {
 }
 
 template <typename T>
-static int dispatch_spec(ab_spec_fn fn, const KParams<T>& kp, int device, cudaStream_t st) {
+static int dispatch_spec(ab_spec_fn fn, const KParams<T>& kp, int device, cudaStream_t st, std::atomic<uint64_t>& hits) {
   DevInfo di;
   int rc = dev_info(device, di);
   if (rc) return rc;
@@ -378,8 +379,89 @@ static int dispatch_spec(ab_spec_fn fn, const KParams<T>& kp, int device, cudaSt
   if (e != cudaSuccess) return fail(AB_ECUDA, "specialised interpreter launch: %s", cudaGetErrorString(e));
   if (status != AB_OK) return fail(status, "interpreter stacks (%u P, %u V slots) do not fit in shared memory", kp.n_pslots, kp.n_vslots);
   g_launches++;
-  g_spec_hits++;
+  hits++;
   return AB_OK;
+}
+
+
+// ---- program-compiled kernels (aegolius_b200/codegen.py) ------------------------------------------------------------------------
+// One straight-line kernel per program STRUCTURE: the sequence of (opcode, a, b) before the terminator. Arguments still
+// travel in KParams at every launch, so a parameter sweep or an optimisation loop reuses one binary. The generated shared
+// object exports a launcher with the signature of ab_spec_fn; it is registered here under the structure's signature and
+// run_program prefers it over the interpreter tiers. Same op bodies, same arithmetic: results are bit-identical.
+struct ProgEntry {
+  int dtype, grad_mode;  // grad_mode | flavor << 8 (flavor 1: the binary serves 2D grids, 0: 3D grids and point lists)
+  std::vector<uint32_t> sig;
+  ab_spec_fn fn;
+};
+static std::unordered_map<uint64_t, std::vector<ProgEntry>> g_progs;
+static std::mutex g_prog_mu;
+static std::atomic<int> g_prog_enabled{1};
+
+static uint64_t sig_hash(const uint32_t* sig, uint32_t n, int dtype, int grad_mode) {
+  uint64_t h = 1469598103934665603ull;  // FNV-1a over the signature words, dtype and gradient mode
+  auto mix = [&](uint32_t w) {
+    for (int k = 0; k < 4; k++) {
+      h ^= (w >> (8 * k)) & 0xffu;
+      h *= 1099511628211ull;
+    }
+  };
+  for (uint32_t i = 0; i < n; i++) mix(sig[i]);
+  mix((uint32_t)dtype);
+  mix((uint32_t)grad_mode);
+  return h;
+}
+
+extern "C" uint64_t ab_prog_signature_hash(const uint32_t* signature, uint32_t n_sig, int dtype, int grad_mode) {
+  return (signature && n_sig <= AB_MAX_OPS) ? sig_hash(signature, n_sig, dtype, grad_mode) : 0;
+}
+
+extern "C" int ab_prog_register(const uint32_t* signature, uint32_t n_sig, int dtype, int grad_mode, int flavor,
+                                void* launch_fn, uint64_t kparams_size) {
+  if (!signature || n_sig == 0 || n_sig > AB_MAX_OPS || !launch_fn) return fail(AB_EINVAL, "bad compiled-program descriptor");
+  if (dtype != AB_F32 && dtype != AB_F64) return fail(AB_EINVAL, "bad dtype %d", dtype);
+  if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL && grad_mode != AB_GRAD_PARAM) return fail(AB_EINVAL, "bad grad_mode %d", grad_mode);
+  if (flavor != 0 && flavor != 1) return fail(AB_EINVAL, "bad flavor %d", flavor);
+  grad_mode |= flavor << 8;
+  const uint64_t want = dtype == AB_F32 ? sizeof(KParams<float>) : sizeof(KParams<double>);
+  if (kparams_size != want) return fail(AB_EINVAL, "compiled program built against another library version (KParams %llu != %llu bytes)", (unsigned long long)kparams_size, (unsigned long long)want);
+  ProgEntry e;
+  e.dtype = dtype;
+  e.grad_mode = grad_mode;
+  e.sig.assign(signature, signature + n_sig);
+  e.fn = (ab_spec_fn)launch_fn;
+  std::lock_guard<std::mutex> lk(g_prog_mu);
+  auto& bucket = g_progs[sig_hash(signature, n_sig, dtype, grad_mode)];
+  for (ProgEntry& o : bucket)
+    if (o.dtype == dtype && o.grad_mode == grad_mode && o.sig == e.sig) {
+      o.fn = e.fn;  // re-registration replaces the launcher
+      return AB_OK;
+    }
+  bucket.push_back(std::move(e));
+  return AB_OK;
+}
+extern "C" int ab_prog_clear(void) {
+  std::lock_guard<std::mutex> lk(g_prog_mu);
+  g_progs.clear();
+  return AB_OK;
+}
+extern "C" uint64_t ab_prog_hits(void) { return g_prog_hits.load(); }
+// 0: run_program ignores the registered compiled kernels (tests compare them against the interpreter); returns the old value
+extern "C" int ab_prog_enable(int on) { return g_prog_enabled.exchange(on ? 1 : 0); }
+
+static ab_spec_fn find_prog(const ab_program* prog, uint32_t n_ops, int dtype, int grad_mode, int flavor) {
+  if (!g_prog_enabled.load()) return nullptr;
+  grad_mode |= flavor << 8;
+  uint32_t sig[AB_MAX_OPS];
+  for (uint32_t i = 0; i < n_ops; i++)
+    sig[i] = (uint32_t)prog->ops[i].opcode | ((uint32_t)prog->ops[i].a << 16) | ((uint32_t)prog->ops[i].b << 24);
+  const uint64_t h = sig_hash(sig, n_ops, dtype, grad_mode);
+  std::lock_guard<std::mutex> lk(g_prog_mu);
+  auto it = g_progs.find(h);
+  if (it == g_progs.end()) return nullptr;
+  for (const ProgEntry& e : it->second)
+    if (e.dtype == dtype && e.grad_mode == grad_mode && e.sig.size() == n_ops && !memcmp(e.sig.data(), sig, n_ops * 4)) return e.fn;
+  return nullptr;
 }
 
 template <typename S, typename T, int TIER, bool PARAM = false>
@@ -394,6 +476,40 @@ static int dispatch_fixed(const KParams<T>& kp, int device, cudaStream_t st) {
   if (status != AB_OK) return fail(status, "interpreter stacks (%u P, %u V slots) do not fit in shared memory", kp.n_pslots, kp.n_vslots);
   g_launches++;
   return AB_OK;
+}
+
+
+// Offsets of every op's arguments in the kernel's repacked pool: each op on a 16-byte boundary (vector loads from shared
+// memory); first the ops with a fixed argument count, in program order, then the tables (instance records, sector tables,
+// polylines ...). The offsets of the fixed ones then depend on the op sequence alone, which is what lets a
+// program-compiled kernel (codegen.py) address them as compile-time constants of the constant bank.
+static int arg_layout(const ab_program* prog, uint32_t n_ops, uint32_t* offsets, int* counts, uint32_t* total) {
+  uint32_t cursor = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    for (uint32_t i = 0; i < n_ops; i++) {
+      if ((int)is_table_op(prog->ops[i].opcode) != pass) continue;
+      int cnt = 0;
+      int rc = op_arg_count(prog->ops[i], prog->args, prog->n_args, &cnt);
+      if (rc) return rc;
+      if (cursor + (uint32_t)cnt + 4 > AB_MAX_ARGS)
+        return fail(AB_ETOOLARGE, "program arguments exceed %d after alignment", AB_MAX_ARGS);
+      offsets[i] = cursor;
+      if (counts) counts[i] = cnt;
+      cursor = (cursor + (uint32_t)cnt + 3u) & ~3u;
+    }
+  }
+  *total = cursor;
+  return AB_OK;
+}
+
+// host-only view of the layout above (tests compare it with codegen.fixed_arg_offsets)
+extern "C" int ab_prog_arg_layout(const ab_program* prog, uint32_t* offsets_out, uint32_t* n_args_out) {
+  int rc = validate(prog);
+  if (rc) return rc;
+  if (!offsets_out || !n_args_out) return fail(AB_EINVAL, "null pointer");
+  uint32_t n_ops = prog->n_ops;
+  while (n_ops > 0 && prog->ops[n_ops - 1].opcode == AB_OP_END) n_ops--;
+  return arg_layout(prog, n_ops, offsets_out, nullptr, n_args_out);
 }
 
 template <typename T>
@@ -428,31 +544,34 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
     const int t = op_tier(prog->ops[i].opcode);
     if (t > kp.tier) kp.tier = t;
   }
-  // repack: every op's arguments start on a 16-byte boundary of the kernel's pool (vector loads from shared memory)
+  // repack the arguments into the kernel's pool (layout: arg_layout above)
   uint32_t cursor = 0;
-  for (uint32_t i = 0; i < kp.n_ops; i++) {
-    const uint32_t dense = (uint32_t)dense_opcode(prog->ops[i].opcode);  // validated above
-    int cnt = 0;
-    op_arg_count(prog->ops[i], prog->args, prog->n_args, &cnt);
-    if (cursor + (uint32_t)cnt + 4 > AB_MAX_ARGS)
-      return fail(AB_ETOOLARGE, "program arguments exceed %d after alignment", AB_MAX_ARGS);
-    kp.ops[i] = make_uint2(dense, cursor | ((uint32_t)prog->ops[i].a << 16) | ((uint32_t)prog->ops[i].b << 24));
-    for (int k = 0; k < cnt; k++) kp.args[cursor + k] = (T)prog->args[prog->ops[i].arg + k];
-    if (grad_mode == AB_GRAD_PARAM) {
-      // tangents of the arguments go to the upper half of the pool; table-driven ops are structural (their tables are
-      // read without tangents), so a parameter that reaches one of them cannot be differentiated here
-      if (cursor + (uint32_t)cnt + 4 > kParamHalf)
-        return fail(AB_ETOOLARGE, "program arguments exceed %u in parameter-tangent mode", kParamHalf);
-      for (int k = 0; k < cnt; k++) {
-        const double dk = prog->dargs[prog->ops[i].arg + k];
-        kp.args[kParamHalf + cursor + k] = (T)dk;
-        if (dk != 0.0 && structural_arg(prog->ops[i].opcode, k))
-          return fail(AB_EUNSUPPORTED_OP, "op %u (opcode %u): the differentiated parameter reaches a table argument (index %d); "
-                      "parameter tangents through instance / vertex / sector tables are not supported", i,
-                      (unsigned)prog->ops[i].opcode, k);
+  {
+    static thread_local uint32_t offs[AB_MAX_OPS];
+    static thread_local int cnts[AB_MAX_OPS];
+    rc = arg_layout(prog, kp.n_ops, offs, cnts, &cursor);
+    if (rc) return rc;
+    if (grad_mode == AB_GRAD_PARAM && cursor + 4 > kParamHalf)
+      return fail(AB_ETOOLARGE, "program arguments exceed %u in parameter-tangent mode", kParamHalf);
+    for (uint32_t i = 0; i < kp.n_ops; i++) {
+      const uint32_t dense = (uint32_t)dense_opcode(prog->ops[i].opcode);  // validated above
+      const uint32_t off = offs[i];
+      const int cnt = cnts[i];
+      kp.ops[i] = make_uint2(dense, off | ((uint32_t)prog->ops[i].a << 16) | ((uint32_t)prog->ops[i].b << 24));
+      for (int k = 0; k < cnt; k++) kp.args[off + k] = (T)prog->args[prog->ops[i].arg + k];
+      if (grad_mode == AB_GRAD_PARAM) {
+        // tangents of the arguments go to the upper half of the pool; table-driven ops are structural (their tables are
+        // read without tangents), so a parameter that reaches one of them cannot be differentiated here
+        for (int k = 0; k < cnt; k++) {
+          const double dk = prog->dargs[prog->ops[i].arg + k];
+          kp.args[kParamHalf + off + k] = (T)dk;
+          if (dk != 0.0 && structural_arg(prog->ops[i].opcode, k))
+            return fail(AB_EUNSUPPORTED_OP, "op %u (opcode %u): the differentiated parameter reaches a table argument (index %d); "
+                        "parameter tangents through instance / vertex / sector tables are not supported", i,
+                        (unsigned)prog->ops[i].opcode, k);
+        }
       }
     }
-    cursor = (cursor + (uint32_t)cnt + 3u) & ~3u;
   }
   kp.n_args = grad_mode == AB_GRAD_PARAM ? kParamHalf + cursor : cursor;
   kp.dargs_off = grad_mode == AB_GRAD_PARAM ? kParamHalf : 0;
@@ -511,7 +630,8 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   }
 
   // a registered program-specialised kernel that covers every op of this program takes precedence over the tiers
-  const ab_spec_fn spec = find_spec(prog, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode);
+  const ab_spec_fn compiled = find_prog(prog, kp.n_ops, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode, (tg.grid_mode && tg.g.is2d) ? 1 : 0);
+  const ab_spec_fn spec = compiled ? nullptr : find_spec(prog, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode);
   constexpr int WV = sizeof(T) == 4 ? 4 : 2;  // one 128-bit store per thread
   constexpr int WG = sizeof(T) == 4 ? 2 : 1;  // dual numbers carry 4x the state: halve the points per thread
   // the kernel indexes points with 32 bits: split big jobs into launches of < 2^31 points (whole planes in grid mode)
@@ -544,7 +664,8 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
     } else {
       kp.co = (const char*)tg.co + done * (tg.co_is_f64 ? 8 : 4);
     }
-    if (spec) rc = dispatch_spec<T>(spec, kp, device, st);
+    if (compiled) rc = dispatch_spec<T>(compiled, kp, device, st, g_prog_hits);
+    else if (spec) rc = dispatch_spec<T>(spec, kp, device, st, g_spec_hits);
     else if (grad_mode == AB_GRAD_NONE) {
       if constexpr (sizeof(T) == 4) {
         // lite programs are cheap per op, so 8 points per thread (two 128-bit stores) halve the per-point dispatch and

@@ -145,6 +145,112 @@ AB_DEV void grid_coord_run(const GridK& g, int c, int32_t i, Pack<double, W>& ou
   for (int j = 0; j < W; j++) out.v[j] = (i + j >= 0) ? grid_coord(g, c, (uint32_t)(i + j), 0.0) : 0.0;
 }
 
+// ---- walking the slab tile by tile ------------------------------------------------------------------------------------------
+// A CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...; every thread carries the index-axis coordinates (i0, i1, i2) of
+// its own first point in the current tile: two real divisions per thread at kernel start (tile_walk_begin), then three
+// carried additions per tile (the launcher decomposed the stride gridDim.x * tile points into tile_stride[]). No division
+// or multiply-high in the loop. Shared by the interpreter and by the program-compiled kernels (codegen.py).
+struct TileWalk {
+  uint32_t i0, i1, i2;  // local to the launch (the slab offsets i0_begin / i1_begin are added when coordinates are made)
+};
+template <typename T>
+AB_DEV void tile_walk_begin(const KParams<T>& kp, uint32_t tile_pts, uint32_t w_pts, TileWalk& w) {
+  w.i0 = w.i1 = w.i2 = 0;
+  if (kp.grid_mode) {
+    const uint32_t start = blockIdx.x * tile_pts + threadIdx.x * w_pts;
+    w.i0 = start / kp.g.plane;
+    const uint32_t rem = start - w.i0 * kp.g.plane;
+    w.i1 = rem / kp.g.n2;
+    w.i2 = rem - w.i1 * kp.g.n2;
+  }
+}
+// coordinates of this thread's W consecutive points (first local index idx) and the step to the CTA's next tile.
+// IS2D: -1 = read kp.g.is2d (interpreter), 0 / 1 = known at compile time (program-compiled kernels: saves 3 W selects)
+template <int IS2D = -1, typename T, int W>
+AB_DEV void tile_coords(const KParams<T>& kp, TileWalk& w, uint32_t idx, uint32_t n32, Pack<T, W>& cx, Pack<T, W>& cy,
+                        Pack<T, W>& cz) {
+  typedef Pack<T, W> P;
+  if (kp.grid_mode) {
+    uint32_t i2 = w.i2, i1 = w.i1 + kp.g.i1_begin, i0 = w.i0 + kp.g.i0_begin;
+    P ua, ub, uc;  // samples along index axes (slow, middle, fast)
+    if (i2 + W <= kp.g.n2) {  // the W points share one row: the common case
+      ua = P(grid_coord(kp.g, 0, i0, T()));
+      ub = P(grid_coord(kp.g, 1, i1, T()));
+      grid_coord_run(kp.g, 2, (int32_t)i2, uc);
+    } else if (kp.g.n2 >= (uint32_t)W) {  // exactly one row boundary inside the run: points j >= s sit on the next row
+      const int s = (int)(kp.g.n2 - i2);
+      uint32_t j1 = i1 + 1, j0 = i0;
+      if (j1 == kp.g.n1 + kp.g.i1_begin) {
+        j1 = kp.g.i1_begin;
+        ++j0;
+      }
+      const T a0 = grid_coord(kp.g, 0, i0, T()), a1 = grid_coord(kp.g, 1, i1, T());
+      const T n0 = grid_coord(kp.g, 0, j0, T()), n1 = grid_coord(kp.g, 1, j1, T());
+      P ra, rb;
+      grid_coord_run(kp.g, 2, (int32_t)i2, ra);
+      grid_coord_run(kp.g, 2, -s, rb);
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        const bool first = j < s;
+        ua.v[j] = first ? a0 : n0;
+        ub.v[j] = first ? a1 : n1;
+        uc.v[j] = first ? ra.v[j] : rb.v[j];
+      }
+    } else {  // rows shorter than the run (tiny grids): walk point by point
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        ua.v[j] = grid_coord(kp.g, 0, i0, T());
+        ub.v[j] = grid_coord(kp.g, 1, i1, T());
+        uc.v[j] = grid_coord(kp.g, 2, i2, T());
+        if (++i2 == kp.g.n2) {
+          i2 = 0;
+          if (++i1 == kp.g.n1 + kp.g.i1_begin) {
+            i1 = kp.g.i1_begin;
+            ++i0;
+          }
+        }
+      }
+    }
+    if (IS2D < 0 ? kp.g.is2d != 0 : IS2D != 0) {  // index axes (1, nx, ny): x = axis-1 sample, y = axis-2 sample, z = +0
+      cx = ub;
+      cy = uc;
+      cz = P(T(0));
+    } else {
+      cx = ua;
+      cy = ub;
+      cz = uc;
+    }
+    // advance this thread's first point by gridDim.x tiles
+    w.i2 += kp.tile_stride[2];
+    if (w.i2 >= kp.g.n2) {
+      w.i2 -= kp.g.n2;
+      w.i1++;
+    }
+    w.i1 += kp.tile_stride[1];
+    if (w.i1 >= kp.g.n1) {
+      w.i1 -= kp.g.n1;
+      w.i0++;
+    }
+    w.i0 += kp.tile_stride[0];
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+      const uint64_t k = idx + j < n32 ? idx + j : n32 - 1;
+      if (kp.co_is_f64) {
+        const double* c = (const double*)kp.co;
+        cx.v[j] = (T)__ldcs(c + k);
+        cy.v[j] = (T)__ldcs(c + kp.co_stride + k);
+        cz.v[j] = (T)__ldcs(c + 2 * kp.co_stride + k);
+      } else {
+        const float* c = (const float*)kp.co;
+        cx.v[j] = (T)__ldcs(c + k);
+        cy.v[j] = (T)__ldcs(c + kp.co_stride + k);
+        cz.v[j] = (T)__ldcs(c + 2 * kp.co_stride + k);
+      }
+    }
+  }
+}
+
 // ---- stack in shared memory: element [slot][tid] is one 16-byte Pack column --------------------------------------------
 template <typename P>
 AB_DEV void st_pack(P* base, int slot, int nt, const P& v) { base[slot * nt + threadIdx.x] = v; }
@@ -200,47 +306,90 @@ struct StackOf<Dual<Pk, K>> {
   }
 };
 
-// ---- 128-bit streaming stores ---------------------------------------------------------------------------------------------
+// ---- 128-bit stores ---------------------------------------------------------------------------------------------------------
+// AB_STORE_POLICY: 0 = streaming (st.global.cs: the field is written once and not read back by this kernel), 1 = default
+// write-back, 2 = st.global.cg, 3 = write-through. Measured on B200 in profiles/r02_jit_sweep.md.
+#ifndef AB_STORE_POLICY
+#define AB_STORE_POLICY 0
+#endif
+template <typename V>
+AB_DEV void ab_st(V* p, const V& v) {
+#if AB_STORE_POLICY == 0
+  __stcs(p, v);
+#elif AB_STORE_POLICY == 1
+  *p = v;
+#elif AB_STORE_POLICY == 2
+  __stcg(p, v);
+#else
+  __stwt(p, v);
+#endif
+}
 AB_DEV void store_pack(float* dst, const Pack<float, 4>& v, uint64_t idx, uint64_t n, bool aligned) {
   if (aligned && idx + 4 <= n) {
-    __stcs(reinterpret_cast<float4*>(dst + idx), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+    ab_st(reinterpret_cast<float4*>(dst + idx), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
   } else {
 #pragma unroll
     for (int i = 0; i < 4; i++)
-      if (idx + i < n) __stcs(dst + idx + i, v.v[i]);
+      if (idx + i < n) ab_st(dst + idx + i, v.v[i]);
   }
 }
 AB_DEV void store_pack(float* dst, const Pack<float, 8>& v, uint64_t idx, uint64_t n, bool aligned) {
   if (aligned && idx + 8 <= n) {
-    __stcs(reinterpret_cast<float4*>(dst + idx), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
-    __stcs(reinterpret_cast<float4*>(dst + idx) + 1, make_float4(v.v[4], v.v[5], v.v[6], v.v[7]));
+    ab_st(reinterpret_cast<float4*>(dst + idx), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+    ab_st(reinterpret_cast<float4*>(dst + idx) + 1, make_float4(v.v[4], v.v[5], v.v[6], v.v[7]));
   } else {
 #pragma unroll
     for (int i = 0; i < 8; i++)
-      if (idx + i < n) __stcs(dst + idx + i, v.v[i]);
+      if (idx + i < n) ab_st(dst + idx + i, v.v[i]);
   }
 }
 AB_DEV void store_pack(float* dst, const Pack<float, 2>& v, uint64_t idx, uint64_t n, bool aligned) {
   if (aligned && idx + 2 <= n) {
-    __stcs(reinterpret_cast<float2*>(dst + idx), make_float2(v.v[0], v.v[1]));
+    ab_st(reinterpret_cast<float2*>(dst + idx), make_float2(v.v[0], v.v[1]));
   } else {
 #pragma unroll
     for (int i = 0; i < 2; i++)
-      if (idx + i < n) __stcs(dst + idx + i, v.v[i]);
+      if (idx + i < n) ab_st(dst + idx + i, v.v[i]);
   }
 }
 AB_DEV void store_pack(double* dst, const Pack<double, 2>& v, uint64_t idx, uint64_t n, bool aligned) {
   if (aligned && idx + 2 <= n) {
-    __stcs(reinterpret_cast<double2*>(dst + idx), make_double2(v.v[0], v.v[1]));
+    ab_st(reinterpret_cast<double2*>(dst + idx), make_double2(v.v[0], v.v[1]));
   } else {
 #pragma unroll
     for (int i = 0; i < 2; i++)
-      if (idx + i < n) __stcs(dst + idx + i, v.v[i]);
+      if (idx + i < n) ab_st(dst + idx + i, v.v[i]);
   }
 }
 template <typename T>
 AB_DEV void store_pack(T* dst, const Pack<T, 1>& v, uint64_t idx, uint64_t n, bool) {
-  if (idx < n) __stcs(dst + idx, v.v[0]);
+  if (idx < n) ab_st(dst + idx, v.v[0]);
+}
+
+// Pack<float, 8> through a per-warp transposition in shared memory: a thread owns 8 consecutive points (32 bytes), so its
+// two direct 128-bit stores would each cover only half of every 32-byte sector the warp touches. Staged through 1 KB of
+// shared memory per warp (two conflict-free STS.128 + two LDS.128, __syncwarp), every STG.128 of the warp writes 512
+// contiguous bytes. `stage` = this warp's 64 float4; idx0 = first local point of the WARP (lane 0's idx).
+AB_DEV void store_pack_w8_transposed(float* dst, const Pack<float, 8>& v, uint32_t idx0, uint64_t n, bool aligned, float4* stage) {
+  const int lane = threadIdx.x & 31;
+  auto swz = [](int i) { return i ^ ((i >> 3) & 1); };
+  stage[swz(2 * lane)] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+  stage[swz(2 * lane + 1)] = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
+  __syncwarp();
+  const float4 a = stage[swz(lane)], b = stage[swz(32 + lane)];
+  __syncwarp();
+  const uint64_t ia = (uint64_t)idx0 + 4 * lane, ib = ia + 128;
+  if (aligned && ib + 4 <= n) {
+    ab_st(reinterpret_cast<float4*>(dst + ia), a);
+    ab_st(reinterpret_cast<float4*>(dst + ib), b);
+  } else {
+    const float va[4] = {a.x, a.y, a.z, a.w}, vb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (ia + i < n) ab_st(dst + ia + i, va[i]);
+      if (ib + i < n) ab_st(dst + ib + i, vb[i]);
+    }
+  }
 }
 
 // ---- seeding ------------------------------------------------------------------------------------------------------------
@@ -439,106 +588,14 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
   const uint32_t tile_pts = (uint32_t)NT * W;
   const uint32_t n32 = (uint32_t)kp.n;
   const uint32_t n_tiles = (n32 + tile_pts - 1) / tile_pts;
-  // (ix, iy, iz) of this CTA's first tile: one real division per CTA, then carried additions per tile
-  uint32_t b0 = 0, b1 = 0, b2 = 0;
-  if (kp.grid_mode) {
-    const uint32_t start = blockIdx.x * tile_pts;
-    b0 = start / kp.g.plane;
-    const uint32_t rem = start - b0 * kp.g.plane;
-    b1 = rem / kp.g.n2;
-    b2 = rem - b1 * kp.g.n2;
-  }
+  TileWalk walk;
+  tile_walk_begin(kp, tile_pts, (uint32_t)W, walk);
 
   double loss_sum = 0.0, dloss_sum = 0.0;  // loss mode only (PARAM kernels)
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t idx = tile * tile_pts + threadIdx.x * W;  // first local point of this thread
     P cx, cy, cz;
-    if (kp.grid_mode) {
-      uint32_t q, i2, i1, i0;
-      divmod_small(b2 + threadIdx.x * W, kp.g.n2, kp.g.m2, q, i2);
-      divmod_small(b1 + q, kp.g.n1, kp.g.m1, q, i1);
-      i0 = b0 + q + kp.g.i0_begin;
-      i1 += kp.g.i1_begin;
-      const int ca = kp.g.is2d ? 1 : 0, cb = kp.g.is2d ? 2 : 1;  // parameter sets of the two slow coordinates
-      P ua, ub, uc;  // samples along index axes (slow, middle, fast)
-      if (i2 + W <= kp.g.n2) {  // the W points share one row: the common case
-        ua = P(grid_coord(kp.g, 0, i0, T()));
-        ub = P(grid_coord(kp.g, 1, i1, T()));
-        grid_coord_run(kp.g, 2, (int32_t)i2, uc);
-      } else if (kp.g.n2 >= (uint32_t)W) {  // exactly one row boundary inside the run: points j >= s sit on the next row
-        const int s = (int)(kp.g.n2 - i2);
-        uint32_t j1 = i1 + 1, j0 = i0;
-        if (j1 == kp.g.n1 + kp.g.i1_begin) {
-          j1 = kp.g.i1_begin;
-          ++j0;
-        }
-        const T a0 = grid_coord(kp.g, 0, i0, T()), a1 = grid_coord(kp.g, 1, i1, T());
-        const T n0 = grid_coord(kp.g, 0, j0, T()), n1 = grid_coord(kp.g, 1, j1, T());
-        P ra, rb;
-        grid_coord_run(kp.g, 2, (int32_t)i2, ra);
-        grid_coord_run(kp.g, 2, -s, rb);
-#pragma unroll
-        for (int j = 0; j < W; j++) {
-          const bool first = j < s;
-          ua.v[j] = first ? a0 : n0;
-          ub.v[j] = first ? a1 : n1;
-          uc.v[j] = first ? ra.v[j] : rb.v[j];
-        }
-      } else {  // rows shorter than the run (tiny grids): walk point by point
-#pragma unroll
-        for (int j = 0; j < W; j++) {
-          ua.v[j] = grid_coord(kp.g, 0, i0, T());
-          ub.v[j] = grid_coord(kp.g, 1, i1, T());
-          uc.v[j] = grid_coord(kp.g, 2, i2, T());
-          if (++i2 == kp.g.n2) {
-            i2 = 0;
-            if (++i1 == kp.g.n1 + kp.g.i1_begin) {
-              i1 = kp.g.i1_begin;
-              ++i0;
-            }
-          }
-        }
-      }
-      (void)ca;
-      (void)cb;
-      if (kp.g.is2d) {
-        cx = ub;
-        cy = uc;
-        cz = P(T(0));
-      } else {
-        cx = ua;
-        cy = ub;
-        cz = uc;
-      }
-      // advance the tile origin by gridDim.x tiles
-      b2 += kp.tile_stride[2];
-      if (b2 >= kp.g.n2) {
-        b2 -= kp.g.n2;
-        b1++;
-      }
-      b1 += kp.tile_stride[1];
-      if (b1 >= kp.g.n1) {
-        b1 -= kp.g.n1;
-        b0++;
-      }
-      b0 += kp.tile_stride[0];
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; j++) {
-        const uint64_t k = idx + j < n32 ? idx + j : n32 - 1;
-        if (kp.co_is_f64) {
-          const double* c = (const double*)kp.co;
-          cx.v[j] = (T)__ldcs(c + k);
-          cy.v[j] = (T)__ldcs(c + kp.co_stride + k);
-          cz.v[j] = (T)__ldcs(c + 2 * kp.co_stride + k);
-        } else {
-          const float* c = (const float*)kp.co;
-          cx.v[j] = (T)__ldcs(c + k);
-          cy.v[j] = (T)__ldcs(c + kp.co_stride + k);
-          cz.v[j] = (T)__ldcs(c + 2 * kp.co_stride + k);
-        }
-      }
-    }
+    tile_coords(kp, walk, idx, n32, cx, cy, cz);
 
     Pt<S> p;
     seed(p, cx, cy, cz);
@@ -684,57 +741,41 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
         // post-processing (post_processing.py:380-560)
 #if AB_TIER_FULL
 #if AB_SPEC_PP_SIGMOID
-        case D_PP_SIGMOID: acc = div_(constant_like(acc, a[0]), exp_(acc * (T(4) * rcp_arg(a[1]))) + T(1)); break;
+        case D_PP_SIGMOID: acc = pp_sigmoid(acc, a); break;
 #endif
 #endif
 #if AB_TIER_FULL
-        case D_PP_POS_SIGMOID:
-          acc = div_(constant_like(acc, a[0]), exp_((acc - a[1]) * (T(4) * rcp_arg(a[1]))) + T(1));
-          break;
+        case D_PP_POS_SIGMOID: acc = pp_pos_sigmoid(acc, a); break;
 #endif
 #if AB_TIER_FULL
 #if AB_SPEC_PP_CAPPED_EXP
-        case D_PP_CAPPED_EXP: acc = min_(exp_(acc * (T(-4) * rcp_arg(a[1]))), T(1)) * a[0]; break;
+        case D_PP_CAPPED_EXP: acc = pp_capped_exp(acc, a); break;
 #endif
 #endif
 #if AB_TIER_FULL
-        case D_PP_HARD_BIN:
-          acc = select_(le_(acc, a[0]), constant_like(acc, T(1)), constant_like(acc, T(0)));
-          break;
+        case D_PP_HARD_BIN: acc = pp_hard_bin(acc, a); break;
 #endif
 #if AB_TIER_FULL
 #if AB_SPEC_PP_LINEAR
-        case D_PP_LINEAR: acc = clamp_(T(1) - acc * rcp_arg(a[1]), T(0), T(1)) * a[0]; break;
+        case D_PP_LINEAR: acc = pp_linear(acc, a); break;
 #endif
 #endif
 #if AB_TIER_FULL
 #if AB_SPEC_PP_RELU
-        case D_PP_RELU: acc = max_(acc * rcp_arg(a[0]), T(0)); break;
+        case D_PP_RELU: acc = pp_relu(acc, a); break;
 #endif
 #endif
 #if AB_TIER_FULL
-        case D_PP_SMOOTH_RELU: {
-          S v = acc * rcp_arg(a[1]);
-          acc = (v + sqrt_(fma_(v, v, constant_like(v, a[0])))) * T(0.5);
-        } break;
+        case D_PP_SMOOTH_RELU: acc = pp_smooth_relu(acc, a); break;
 #endif
 #if AB_TIER_FULL
-        case D_PP_SLOWSTART: {
-          S v = max_(acc * rcp_arg(a[0]), T(0));
-          acc = sqrt_(fma_(v, v, constant_like(v, a[1]))) - a[2];
-        } break;
+        case D_PP_SLOWSTART: acc = pp_slowstart(acc, a); break;
 #endif
 #if AB_TIER_FULL
-        case D_PP_GAUSS_BOUNDARY: {
-          S v = acc * rcp_arg(a[1]);
-          acc = exp_(v * v * T(-4)) * a[0];
-        } break;
+        case D_PP_GAUSS_BOUNDARY: acc = pp_gauss_boundary(acc, a); break;
 #endif
 #if AB_TIER_FULL
-        case D_PP_GAUSS_FALLOFF: {
-          S v = max_(acc, T(0)) * rcp_arg(a[1]);
-          acc = exp_(v * v * T(-4)) * a[0];
-        } break;
+        case D_PP_GAUSS_FALLOFF: acc = pp_gauss_falloff(acc, a); break;
 #endif
         // combine: acc = f(V[a], acc)
 #if AB_SPEC_C_UNION
@@ -947,6 +988,16 @@ struct LaunchCfg {
 // returns cudaSuccess or the CUDA error; *status is AB_OK / AB_ETOOLARGE
 template <typename S, typename T, int TIER, bool PARAM = false>
 cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream_t st, int* status);
+
+// ops whose argument count depends on the program (tables): the launcher packs them after the fixed-size arguments
+inline bool is_table_op(int ab_opcode) {
+  switch (ab_opcode) {
+    case AB_OP_ROTSYM: case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D: return true;
+    default: return false;
+  }
+}
+// AB_GRAD_PARAM: args[kParamHalf + i] = d args[i] / d theta (second half of the pool)
+constexpr uint32_t kParamHalf = (AB_MAX_ARGS / 2) & ~3u;
 
 inline int op_tier(int ab_opcode);
 inline bool is_lite_op(int ab_opcode) {

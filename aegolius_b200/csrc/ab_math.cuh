@@ -120,14 +120,20 @@ AB_DEV double s_pow(double a, double b) { return ab_pow(a, b); }
 AB_DEV float s_log(float a) { return logf(a); }
 AB_DEV double s_log(double a) { return log(a); }
 
-// np.mod semantics for b > 0 (floor-mod, result in [0, b)): r = a - floor(a/b)*b evaluated with one FMA (exact when
-// the quotient is right) and repaired when the rounded quotient is off by one.
+// np.mod semantics (floor-mod: result in [0, b) for b > 0, in (b, 0] for b < 0 — the sign of the divisor):
+// r = a - floor(a/b)*b evaluated with one FMA (exact when the quotient is right) and repaired when the rounded quotient
+// is off by one.
 template <typename T>
 AB_DEV T s_mod(T a, T b) {
   T k = s_floor(s_div(a, b));
   T r = s_fma(-k, b, a);
-  if (r < T(0)) r += b;
-  if (r >= b) r -= b;
+  if (b > T(0)) {
+    if (r < T(0)) r += b;
+    if (r >= b) r -= b;
+  } else {
+    if (r > T(0)) r += b;
+    if (r <= b) r -= b;
+  }
   return r;
 }
 
@@ -153,7 +159,10 @@ struct alignas(sizeof(T) * W >= 16 ? 16 : sizeof(T) * W) Pack {
 
 #define AB_PACK_LOOP for (int i = 0; i < W; i++)
 
-// --- add / sub / mul / fma: packed f32x2 for float, plain otherwise
+// --- add / sub / mul / fma: packed f32x2 for float, scalar otherwise. Always the explicitly rounded (_rn) forms: the
+// compiler then never contracts a multiply of one op with an add of the next into an FMA, so the interpreter and the
+// program-compiled straight-line kernels (codegen.py), which inline the same op bodies back to back, return identical
+// bits. Every FMA the ops want is written as fma_().
 template <int W>
 AB_DEV Pack<float, W> p_add(const Pack<float, W>& a, const Pack<float, W>& b) {
   Pack<float, W> r;
@@ -170,7 +179,7 @@ AB_DEV Pack<float, W> p_add(const Pack<float, W>& a, const Pack<float, W>& b) {
 #endif
   {
 #pragma unroll
-    AB_PACK_LOOP r.v[i] = a.v[i] + b.v[i];
+    AB_PACK_LOOP r.v[i] = __fadd_rn(a.v[i], b.v[i]);
     return r;
   }
 }
@@ -190,7 +199,7 @@ AB_DEV Pack<float, W> p_mul(const Pack<float, W>& a, const Pack<float, W>& b) {
 #endif
   {
 #pragma unroll
-    AB_PACK_LOOP r.v[i] = a.v[i] * b.v[i];
+    AB_PACK_LOOP r.v[i] = __fmul_rn(a.v[i], b.v[i]);
     return r;
   }
 }
@@ -219,14 +228,14 @@ template <int W>
 AB_DEV Pack<double, W> p_add(const Pack<double, W>& a, const Pack<double, W>& b) {
   Pack<double, W> r;
 #pragma unroll
-  AB_PACK_LOOP r.v[i] = a.v[i] + b.v[i];
+  AB_PACK_LOOP r.v[i] = __dadd_rn(a.v[i], b.v[i]);
   return r;
 }
 template <int W>
 AB_DEV Pack<double, W> p_mul(const Pack<double, W>& a, const Pack<double, W>& b) {
   Pack<double, W> r;
 #pragma unroll
-  AB_PACK_LOOP r.v[i] = a.v[i] * b.v[i];
+  AB_PACK_LOOP r.v[i] = __dmul_rn(a.v[i], b.v[i]);
   return r;
 }
 template <int W>

@@ -307,6 +307,41 @@ AB_DEV S op_extrude_end(const S& d, const S& w1) {
   return min_(max_(d, w1), T(0)) + norm2_(o0, o1);
 }
 
+// ---- post-processing value maps (post_processing.py:380-560; wrappers modifications.py:1361-1587) ---------------------------
+// args as laid out by program.py::mod_pre: (amplitude, width), (threshold), (width), (b, width), (width, b/width, ground)
+template <typename S, typename A>
+AB_DEV S pp_sigmoid(const S& v, A a) { typedef typename S::scalar T; return div_(constant_like(v, a[0]), exp_(v * (T(4) * rcp_arg(a[1]))) + T(1)); }
+template <typename S, typename A>
+AB_DEV S pp_pos_sigmoid(const S& v, A a) { typedef typename S::scalar T; return div_(constant_like(v, a[0]), exp_((v - a[1]) * (T(4) * rcp_arg(a[1]))) + T(1)); }
+template <typename S, typename A>
+AB_DEV S pp_capped_exp(const S& v, A a) { typedef typename S::scalar T; return min_(exp_(v * (T(-4) * rcp_arg(a[1]))), T(1)) * a[0]; }
+template <typename S, typename A>
+AB_DEV S pp_hard_bin(const S& v, A a) { typedef typename S::scalar T; return select_(le_(v, a[0]), constant_like(v, T(1)), constant_like(v, T(0))); }
+template <typename S, typename A>
+AB_DEV S pp_linear(const S& v, A a) { typedef typename S::scalar T; return clamp_(T(1) - v * rcp_arg(a[1]), T(0), T(1)) * a[0]; }
+template <typename S, typename A>
+AB_DEV S pp_relu(const S& v, A a) { typedef typename S::scalar T; return max_(v * rcp_arg(a[0]), T(0)); }
+template <typename S, typename A>
+AB_DEV S pp_smooth_relu(const S& v, A a) { typedef typename S::scalar T;
+  S u = v * rcp_arg(a[1]);
+  return (u + sqrt_(fma_(u, u, constant_like(u, a[0])))) * T(0.5);
+}
+template <typename S, typename A>
+AB_DEV S pp_slowstart(const S& v, A a) { typedef typename S::scalar T;
+  S u = max_(v * rcp_arg(a[0]), T(0));
+  return sqrt_(fma_(u, u, constant_like(u, a[1]))) - a[2];
+}
+template <typename S, typename A>
+AB_DEV S pp_gauss_boundary(const S& v, A a) { typedef typename S::scalar T;
+  S u = v * rcp_arg(a[1]);
+  return exp_(u * u * T(-4)) * a[0];
+}
+template <typename S, typename A>
+AB_DEV S pp_gauss_falloff(const S& v, A a) { typedef typename S::scalar T;
+  S u = max_(v, T(0)) * rcp_arg(a[1]);
+  return exp_(u * u * T(-4)) * a[0];
+}
+
 // ---- combine ops (combine.py:12-78) --------------------------------------------------------------------------------------
 template <typename S, typename U>
 AB_DEV S smin_poly2(const S& x, const S& y, const U& w) {  // combine.py:12-18

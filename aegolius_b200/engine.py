@@ -17,6 +17,7 @@ from . import cabi
 from .grid import resolution_conversion, GridSpec, detect_grid
 from .program import Program, flatten
 from . import opcodes as oc
+from . import codegen
 
 _DT = {"f32": (cabi.AB_F32, np.float32), "f64": (cabi.AB_F64, np.float64),
        "float32": (cabi.AB_F32, np.float32), "float64": (cabi.AB_F64, np.float64),
@@ -46,6 +47,25 @@ def _grad_mode(grad):
     if grad == "param":
         return cabi.AB_GRAD_PARAM, 1
     raise ValueError(f"unknown grad mode {grad!r} (use None, 'spatial' or 'param')")
+
+
+def _is_2d(spec) -> bool:
+    """The grids the kernels walk as (1, nx, ny) (make_gridk in csrc/ab_capi.cu)."""
+    return spec.res[2] == 1 and spec.res[1] > 1 and float(spec.size[2]) == 0.0
+
+
+def compile_program(obj, *, dtype="f32", grad=None, is2d=False, **opts):
+    """Blocks until the straight-line kernel for this program's structure is built (nvcc, a few seconds, cached under
+    aegolius_b200/jit/) and registered. create() / create_torch() do the same in the background on first use; this is
+    for callers who want the first evaluation to run on it already."""
+    prog = _as_program(obj)
+    code, _ = _dtype(dtype)
+    return codegen.ensure(prog, "f32" if code == cabi.AB_F32 else "f64", grad, is2d=is2d, how="sync", **opts)
+
+
+def wait_for_compilations(timeout=None):
+    """Blocks until every background kernel build started so far is registered."""
+    codegen.wait(timeout)
 
 
 def slab_ranges(n_planes: int, parts: int):
@@ -217,6 +237,9 @@ def create(obj, co, *, dtype="f32", grad=None, device=0, out=None, out_grad=None
         # path walks its octree once per warp of samples instead of once per sample
         dim = int(prog.ops[0]["a"])
         return point_cloud_sdf(spec, prog.blobs[int(prog.ops[0]["b"])][:dim], dim=dim, dtype=dtype, device=device, slab=slab)
+    # default path: the straight-line kernel compiled for this program's structure (built in the background on first
+    # use and cached on disk; the interpreter serves the calls made meanwhile — identical results either way)
+    codegen.ensure(prog, "f32" if code == cabi.AB_F32 else "f64", grad, is2d=spec is not None and _is_2d(spec))
     cp = cabi.CProgram(prog)
     lib = cabi.lib()
     if spec is not None:
@@ -262,6 +285,7 @@ def _create_staged(prog, spec, code, npdt, device):
     res3 = (C.c_uint32 * 3)(*spec.res)
     bound = [None] * len(prog.blobs)
     bufs = []
+    jdt = "f32" if code == cabi.AB_F32 else "f64"
     try:
         for st in sorted(prog.stages, key=prog.stage_op_index):
             want = tuple(resolution_conversion(int(r)) for r in st["res"] if r)
@@ -271,6 +295,7 @@ def _create_staged(prog, spec, code, npdt, device):
             d_in, d_out = _DevBuf(n * item, device), _DevBuf(n * item, device)
             bufs += [d_in, d_out]
             cp = cabi.CProgram(pre, device_blobs=bound)
+            codegen.ensure(pre, jdt, None, is2d=_is_2d(spec))
             cabi.check(lib.ab_eval_grid(cp.ref(), C.byref(g), code, cabi.AB_GRAD_NONE, d_in.ptr, None, 0, device, None))
             if st["kind"] == 0:
                 ks = (C.c_uint32 * 3)(*st["ksize"])
@@ -281,6 +306,7 @@ def _create_staged(prog, spec, code, npdt, device):
         d_res = _DevBuf(n * item, device)
         bufs.append(d_res)
         cp = cabi.CProgram(prog, device_blobs=bound)
+        codegen.ensure(prog, jdt, None, is2d=_is_2d(spec))
         cabi.check(lib.ab_eval_grid(cp.ref(), C.byref(g), code, cabi.AB_GRAD_NONE, d_res.ptr, None, 0, device, None))
         field = np.empty(n, dtype=npdt)
         d_res.download(field)
@@ -379,6 +405,7 @@ def value_and_grad(geometry, spec, target, *, dtype="f32", device=0, post=None, 
             if post is None:
                 # fused: the kernel reduces sum r^2 and sum 2 r dF/dtheta_k itself (ab_eval_grid_loss), nothing is stored
                 cp = cabi.CProgram(prog)
+                codegen.ensure(prog, "f32" if code == cabi.AB_F32 else "f64", "param", is2d=_is_2d(spec))
                 g = cabi.make_grid(spec.size, spec.res)
                 stream = torch.cuda.current_stream(dev).cuda_stream
                 cabi.check(cabi.lib().ab_eval_grid_loss(cp.ref(), C.byref(g), code, tgt.data_ptr(), accum.data_ptr(), device,
@@ -410,6 +437,7 @@ def create_torch(obj, spec: GridSpec, *, dtype="f32", grad=None, device=0, slab=
     prog = _as_program(obj)
     _auto_specialize(prog, dtype, grad)
     code, npdt = _dtype(dtype)
+    codegen.ensure(prog, "f32" if code == cabi.AB_F32 else "f64", grad, is2d=_is_2d(spec))
     tdt = torch.float32 if code == cabi.AB_F32 else torch.float64
     gmode, rows = _grad_mode(grad)
     x0, x1 = (0, spec.res[0]) if slab is None else slab

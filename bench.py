@@ -40,19 +40,24 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _traffic(n_local):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
-    (profiles/r01_c5_dual_kernel_ncu_summary.json, taken on the whole 1025^3 grid), scaled to this rank's slab."""
-    p = os.path.join(ROOT, "profiles", "r01_c5_dual_kernel_ncu_summary.json")
-    try:
-        with open(p) as fh:
-            d = json.load(fh)
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_c5_compiled_kernel_ncu_summary.json")
 
-        def gb(key):
-            v, unit = d[key].split()[:2]
-            return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
-        total = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
-        return total * n_local / 1076890625.0
+
+def _ncu_summary():
+    """Counters of the dominant kernel from the committed `ncu --set full` capture of this same command
+    (profiles/r02_c5_compiled_kernel_ncu_summary.json: one launch over the whole 1025^3 grid)."""
+    try:
+        with open(NCU_SUMMARY) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+def _traffic(n_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, scaled to this rank's slab."""
+    d = _ncu_summary()
+    try:
+        return (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])) * n_local / float(d["points"])
     except Exception:
         return None
 
@@ -192,6 +197,134 @@ def _workload_name(name, spec):
 
 
 # ---- GPU arm -----------------------------------------------------------------------------------------------------------------------
+def _time_device(fn, dev, reps=5, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b) / reps
+
+
+def _secondary(ab, engine, cabi, prog, spec, dev, local):
+    """Device-time probes beside the headline (rank 0, N = 1): the write-bound side of the roofline (shallow trees), the
+    headline tree in the reference's own precision, the interpreter the compiled kernels replace, and the other kernels of
+    the path (stencils, vector modifiers, point cloud) with their algorithmic bytes."""
+    import ctypes as C
+    import torch
+    from aegolius_b200 import workloads
+    peak_hbm, _ = _peaks()
+    lib = cabi.lib()
+    out = {}
+    sph = ab.Sphere(1.0)
+    sph.move((0.3, 0.1, -0.2))
+    n5 = spec.n_points
+    probes = [
+        ("sphere_1025^3_f32", ab.flatten(sph), ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
+        ("C1_tree_1025^3_f32", ab.flatten(ab.workloads.build_c1()), ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
+        ("C5_tree_1025^3_f32_value_only", prog, spec, "f32", None),
+        ("C5_field+gradient_1025^3_f64", prog, spec, "f64", "spatial"),
+    ]
+    for name, pg, sp, dt, gr in probes:
+        tdt = torch.float32 if dt == "f32" else torch.float64
+        es = 4 if dt == "f32" else 8
+        buf = torch.empty(sp.n_points, dtype=tdt, device=dev)
+        gb = torch.empty((3, (sp.n_points + 3) // 4 * 4), dtype=tdt, device=dev) if gr else None
+        engine.create_torch(pg, sp, dtype=dt, grad=gr, device=local, out=buf, out_grad=gb)
+        engine.wait_for_compilations()
+        h0 = lib.ab_prog_hits()
+        t = _time_device(lambda: engine.create_torch(pg, sp, dtype=dt, grad=gr, device=local, out=buf, out_grad=gb), dev)
+        bpp = es * (4 if gr else 1)
+        out[name] = {"ms": round(t, 4), "Gpts_per_s": round(sp.n_points / t / 1e6, 1),
+                     "output_GBps": round(bpp * sp.n_points / t / 1e6, 1),
+                     "hbm_frac": round(bpp * sp.n_points / t / 1e6 / peak_hbm, 4), "ops": pg.n_ops,
+                     "algorithmic_bytes_per_point": bpp,
+                     "kernel": "program-compiled" if lib.ab_prog_hits() > h0 else "interpreter"}
+        del buf, gb
+        torch.cuda.empty_cache()
+    # the interpreter on the headline step (what runs while a new structure's kernel is being built)
+    fbuf = torch.empty(n5, dtype=torch.float32, device=dev)
+    gbuf = torch.empty((3, (n5 + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    old = lib.ab_prog_enable(0)
+    try:
+        t = _time_device(lambda: engine.create_torch(prog, spec, dtype="f32", grad="spatial", device=local, out=fbuf,
+                                                     out_grad=gbuf), dev, reps=3, warm=2)
+    finally:
+        lib.ab_prog_enable(old)
+    out["C5_field+gradient_interpreter_fallback"] = {"ms": round(t, 4), "Gpts_per_s": round(n5 / t / 1e6, 1),
+                                                     "hbm_frac": round(16 * n5 / t / 1e6 / peak_hbm, 4),
+                                                     "note": "ab_prog_enable(0): the general interpreter tiers"}
+    del fbuf, gbuf
+    torch.cuda.empty_cache()
+    # whole-field kernels on a 513^3 fp32 field (SURVEY §8f N3 / N4, a9), algorithmic bytes per point in the key
+    res = (513, 513, 513)
+    n = res[0] * res[1] * res[2]
+    stride = (n + 3) // 4 * 4
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    f = torch.randn(n, dtype=torch.float32, device=dev)
+    o = torch.empty(n, dtype=torch.float32, device=dev)
+    v = torch.randn(3, stride, dtype=torch.float32, device=dev)
+    ang = torch.randn(n, dtype=torch.float32, device=dev)
+    r3 = (C.c_uint32 * 3)(*res)
+    k3 = (C.c_uint32 * 3)(5, 5, 1)
+    g = cabi.make_grid((0.0, 0.0, 0.0), res)
+    ops = (cabi.ab_vec_op * 2)()
+    ops[0].opcode, ops[0].kind0, ops[0].a0 = cabi.AB_VOP_ROT_Z, cabi.AB_VK_ARRAY, ang.data_ptr()
+    ops[1].opcode, ops[1].kind0, ops[1].kind1, ops[1].a1 = cabi.AB_VOP_ROT_AXIS, cabi.AB_VK_VEC3, cabi.AB_VK_ARRAY, ang.data_ptr()
+    ops[1].c = (C.c_double * 3)(1.0, 0.0, 0.0)
+    jobs = {
+        "from_sdf_513^3_f32": (lambda: cabi.check(lib.ab_fd_gradient(f.data_ptr(), 0, C.byref(g), 3, cabi.AB_F32, 1, v.data_ptr(), stride, local, st)), 16),
+        "box_filter_5x5x1_513^3_f32": (lambda: cabi.check(lib.ab_box_filter(f.data_ptr(), r3, k3, 1, cabi.AB_F32, o.data_ptr(), local, st)), 16),
+        "edge_filter_513^3_f32": (lambda: cabi.check(lib.ab_edge_filter(f.data_ptr(), r3, cabi.AB_F32, o.data_ptr(), local, st)), 8),
+        "vec_rotate_z+rotate_axis_513^3_f32": (lambda: cabi.check(lib.ab_vec_apply(v.data_ptr(), stride, n, ops, 2, cabi.AB_F32, local, st)), 32),
+        "vec_component_phi_513^3_f32": (lambda: cabi.check(lib.ab_vec_component(v.data_ptr(), stride, n, cabi.AB_VC_PHI, cabi.AB_F32, o.data_ptr(), local, st)), 12),
+    }
+    for jn, (fn, bpp) in jobs.items():
+        t = _time_device(fn, dev)
+        out[jn] = {"ms": round(t, 4), "algorithmic_bytes_per_point": bpp, "GBps": round(bpp * n / t / 1e6, 1),
+                   "hbm_frac": round(bpp * n / t / 1e6 / peak_hbm, 4)}
+    del f, o, v, ang
+    torch.cuda.empty_cache()
+    # point cloud -> unsigned distance: C4 through the exact octree walk (incl. the tree build), and the tiled brute-force
+    # kernel on 65^3 queries x 1 M points (unit of work = one (query, cloud point) pair, SURVEY §8d)
+    cloud = workloads.c4_cloud()
+    m = cloud.shape[1]
+    d_cloud = C.c_void_p()
+    cabi.check(lib.ab_cloud_upload(cloud.ctypes.data, m, 3, m, cabi.AB_F32, local, C.byref(d_cloud)))
+    c4 = ab.GridSpec(workloads.CONFIGS["C4"]["size"], workloads.CONFIGS["C4"]["res"])
+    buf = torch.empty(c4.n_points, dtype=torch.float32, device=dev)
+    g4 = cabi.make_grid(c4.size, c4.res)
+    l0 = cabi.launch_count()
+    cabi.check(lib.ab_nn_grid(d_cloud, m, 3, C.byref(g4), cabi.AB_F32, buf.data_ptr(), local, st))
+    per_call = cabi.launch_count() - l0
+    t = _time_device(lambda: cabi.check(lib.ab_nn_grid(d_cloud, m, 3, C.byref(g4), cabi.AB_F32, buf.data_ptr(), local, st)), dev)
+    out["C4_cloud_1M_points_257^3_f32_octree"] = {"ms": round(t, 4), "Mqueries_per_s": round(c4.n_points / t / 1e3, 1),
+                                                 "launches_per_call": per_call,
+                                                 "note": "exact nearest neighbour, octree packet walk incl. the tree build"}
+    small = ab.GridSpec(c4.size, (64, 64, 64))
+    gs = cabi.make_grid(small.size, small.res)
+    os.environ["AB_NN_ALGO"] = "brute"
+    try:
+        t = _time_device(lambda: cabi.check(lib.ab_nn_grid(d_cloud, m, 3, C.byref(gs), cabi.AB_F32, buf.data_ptr(), local, st)),
+                         dev, reps=3, warm=1)
+    finally:
+        del os.environ["AB_NN_ALGO"]
+    pairs = small.n_points * m
+    out["brute_force_nn_65^3_x_1M_f32"] = {"ms": round(t, 3), "Tpairs_per_s": round(pairs / t / 1e9, 3),
+                                          "fma_pipe_ceiling_Tpairs_per_s": 6.2,
+                                          "frac_of_ceiling": round(pairs / t / 1e9 / 6.2, 3),
+                                          "note": "ab_nn_kernel_f32x2; ceiling = 148 SMs x 128 lanes x 1.965 GHz / 6 FMA-pipe cycles per pair"}
+    lib.ab_device_free(d_cloud, local)
+    del buf
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -225,18 +358,23 @@ def run_gpu(args):
     stride = (n_local + 3) // 4 * 4
     field = torch.empty(n_local, dtype=torch.float32, device=dev)
     grad = torch.empty((3, stride), dtype=torch.float32, device=dev)
+    lib = cabi.lib()
 
     def step():
         engine.create_torch(prog, spec, dtype="f32", grad="spatial", device=local, slab=(x0, x1), out=field,
                             out_grad=grad)
 
+    # the default path: the first evaluation of a program structure finds its straight-line kernel in aegolius_b200/jit/
+    # (or starts the build and runs on the interpreter meanwhile). Warm-up ends when that kernel is registered.
+    step()
+    engine.wait_for_compilations()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = cabi.launch_count()
+    l0, h0 = cabi.launch_count(), lib.ab_prog_hits()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -246,142 +384,96 @@ def run_gpu(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = cabi.launch_count() - l0
+    compiled_launches = lib.ab_prog_hits() - h0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(launches), float(compiled_launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, launches = float(tmax[0]), int(tsum[1])
+        ms, launches, compiled_launches = float(tmax[0]), int(tsum[1]), int(tsum[2])
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
-    # ---- e2e: public API, host buffers, D2H inside the timed region ----
+    # ---- e2e: public API, host buffers, D2H inside the timed region, every step ----
     numa_cpus = None if os.environ.get("AB_NO_NUMA_BIND") else engine.bind_to_device_numa(local)
     pf = engine.PinnedArray((n_local,), np.float32)
     pg = engine.PinnedArray((3, n_local), np.float32)
-    e2e_steps = max(1, min(args.steps, 3))
     ab.create(obj, spec, dtype="f32", grad="spatial", device=local, slab=(x0, x1), out=pf.array, out_grad=pg.array)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(args.steps):
         ab.create(obj, spec, dtype="f32", grad="spatial", device=local, slab=(x0, x1), out=pf.array,
                   out_grad=pg.array)
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = (time.perf_counter() - t0) / args.steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
-    checksum = float(pf.array[::4097].astype(np.float64).sum())
+    # GLOBAL checksum, identical for every N: the fp32 bit patterns of every 4097th grid point (global index) and of its
+    # three gradient components, summed as integers (exact and order-independent), all-reduced over the ranks
+    g0 = x0 * spec.res[1] * spec.res[2]
+    first = (-g0) % 4097
+    bits = int(pf.array[first::4097].view(np.int32).astype(np.int64).sum())
+    bits += int(pg.array[:, first::4097].view(np.int32).astype(np.int64).sum())
+    fsum = float(pf.array[first::4097].astype(np.float64).sum())
+    cb = torch.tensor([bits % (1 << 52)], dtype=torch.int64, device=dev)
+    cs = torch.tensor([fsum], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cb, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+    checksum = {"bits_mod_2^52": int(cb[0]) % (1 << 52), "field_sum": round(float(cs[0]), 6),
+                "what": "every 4097th grid point (global index): integer sum of the fp32 bit patterns of field + gradient, "
+                        "and the fp64 sum of the field values; all-reduced, so every N prints the same numbers"}
     pf.free()
     pg.free()
 
-    # ---- secondary device-time probes (rank 0, N=1 only): the shallow-tree side of the roofline ----
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
-        secondary = {}
-        sph = ab.Sphere(1.0)
-        sph.move((0.3, 0.1, -0.2))
-        probes = {"sphere_1025^3_f32": (ab.flatten(sph), ab.GridSpec((4, 4, 4), (1024,) * 3), None),
-                  "C1_tree_1025^3_f32": (ab.flatten(ab.workloads.build_c1()), ab.GridSpec((4, 4, 4), (1024,) * 3), None),
-                  "C5_tree_1025^3_f32_value_only": (prog, spec, None)}
-        peak_hbm, _ = _peaks()
-        for name, (pg, sp, gr) in probes.items():
-            buf = torch.empty(sp.n_points, dtype=torch.float32, device=dev)
-            for _ in range(3):
-                engine.create_torch(pg, sp, dtype="f32", grad=gr, device=local, out=buf)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(dev)
-            a.record()
-            for _ in range(5):
-                engine.create_torch(pg, sp, dtype="f32", grad=gr, device=local, out=buf)
-            b.record()
-            torch.cuda.synchronize(dev)
-            t = a.elapsed_time(b) / 5
-            secondary[name] = {"ms": round(t, 4), "Gpts_per_s": round(sp.n_points / t / 1e6, 1),
-                               "output_GBps": round(4 * sp.n_points / t / 1e6, 1),
-                               "hbm_frac": round(4 * sp.n_points / t / 1e6 / peak_hbm, 4), "ops": pg.n_ops}
-            del buf
-        # the same C5 step on a program-specialised build of the interpreter (engine.specialize: only this program's ops
-        # are compiled in; identical results). Reported beside the headline, which stays on the ahead-of-time kernels.
-        try:
-            path = engine.specialize(prog, dtype="f32", grad="spatial")
-            if path:
-                fbuf = torch.empty(spec.n_points, dtype=torch.float32, device=dev)
-                gbuf2 = torch.empty((3, (spec.n_points + 3) // 4 * 4), dtype=torch.float32, device=dev)
-                for _ in range(3):
-                    engine.create_torch(prog, spec, dtype="f32", grad="spatial", device=local, out=fbuf, out_grad=gbuf2)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize(dev)
-                a.record()
-                for _ in range(5):
-                    engine.create_torch(prog, spec, dtype="f32", grad="spatial", device=local, out=fbuf, out_grad=gbuf2)
-                b.record()
-                torch.cuda.synchronize(dev)
-                t = a.elapsed_time(b) / 5
-                secondary["C5_field+gradient_specialised_kernel"] = {
-                    "ms": round(t, 4), "Gpts_per_s": round(spec.n_points / t / 1e6, 1),
-                    "hbm_frac": round(16 * spec.n_points / t / 1e6 / peak_hbm, 4),
-                    "note": "opt-in aegolius_b200.specialize(obj); compiled (about 10 s, cached) outside any timed region"}
-                del fbuf, gbuf2
-            cabi_mod = __import__("aegolius_b200.cabi", fromlist=["lib"])
-            cabi_mod.lib().ab_spec_clear()
-        except Exception as exc:  # no nvcc on this host: the probe is skipped, nothing else depends on it
-            secondary["C5_field+gradient_specialised_kernel"] = {"skipped": str(exc)[:200]}
-        # C4: point cloud -> unsigned distance (exact octree nearest neighbour), device time of ab_nn_grid incl. tree build
-        import ctypes as C
-        from aegolius_b200 import cabi, workloads
-        cloud = workloads.c4_cloud()
-        c4 = ab.GridSpec(workloads.CONFIGS["C4"]["size"], workloads.CONFIGS["C4"]["res"])
-        lib, d_cloud = cabi.lib(), C.c_void_p()
-        cabi.check(lib.ab_cloud_upload(cloud.ctypes.data, cloud.shape[1], 3, cloud.shape[1], cabi.AB_F32, local, C.byref(d_cloud)))
-        buf = torch.empty(c4.n_points, dtype=torch.float32, device=dev)
-        g = cabi.make_grid(c4.size, c4.res)
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        l0 = cabi.launch_count()
-        for _ in range(2):
-            cabi.check(lib.ab_nn_grid(d_cloud, cloud.shape[1], 3, C.byref(g), cabi.AB_F32, buf.data_ptr(), local, st))
-        per_call = (cabi.launch_count() - l0) // 2
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(dev)
-        a.record()
-        for _ in range(5):
-            cabi.check(lib.ab_nn_grid(d_cloud, cloud.shape[1], 3, C.byref(g), cabi.AB_F32, buf.data_ptr(), local, st))
-        b.record()
-        torch.cuda.synchronize(dev)
-        t = a.elapsed_time(b) / 5
-        secondary["C4_cloud_1M_points_257^3_f32"] = {"ms": round(t, 4), "Mqueries_per_s": round(c4.n_points / t / 1e3, 1),
-                                                    "launches_per_call": per_call,
-                                                    "equivalent_Tpairs_per_s": round(c4.n_points * cloud.shape[1] / t / 1e9, 1)}
-        lib.ab_device_free(d_cloud, local)
-        del buf
-        torch.cuda.empty_cache()
+        secondary = _secondary(ab, engine, cabi, prog, spec, dev, local)
 
     if rank == 0:
         peak, peak_src = _peaks()
         alg_bytes = 16.0 * n_local  # 4 B field + 12 B gradient written per point, 0 B read (grid mode)
-        kern_ms = ms_per_step  # one interpreter launch per step per rank
+        kern_ms = ms_per_step  # one kernel launch per step per rank
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        ncu = _ncu_summary()
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        f_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        issue = None
+        if ncu and "smsp__inst_executed.sum" in ncu:
+            wi_per_pt = float(ncu["smsp__inst_executed.sum"]) / float(ncu["points"])
+            ach = wi_per_pt * n_local / (kern_ms * 1e-3)
+            pk = sms * 4 * f_mhz * 1e6
+            issue = {"warp_inst_per_point": wi_per_pt, "thread_inst_per_point": wi_per_pt * 32,
+                     "achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": pk, "frac": ach / pk,
+                     "peak": f"{sms} SMs x 4 schedulers x {f_mhz:.0f} MHz (sampled under load)",
+                     "source": os.path.relpath(NCU_SUMMARY, ROOT) + " (smsp__inst_executed.sum of the same kernel, one launch)"}
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": max(args.warmup, 3) + 1, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": _workload_name(args.workload, spec), "points": n_total,
                        "slab_planes_rank0": x1 - x0, "program_ops": prog.n_ops, "program_bytes": prog.nbytes(),
-                       "l2": "outputs (16 B/point, >= 2 GB per rank) far exceed the 126 MB L2; no inputs are read"},
+                       "l2": "outputs (16 B/point, >= 2 GB per rank) far exceed the 126 MB L2; no inputs are read",
+                       "kernel_path": "default: program-compiled straight-line kernel (aegolius_b200/codegen.py), built "
+                                      "ahead of time by __graft_entry__.build() / on first use, cached by structure"},
             "clocks": clocks,
             "e2e": {"value": n_total / e2e_s, "unit": "points/s", "h2d_bytes_per_step": prog.nbytes(),
-                    "d2h_bytes_per_step": 16 * n_local, "ms_per_step": e2e_s * 1e3,
+                    "d2h_bytes_per_step": 16 * n_local, "ms_per_step": e2e_s * 1e3, "steps": args.steps,
                     "note": "aegolius_b200.create(obj, grid, grad='spatial') into pinned host arrays (per rank)",
                     "numa_bound_cpus": len(numa_cpus) if numa_cpus else 0},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "gpu_launches": launches, "compiled_kernel_launches": compiled_launches,
+            "roofline": {"bound": "fp32-issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(n_local), "peak_source": peak_src,
-                         "kernel": "ab_interp_kernel<Dual<Pack<float,2>,3>,float>", "algorithmic_bytes_per_point": 16,
-                         "note": "deep tree: FP32-issue-bound, not HBM-bound (SURVEY §8d); 'secondary' holds the shallow-tree "
-                                 "probes that are write-bound; traffic: ncu capture in profiles/ scaled to this slab"},
+                         "kernel": "ab_prog_kernel (program-compiled, Dual<Pack<float,2>,3>)" if compiled_launches else
+                                   "ab_interp_kernel<Dual<Pack<float,2>,3>,float>",
+                         "algorithmic_bytes_per_point": 16, "issue": issue,
+                         "note": "deep tree: FP32-issue-bound, not HBM-bound (SURVEY §8d). achieved/peak/frac = algorithmic "
+                                 "output bytes against the measured HBM copy peak; `issue` = executed warp instructions "
+                                 "against the issue ceiling (what binds); 'secondary' holds the write-bound shallow trees"},
             "checksum": checksum,
         }
         if secondary:

@@ -205,6 +205,23 @@ int ab_spec_clear(void);
 int ab_op_tier(int opcode);
 uint64_t ab_spec_hits(void);
 
+/* Program-compiled kernels (aegolius_b200/codegen.py): ONE straight-line kernel per program structure, generated from
+ * the flattened op list (the evaluation order of geom.py:29-60 / modifications.py:88-98 / combine.py:115-163 unrolled
+ * on the host), built by nvcc into its own shared object and registered here. `signature[i]` = opcode | a << 16 |
+ * b << 24 of op i, for the n_sig ops before the terminator; `flavor` 1 = the binary serves 2D grids, 0 = 3D grids and
+ * point lists; `launch_fn` has the ab_spec_launch contract. Arguments still travel with every launch, so one binary
+ * serves every parameter value. ab_eval_* prefer a registered program over the interpreter tiers; results are
+ * bit-identical. ab_prog_enable(0) makes them ignore the registry (returns the previous setting). */
+int ab_prog_register(const uint32_t* signature, uint32_t n_sig, int dtype, int grad_mode, int flavor, void* launch_fn,
+                     uint64_t kparams_size);
+int ab_prog_clear(void);
+uint64_t ab_prog_hits(void);
+int ab_prog_enable(int on);
+uint64_t ab_prog_signature_hash(const uint32_t* signature, uint32_t n_sig, int dtype, int grad_mode);
+/* Host-only: offset of every op's arguments in the pool the kernels see (one entry per op before the terminator; fixed-size
+ * ops first, tables last, each on a 4-scalar boundary) and the pool length. What a program-compiled kernel hard-codes. */
+int ab_prog_arg_layout(const ab_program* prog, uint32_t* offsets_out, uint32_t* n_args_out);
+
 /* Host-buffer variants (what the Python drop-in calls when the user wants a NumPy array back): allocate/reuse
  * device scratch, run, copy the result to `out_host` (pinned or pageable), synchronise. */
 int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out_host,

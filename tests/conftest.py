@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+# Kernel builds in tests: by default only binaries already in aegolius_b200/jit/ are used (python tools/prebuild_jit.py,
+# run by __graft_entry__.build()), nvcc is never started behind a test's back. tests/test_gpu_jit.py switches modes itself.
+os.environ.setdefault("AB_JIT", "cache")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "reference: needs the SPOMSO sources under /root/reference (build container only)")

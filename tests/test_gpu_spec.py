@@ -10,6 +10,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _interpreter_only():
+    """These tests are about the interpreter builds: keep the program-compiled kernels (the default path) out of the way."""
+    from aegolius_b200 import cabi
+    old = cabi.lib().ab_prog_enable(0)
+    yield
+    cabi.lib().ab_prog_enable(old)
+
+
 @pytest.mark.skipif(shutil.which("nvcc") is None and not __import__("os").path.exists("/usr/local/cuda/bin/nvcc"),
                     reason="needs nvcc at run time")
 def test_specialised_kernel_is_bit_identical_and_selected_by_coverage():
