@@ -17,7 +17,7 @@ from . import codegen  # noqa: F401
 def __getattr__(name):
     # engine (ctypes + CUDA library) is imported lazily so that flattening works without the built library
     if name in ("create", "create_with_gradient", "patch", "unpatch", "from_sdf", "VectorFieldFromSDF",
-                "point_cloud_sdf", "conv_averaging", "conv_edge_detection", "specialize", "set_auto_specialize", "compile_program", "wait_for_compilations", "wait_for_specializations", "engine", "create_torch", "jacfwd", "value_and_grad", "program_tangent", "library_path", "PinnedArray", "slab_ranges"):
+                "point_cloud_sdf", "conv_averaging", "conv_edge_detection", "specialize", "set_auto_specialize", "compile_program", "wait_for_compilations", "from_sdf_torch", "cloud_records", "point_cloud_sdf_torch", "grid_min_step", "wait_for_specializations", "engine", "create_torch", "jacfwd", "value_and_grad", "program_tangent", "library_path", "PinnedArray", "slab_ranges"):
         import importlib
         engine = importlib.import_module(__name__ + ".engine")
         return engine if name == "engine" else getattr(engine, name)

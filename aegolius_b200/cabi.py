@@ -66,6 +66,8 @@ _SIGNATURES = {
     "ab_device_count": (C.c_int, []),
     "ab_eval_grid": (C.c_int, [C.POINTER(ab_program), C.POINTER(ab_grid), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_uint64, C.c_int, C.c_void_p]),
+    "ab_eval_grid_multicast": (C.c_int, [C.POINTER(ab_program), C.POINTER(ab_grid), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_uint64, C.c_int, C.c_void_p]),
     "ab_eval_points": (C.c_int, [C.POINTER(ab_program), C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "ab_eval_grid_loss": (C.c_int, [C.POINTER(ab_program), C.POINTER(ab_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int,
@@ -95,6 +97,7 @@ _SIGNATURES = {
     "ab_box_filter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_int,
                                 C.c_void_p, C.c_int, C.c_void_p]),
     "ab_edge_filter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "ab_signed_field": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ab_vec_apply": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ab_vec_op), C.c_uint32, C.c_int, C.c_int,
                                C.c_void_p]),
     "ab_vec_component": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int,
@@ -102,6 +105,7 @@ _SIGNATURES = {
     "ab_device_alloc": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "ab_device_free": (C.c_int, [C.c_void_p, C.c_int]),
     "ab_host_alloc_pinned": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "ab_host_alloc_pinned_flags": (C.c_int, [C.c_uint64, C.c_uint, C.POINTER(C.c_void_p)]),
     "ab_host_free_pinned": (C.c_int, [C.c_void_p]),
     "ab_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "ab_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),

@@ -373,7 +373,7 @@ AB_PROG_EXPORT int ab_prog_launch(const void* kparams, int sms, unsigned long lo
 }
 AB_PROG_EXPORT unsigned long long ab_prog_kparams_size(void) { return sizeof(ab::KParams<ab::ProgT>); }
 AB_PROG_EXPORT int ab_prog_kind(void) { return @KIND@; }
-AB_PROG_EXPORT int ab_prog_flavor(void) { return @IS2D@; }
+AB_PROG_EXPORT int ab_prog_flavor(void) { return @FLAVOR@; }
 AB_PROG_EXPORT unsigned long long ab_prog_hash(void) { return @HASH@ull; }
 '''
 
@@ -385,9 +385,11 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
         raise ValueError("empty program")
     grad = grad or "none"
     kind, T, K, param = KINDS[(dtype, grad)]
-    o = default_options(sig, dtype, grad)
-    o.update(slots="reg", nt=128, is2d=0, store=0, stage8=False)
+    o = dict(slots="reg", nt=128, is2d=0, store=0, stage8=False, multicast=False)
+    o.update(default_options(sig, dtype, grad))
     o.update({k: v for k, v in opts.items() if v is not None})
+    if o["multicast"]:
+        o["store"] = 4  # multimem.st: `out` is a multicast address (ab_eval_grid_multicast)
     W = int(o["width"])
     if (T, W) not in (("float", 1), ("float", 2), ("float", 4), ("float", 8), ("double", 1), ("double", 2)):
         raise ValueError(f"no {W}-wide store for {T}")
@@ -409,6 +411,7 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
            "T": T, "S": S, "PARAM": "true" if param else "false", "NT": int(o["nt"]),
            "TABLES": "true" if em.tables else "false", "NP": em.n_p if o["slots"] == "smem" else 0,
            "NV": em.n_v if o["slots"] == "smem" else 0, "MINCTAS": int(o["min_ctas"]), "IS2D": int(bool(o["is2d"])), "STOREPOLICY": int(o["store"]),
+           "FLAVOR": int(bool(o["is2d"])) | (2 if o["multicast"] else 0),
            "STAGE8": "true" if (o["stage8"] and W == 8 and K == 0 and T == "float") else "false", "DECLS": "\n".join(decls),
            "BODY": "\n".join(em.lines), "KIND": kind}
     if rep["STAGE8"] == "true":
@@ -437,14 +440,27 @@ _INCLUDED = (os.path.join(CSRC, "ab_interp.cuh"), os.path.join(CSRC, "ab_ops.cuh
              os.path.join(os.path.dirname(HERE), "include", "aegolius_b200.h"))
 
 
+def _abi_relevant(text: str) -> str:
+    """The public header without comments and without function prototypes: what is left (limits, enums, structs) is all a
+    generated kernel depends on, so documenting or adding an entry point does not invalidate the cached binaries."""
+    import re
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    text = re.sub(r"\b(?:int|uint64_t|const\s+char\s*\*)\s+ab_\w+\s*\([^;{]*\)\s*;", " ", text)
+    return " ".join(text.split())
+
+
 def _headers_digest():
     global _header_digest
     if _header_digest is None:
         h = hashlib.sha256()
         for f in _INCLUDED:
             with open(f, "rb") as fh:
-                h.update(os.path.basename(f).encode())
-                h.update(fh.read())
+                data = fh.read()
+            if f.endswith("aegolius_b200.h"):
+                data = _abi_relevant(data.decode()).encode()
+            h.update(os.path.basename(f).encode())
+            h.update(data)
         _header_digest = h.hexdigest()
     return _header_digest
 
@@ -509,11 +525,11 @@ def set_mode(m: str):
     os.environ["AB_JIT"] = m
 
 
-def _key(sig, dtype, grad, is2d):
-    return (np.asarray(sig, dtype=np.uint32).tobytes(), dtype, grad, int(bool(is2d)))
+def _key(sig, dtype, grad, flavor):
+    return (np.asarray(sig, dtype=np.uint32).tobytes(), dtype, grad, int(flavor))
 
 
-def _register(path, sig, dtype, grad, is2d):
+def _register(path, sig, dtype, grad, is2d):  # is2d: the flavour bits (bit 0 2D grid, bit 1 multicast stores)
     import ctypes as C
     from . import cabi
     from .engine import _DT
@@ -523,19 +539,22 @@ def _register(path, sig, dtype, grad, is2d):
         lib.ab_prog_kparams_size.restype = C.c_uint64
         _loaded[path] = lib
     kind = KINDS[(dtype, grad)][0]
-    if lib.ab_prog_kind() != kind or lib.ab_prog_flavor() != int(bool(is2d)):
+    if lib.ab_prog_kind() != kind or lib.ab_prog_flavor() != int(is2d):
         raise RuntimeError(f"{path}: built for another kind / flavour")
     sig = np.ascontiguousarray(sig, dtype=np.uint32)
     gcode = {"none": cabi.AB_GRAD_NONE, "spatial": cabi.AB_GRAD_SPATIAL, "param": cabi.AB_GRAD_PARAM}[grad]
-    cabi.check(cabi.lib().ab_prog_register(sig.ctypes.data, len(sig), _DT[dtype][0], gcode, int(bool(is2d)),
+    cabi.check(cabi.lib().ab_prog_register(sig.ctypes.data, len(sig), _DT[dtype][0], gcode, int(is2d),
                                            C.cast(lib.ab_prog_launch, C.c_void_p), lib.ab_prog_kparams_size()))
 
 
 def compilable(prog) -> bool:
-    return 0 < len(signature(prog)) <= MAX_COMPILED_OPS
+    """Short enough to unroll, and made of ops this generator knows (anything else is the library's to reject)."""
+    sig = signature(prog)
+    return 0 < len(sig) <= MAX_COMPILED_OPS and all((int(w) & 0xffff) in oc.ARG_COUNT and (int(w) & 0xffff) != oc.END
+                                                    for w in sig)
 
 
-def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, **opts):
+def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, multicast=False, **opts):
     """Makes the compiled kernel of `prog`'s structure available to the library. Returns True when it is registered on
     return, False when the interpreter serves this call (build in flight, disabled, too long a program, failed build).
     how: None = mode(); 'sync' blocks on the build."""
@@ -546,6 +565,9 @@ def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, **opts):
         ("f32" if np.dtype(dtype) == np.float32 else "f64")
     grad = _GRAD_NAMES[grad]
     sig = signature(prog)
+    is2d = int(bool(is2d)) | (2 if multicast else 0)  # from here on: the flavour bits
+    if multicast:
+        opts = dict(opts, multicast=True)
     key = _key(sig, dtype, grad, is2d)
     if key in _registered:
         return True
@@ -556,7 +578,7 @@ def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, **opts):
             return True
         th = _pending.get(key)
         if th is None:
-            src = generate(sig, dtype, grad, is2d=is2d, **opts)
+            src = generate(sig, dtype, grad, is2d=is2d & 1, **opts)
             path = binary_path(src)
             if os.path.exists(path):  # built earlier (this process, another one, or shipped with the tree): just load it
                 _register(path, sig, dtype, grad, is2d)

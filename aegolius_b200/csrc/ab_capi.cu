@@ -297,6 +297,7 @@ struct EvalTarget {
   uint64_t grad_stride;
   const T* target;     // loss mode (ab_eval_grid_loss): no per-point outputs
   double* loss_accum;
+  int multicast;       // out / grad are multicast addresses: only a program-compiled kernel built for multimem.st may run
 };
 
 template <typename S, typename T>
@@ -390,7 +391,8 @@ static int dispatch_spec(ab_spec_fn fn, const KParams<T>& kp, int device, cudaSt
 // object exports a launcher with the signature of ab_spec_fn; it is registered here under the structure's signature and
 // run_program prefers it over the interpreter tiers. Same op bodies, same arithmetic: results are bit-identical.
 struct ProgEntry {
-  int dtype, grad_mode;  // grad_mode | flavor << 8 (flavor 1: the binary serves 2D grids, 0: 3D grids and point lists)
+  int dtype, grad_mode;  // grad_mode | flavor << 8; flavor bit 0: the binary serves 2D grids (else 3D grids and point lists),
+                         // bit 1: it stores through multimem.st (outputs are multicast addresses, ab_eval_grid_multicast)
   std::vector<uint32_t> sig;
   ab_spec_fn fn;
 };
@@ -421,7 +423,7 @@ extern "C" int ab_prog_register(const uint32_t* signature, uint32_t n_sig, int d
   if (!signature || n_sig == 0 || n_sig > AB_MAX_OPS || !launch_fn) return fail(AB_EINVAL, "bad compiled-program descriptor");
   if (dtype != AB_F32 && dtype != AB_F64) return fail(AB_EINVAL, "bad dtype %d", dtype);
   if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL && grad_mode != AB_GRAD_PARAM) return fail(AB_EINVAL, "bad grad_mode %d", grad_mode);
-  if (flavor != 0 && flavor != 1) return fail(AB_EINVAL, "bad flavor %d", flavor);
+  if (flavor < 0 || flavor > 3) return fail(AB_EINVAL, "bad flavor %d", flavor);
   grad_mode |= flavor << 8;
   const uint64_t want = dtype == AB_F32 ? sizeof(KParams<float>) : sizeof(KParams<double>);
   if (kparams_size != want) return fail(AB_EINVAL, "compiled program built against another library version (KParams %llu != %llu bytes)", (unsigned long long)kparams_size, (unsigned long long)want);
@@ -630,7 +632,11 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   }
 
   // a registered program-specialised kernel that covers every op of this program takes precedence over the tiers
-  const ab_spec_fn compiled = find_prog(prog, kp.n_ops, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode, (tg.grid_mode && tg.g.is2d) ? 1 : 0);
+  const ab_spec_fn compiled = find_prog(prog, kp.n_ops, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode,
+                                           ((tg.grid_mode && tg.g.is2d) ? 1 : 0) | (tg.multicast ? 2 : 0));
+  if (tg.multicast && !compiled)
+    return fail(AB_EUNSUPPORTED_OP, "no multicast-store kernel is registered for this program structure (build it with "
+                "aegolius_b200.codegen.ensure(..., multicast=True)); the interpreter tiers store to one GPU only");
   const ab_spec_fn spec = compiled ? nullptr : find_spec(prog, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode);
   constexpr int WV = sizeof(T) == 4 ? 4 : 2;  // one 128-bit store per thread
   constexpr int WG = sizeof(T) == 4 ? 2 : 1;  // dual numbers carry 4x the state: halve the points per thread
@@ -689,8 +695,9 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
 
 template <typename T>
 static int eval_grid_t(const ab_program* prog, const ab_grid* grid, int grad_mode, void* out, void* out_grad,
-                       uint64_t grad_stride, int device, cudaStream_t st) {
+                       uint64_t grad_stride, int device, cudaStream_t st, int multicast = 0) {
   EvalTarget<T> tg{};
+  tg.multicast = multicast;
   int rc = make_gridk(grid, tg.g, &tg.n);
   if (rc) return rc;
   tg.grid_mode = 1;
@@ -729,6 +736,16 @@ extern "C" int ab_eval_grid(const ab_program* prog, const ab_grid* grid, int dty
   if (rc) return rc;
   if (dtype == AB_F32) return eval_grid_t<float>(prog, grid, grad_mode, out, out_grad, grad_stride, device, (cudaStream_t)stream);
   if (dtype == AB_F64) return eval_grid_t<double>(prog, grid, grad_mode, out, out_grad, grad_stride, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
+extern "C" int ab_eval_grid_multicast(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out_mc,
+                                      void* out_grad_mc, uint64_t grad_stride, int device, void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (grad_mode == AB_GRAD_PARAM) return fail(AB_EINVAL, "ab_eval_grid_multicast: AB_GRAD_NONE or AB_GRAD_SPATIAL");
+  if (dtype == AB_F32) return eval_grid_t<float>(prog, grid, grad_mode, out_mc, out_grad_mc, grad_stride, device, (cudaStream_t)stream, 1);
+  if (dtype == AB_F64) return eval_grid_t<double>(prog, grid, grad_mode, out_mc, out_grad_mc, grad_stride, device, (cudaStream_t)stream, 1);
   return fail(AB_EINVAL, "bad dtype %d", dtype);
 }
 
@@ -844,29 +861,61 @@ extern "C" int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, in
     d_out[b] = (char*)base + b * per_buf;
     d_grad[b] = rows ? (char*)d_out[b] + (size_t)dstride * es : nullptr;
   }
+  // host blobs (point clouds) go to the device ONCE, before the chunk loop: per chunk they would be re-staged and re-uploaded
+  // with a blocking copy, which serialises the compute / copy pipeline
+  ab_program dprog = *prog;
+  std::vector<ab_blob> dblobs(prog->blobs ? prog->blobs : nullptr, prog->blobs ? prog->blobs + prog->n_blobs : nullptr);
+  std::vector<void*> uploaded;
+  auto release = [&]() {
+    for (void* d : uploaded) cudaFree(d);
+  };
+  for (uint32_t b = 0; b < prog->n_blobs && prog->blobs; b++) {
+    ab_blob& bl = dblobs[b];
+    if (bl.on_device || bl.dim == 1 || !bl.data || bl.count == 0 || bl.count > 0xffffffffull) continue;
+    void* d = nullptr;
+    rc = dtype == AB_F64 ? upload_cloud<double>((const double*)bl.data, bl.count, 3, bl.count, 0, &d, false)
+                         : upload_cloud<float>((const double*)bl.data, bl.count, 3, bl.count, 0, &d, false);
+    if (rc) {
+      release();
+      return rc;
+    }
+    uploaded.push_back(d);
+    bl.data = d;
+    bl.on_device = 1;
+  }
+  if (!dblobs.empty()) dprog.blobs = dblobs.data();
   uint64_t done_planes = 0;
   int c = 0;
-  while (done_planes < total_planes) {
+  rc = AB_OK;
+  cudaError_t ce = cudaSuccess;
+  while (done_planes < total_planes && rc == AB_OK && ce == cudaSuccess) {
     const uint64_t np = (total_planes - done_planes < planes_per_chunk) ? total_planes - done_planes : planes_per_chunk;
     const uint64_t pts = np * plane, off = done_planes * plane;
     const int b = c & 1;
     ab_grid sub = *grid;
     sub.slab_begin = grid->slab_begin + (uint32_t)done_planes;
     sub.slab_end = sub.slab_begin + (uint32_t)np;
-    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(pp->comp, pp->freed[b], 0));
-    rc = ab_eval_grid(prog, &sub, dtype, grad_mode, d_out[b], d_grad[b], dstride, device, pp->comp);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(pp->done[b], pp->comp));
-    CUDA_TRY(cudaStreamWaitEvent(pp->copy, pp->done[b], 0));
-    CUDA_TRY(cudaMemcpyAsync((char*)out_host + off * es, d_out[b], pts * es, cudaMemcpyDeviceToHost, pp->copy));
+    if (c >= 2) ce = cudaStreamWaitEvent(pp->comp, pp->freed[b], 0);
+    if (ce != cudaSuccess) break;
+    rc = ab_eval_grid(&dprog, &sub, dtype, grad_mode, d_out[b], d_grad[b], dstride, device, pp->comp);
+    if (rc) break;
+    if ((ce = cudaEventRecord(pp->done[b], pp->comp)) != cudaSuccess) break;
+    if ((ce = cudaStreamWaitEvent(pp->copy, pp->done[b], 0)) != cudaSuccess) break;
+    if ((ce = cudaMemcpyAsync((char*)out_host + off * es, d_out[b], pts * es, cudaMemcpyDeviceToHost, pp->copy)) != cudaSuccess) break;
     if (rows)  // all gradient rows of the chunk in one strided copy
-      CUDA_TRY(cudaMemcpy2DAsync((char*)out_grad_host + off * es, (size_t)grad_stride * es, d_grad[b], (size_t)dstride * es,
-                                 pts * es, rows, cudaMemcpyDeviceToHost, pp->copy));
-    CUDA_TRY(cudaEventRecord(pp->freed[b], pp->copy));
+      if ((ce = cudaMemcpy2DAsync((char*)out_grad_host + off * es, (size_t)grad_stride * es, d_grad[b], (size_t)dstride * es,
+                                  pts * es, rows, cudaMemcpyDeviceToHost, pp->copy)) != cudaSuccess) break;
+    if ((ce = cudaEventRecord(pp->freed[b], pp->copy)) != cudaSuccess) break;
     done_planes += np;
     c++;
   }
-  CUDA_TRY(cudaStreamSynchronize(pp->copy));
+  // also on the error paths: no copy may still be writing into the caller's buffers when this function returns
+  const cudaError_t se = cudaStreamSynchronize(pp->copy);
+  cudaStreamSynchronize(pp->comp);
+  release();
+  if (rc) return rc;
+  if (ce != cudaSuccess) return fail(AB_ECUDA, "host pipeline: %s", cudaGetErrorString(ce));
+  if (se != cudaSuccess) return fail(AB_ECUDA, "host pipeline: %s", cudaGetErrorString(se));
   return AB_OK;
 }
 
@@ -1281,6 +1330,52 @@ extern "C" int ab_edge_filter(const void* field_dev, const uint32_t res[3], int 
   return AB_OK;
 }
 
+// ---- signed: unsigned -> signed distance field (modifications.py:220-275) ---------------------------------------------------------
+template <typename T>
+static int signed_field_t(const void* field, const uint32_t res[3], double threshold, void* out, int device, cudaStream_t st) {
+  const uint64_t n = (uint64_t)res[0] * res[1] * res[2];
+  Field3 f{res[0], res[1], res[2]};
+  char* buf = nullptr;
+  auto al = [](uint64_t b) { return (b + 255) & ~255ull; };
+  const uint64_t off_par1 = al(n), off_int = off_par1 + al(n), off_smooth = off_int + al(n * sizeof(T)),
+                 off_flags = off_smooth + al(n * sizeof(T)), total = off_flags + 256;
+  CUDA_TRY(cudaMallocAsync((void**)&buf, total, st));
+  uint8_t *par0 = (uint8_t*)buf, *par1 = (uint8_t*)(buf + off_par1);
+  T *interior = (T*)(buf + off_int), *smooth = (T*)(buf + off_smooth);
+  int* flags = (int*)(buf + off_flags);
+  int rc = AB_OK;
+  do {
+    if (cudaMemsetAsync(flags, 0, 2 * sizeof(int), st) != cudaSuccess) { rc = fail(AB_ECUDA, "memset"); break; }
+    const uint64_t cols = (uint64_t)std::max(res[0], res[1]) * res[2];
+    ab_signed_scan_kernel<T><<<dim3((unsigned)((cols + 255) / 256), 2), 256, 0, st>>>((const T*)field, f, (T)threshold, par0, par1, flags);
+    const dim3 g3((res[2] + 255) / 256, res[1], res[0]);
+    ab_signed_interior_kernel<T><<<g3, 256, 0, st>>>(par0, par1, f, interior);
+    const uint32_t ks[3] = {2, 2, 1};
+    rc = box_filter_t<T>(interior, res, ks, 1, smooth, device, st);  // conv_averaging(interior, (2, 2, 1), 1)
+    if (rc) break;
+    ab_signed_apply_kernel<T><<<g3, 256, 0, st>>>((const T*)field, smooth, f, flags, (T*)out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { rc = fail(AB_ECUDA, "signed launch: %s", cudaGetErrorString(e)); break; }
+    g_launches += 3;
+  } while (0);
+  cudaFreeAsync(buf, st);
+  return rc;
+}
+
+extern "C" int ab_signed_field(const void* field_dev, const uint32_t res[3], double threshold, int dtype, void* out_dev, int device,
+                               void* stream) {
+  int rc = use_device(device);
+  if (rc) return rc;
+  rc = check_field_args(field_dev, res, out_dev);
+  if (rc) return rc;
+  if (res[0] < 3 || res[1] < 3 || res[2] < 3) return fail(AB_EINVAL, "signed needs at least 3 samples per axis (the reference pads an empty interior otherwise)");
+  if (res[0] > 65535 || res[1] > 65535) return fail(AB_ETOOLARGE, "field axis longer than 65535 samples");
+  if (field_dev == out_dev) return fail(AB_EINVAL, "signed cannot run in place");
+  if (dtype == AB_F32) return signed_field_t<float>(field_dev, res, threshold, out_dev, device, (cudaStream_t)stream);
+  if (dtype == AB_F64) return signed_field_t<double>(field_dev, res, threshold, out_dev, device, (cudaStream_t)stream);
+  return fail(AB_EINVAL, "bad dtype %d", dtype);
+}
+
 static int check_vec_op(const ab_vec_op& op, uint32_t i, uint64_t n) {
   auto scalar_ok = [&](uint32_t kind, const void* a) { return kind == AB_VK_SCALAR || (kind == AB_VK_ARRAY && a); };
   switch (op.opcode) {
@@ -1390,6 +1485,17 @@ extern "C" int ab_host_alloc_pinned(uint64_t bytes, void** out_host) {
   if (!out_host) return fail(AB_EINVAL, "null pointer");
   if (ab_device_count() == 0) return fail(AB_ENODEVICE, "no CUDA device visible");
   CUDA_TRY(cudaHostAlloc(out_host, bytes ? bytes : 1, cudaHostAllocDefault));
+  return AB_OK;
+}
+// flags: bit 0 cudaHostAllocPortable, bit 1 cudaHostAllocWriteCombined (device -> host result buffers are written by the
+// GPU and read once by the CPU: write-combined pages skip the cache snoop on every PCIe write)
+extern "C" int ab_host_alloc_pinned_flags(uint64_t bytes, unsigned flags, void** out_host) {
+  if (!out_host) return fail(AB_EINVAL, "null pointer");
+  if (ab_device_count() == 0) return fail(AB_ENODEVICE, "no CUDA device visible");
+  unsigned f = cudaHostAllocDefault;
+  if (flags & 1u) f |= cudaHostAllocPortable;
+  if (flags & 2u) f |= cudaHostAllocWriteCombined;
+  CUDA_TRY(cudaHostAlloc(out_host, bytes ? bytes : 1, f));
   return AB_OK;
 }
 extern "C" int ab_host_free_pinned(void* host) {

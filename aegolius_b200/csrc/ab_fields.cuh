@@ -181,6 +181,85 @@ __global__ void __launch_bounds__(256) ab_edge_kernel(const T* __restrict__ in, 
   }
 }
 
+// ---- signed: unsigned distance field -> signed distance field (modifications.py:220-275) -----------------------------------------
+// boundary = field < threshold (the smallest grid step). Along axis 0 and along axis 1 the reference counts the entries
+// into a boundary run on the way forward (chu) and the exits (chuu); a sample is "interior" along an axis when the inclusive
+// prefix count of entries at i is odd OR the prefix count of exits at n-1-i is odd (the reference flips the cumulative sum,
+// not the sequence); the two axes are AND-ed, smoothed by the (2,2,1) box filter, the outermost samples take their inner
+// neighbour's value, and the field is negated where the result exceeds 1/2. If the field has a negative sample it is
+// returned untouched.
+//
+// ab_signed_scan_kernel: a thread owns one column along the scanned axis and marches it once, storing both prefix
+// parities per sample (bit 0: entries, bit 1: exits). blockIdx.y selects the axis: 0 scans along axis 0 (thread = (i1, i2)),
+// 1 scans along axis 1 (thread = (i0, i2)); threads are consecutive in i2, so every access is coalesced. It also raises
+// flags[0] when a sample is negative and flags[1] when one is NaN.
+template <typename T>
+__global__ void __launch_bounds__(256) ab_signed_scan_kernel(const T* __restrict__ field, Field3 f, T threshold, uint8_t* __restrict__ par0,
+                                                             uint8_t* __restrict__ par1, int* __restrict__ flags) {
+  const int axis = blockIdx.y;
+  const uint32_t ncols = (axis == 0 ? f.n1 : f.n0) * f.n2;
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const uint32_t a = col / f.n2, i2 = col - a * f.n2;  // a = i1 (axis 0) or i0 (axis 1)
+  const uint64_t plane = (uint64_t)f.n1 * f.n2;
+  const uint64_t base = axis == 0 ? (uint64_t)a * f.n2 + i2 : (uint64_t)a * plane + i2;
+  const uint64_t step = axis == 0 ? plane : f.n2;
+  const uint32_t n = axis == 0 ? f.n0 : f.n1;
+  uint8_t* par = axis == 0 ? par0 : par1;
+  bool neg = false, nan = false;
+  unsigned p_in = 0, p_out = 0;
+  T cur = field[base];
+  bool b_prev = false, b_cur = cur < threshold;
+  for (uint32_t i = 0; i < n; i++) {
+    const T nxt = i + 1 < n ? field[base + (uint64_t)(i + 1) * step] : T(0);
+    const bool b_next = i + 1 < n ? nxt < threshold : false;
+    if (axis == 0) {
+      neg |= cur < T(0);
+      nan |= cur != cur;
+    }
+    if (i > 0 && b_cur && !b_prev) p_in ^= 1u;      // chu[i]  = boundary[i] & ~boundary[i-1]   (i >= 1)
+    if (i + 1 < n && b_cur && !b_next) p_out ^= 1u;  // chuu[i] = boundary[i] & ~boundary[i+1]   (i <= n-2)
+    par[base + (uint64_t)i * step] = (uint8_t)(p_in | (p_out << 1));
+    b_prev = b_cur;
+    b_cur = b_next;
+    cur = nxt;
+  }
+  if (neg) atomicOr(flags, 1);
+  if (nan) atomicOr(flags + 1, 1);
+}
+
+// interior = (in0[i0] | out0[n0-1-i0]) & (in1[i1] | out1[n1-1-i1]) as a 0 / 1 field of T
+template <typename T>
+__global__ void __launch_bounds__(256) ab_signed_interior_kernel(const uint8_t* __restrict__ par0, const uint8_t* __restrict__ par1, Field3 f,
+                                                                 T* __restrict__ interior) {
+  const uint32_t i2 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i0 = blockIdx.z;
+  if (i2 >= f.n2) return;
+  const uint64_t plane = (uint64_t)f.n1 * f.n2;
+  const uint64_t k = i0 * plane + (uint64_t)i1 * f.n2 + i2;
+  const unsigned a = (par0[k] & 1u) | ((par0[(uint64_t)(f.n0 - 1 - i0) * plane + (uint64_t)i1 * f.n2 + i2] >> 1) & 1u);
+  const unsigned b = (par1[k] & 1u) | ((par1[i0 * plane + (uint64_t)(f.n1 - 1 - i1) * f.n2 + i2] >> 1) & 1u);
+  interior[k] = (a & b) ? T(1) : T(0);
+}
+
+// out = field * (1 - 2 (smooth[clamped index] > 1/2)); untouched when the field had a negative sample (and no NaN: np.amin
+// of a field with a NaN is NaN, which is not < 0)
+template <typename T>
+__global__ void __launch_bounds__(256) ab_signed_apply_kernel(const T* __restrict__ field, const T* __restrict__ smooth, Field3 f,
+                                                              const int* __restrict__ flags, T* __restrict__ out) {
+  const uint32_t i2 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i0 = blockIdx.z;
+  if (i2 >= f.n2) return;
+  const uint64_t plane = (uint64_t)f.n1 * f.n2;
+  const uint64_t k = i0 * plane + (uint64_t)i1 * f.n2 + i2;
+  const T v = field[k];
+  if (flags[0] && !flags[1]) {
+    out[k] = v;
+    return;
+  }
+  auto inner = [](uint32_t i, uint32_t n) { return i < 1 ? 1u : (i > n - 2 ? n - 2 : i); };  // [1:-1] then edge padding
+  const T s = smooth[inner(i0, f.n0) * plane + (uint64_t)inner(i1, f.n1) * f.n2 + inner(i2, f.n2)];
+  out[k] = s > T(0.5) ? -v : v;
+}
+
 // ---- vector-field modifiers ----------------------------------------------------------------------------------------------
 struct VecOpK {
   uint32_t opcode;

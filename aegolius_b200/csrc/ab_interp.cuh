@@ -308,10 +308,27 @@ struct StackOf<Dual<Pk, K>> {
 
 // ---- 128-bit stores ---------------------------------------------------------------------------------------------------------
 // AB_STORE_POLICY: 0 = streaming (st.global.cs: the field is written once and not read back by this kernel), 1 = default
-// write-back, 2 = st.global.cg, 3 = write-through. Measured on B200 in profiles/r02_jit_sweep.md.
+// write-back, 2 = st.global.cg, 3 = write-through (measured on B200 in profiles/r02_jit_sweep.md), 4 = multimem.st: `out`
+// is the MULTICAST address of a symmetric allocation (NVLS), so one store lands in the same place of every GPU's buffer
+// and the field is assembled on all ranks by the evaluation itself (distributed.evaluate_multicast), no gather pass.
 #ifndef AB_STORE_POLICY
 #define AB_STORE_POLICY 0
 #endif
+#if AB_STORE_POLICY == 4
+AB_DEV void ab_st(float4* p, const float4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+AB_DEV void ab_st(float2* p, const float2& v) {
+  asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+AB_DEV void ab_st(float* p, const float& v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+AB_DEV void ab_st(double* p, const double& v) { asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+AB_DEV void ab_st(double2* p, const double2& v) {  // (no .v2.f64 form: the 16 bytes travel as four 32-bit lanes)
+  const float a = __int_as_float(__double2loint(v.x)), b = __int_as_float(__double2hiint(v.x));
+  const float c = __int_as_float(__double2loint(v.y)), d = __int_as_float(__double2hiint(v.y));
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+#else
 template <typename V>
 AB_DEV void ab_st(V* p, const V& v) {
 #if AB_STORE_POLICY == 0
@@ -324,6 +341,7 @@ AB_DEV void ab_st(V* p, const V& v) {
   __stwt(p, v);
 #endif
 }
+#endif
 AB_DEV void store_pack(float* dst, const Pack<float, 4>& v, uint64_t idx, uint64_t n, bool aligned) {
   if (aligned && idx + 4 <= n) {
     ab_st(reinterpret_cast<float4*>(dst + idx), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));

@@ -70,12 +70,26 @@ AB_DEV void op_scale_p(Pt<S>& p, A a) {
   p.z = p.z * a[0];
 }
 // modifications.py:91-93  q = p - clip(p, -e/2, e/2)
+template <typename S, typename U>
+AB_DEV S elongate_axis(const S& q, const U& lo, const U& hi) { return q - clamp_(q, lo, hi); }
+// dual coordinate, plain bounds: the tangent passes through outside [lo, hi] and vanishes inside (one select per
+// component instead of two dual min / max and a dual subtraction)
+template <typename P, int K>
+AB_DEV Dual<P, K> elongate_axis(const Dual<P, K>& q, const typename P::scalar& lo, const typename P::scalar& hi) {
+  typedef typename P::scalar T;
+  Dual<P, K> r;
+  r.v = q.v - clamp_(q.v, lo, hi);
+  const Mask<P::width> inside = ge_(q.v, lo) & le_(q.v, hi);
+#pragma unroll
+  for (int k = 0; k < K; k++) r.d[k] = select_(inside, P(T(0)), q.d[k]);
+  return r;
+}
 template <typename S, typename A>
 AB_DEV void op_elongate(Pt<S>& p, A a) {
   typedef typename S::scalar T;
-  p.x = p.x - clamp_(p.x, a[0], a[3]);
-  p.y = p.y - clamp_(p.y, a[1], a[4]);
-  p.z = p.z - clamp_(p.z, a[2], a[5]);
+  p.x = elongate_axis(p.x, a[0], a[3]);
+  p.y = elongate_axis(p.y, a[1], a[4]);
+  p.z = elongate_axis(p.z, a[2], a[5]);
 }
 // modifications.py:516-522
 template <typename S, typename A>
@@ -205,6 +219,102 @@ AB_DEV void op_lin_inst(Pt<S>& p, A a, int inner_on) {
   }
   p.x = v;
 }
+// min / max over the warp of a NON-NEGATIVE value: the bit patterns of non-negative floats order like unsigned integers, so
+// fp32 takes one REDUX instruction instead of a five-round shuffle butterfly
+AB_DEV float warp_min_nonneg(float v) { return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v))); }
+AB_DEV float warp_max_nonneg(float v) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v))); }
+AB_DEV double warp_min_nonneg(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+AB_DEV double warp_max_nonneg(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+// the first four scalars of a 16-byte aligned record with one 128-bit load
+AB_DEV void load4(const float* q, float& a, float& b, float& c, float& d) {
+  const float4 v = *reinterpret_cast<const float4*>(q);
+  a = v.x; b = v.y; c = v.z; d = v.w;
+}
+AB_DEV void load4(const double* q, double& a, double& b, double& c, double& d) {
+  const double2 u = *reinterpret_cast<const double2*>(q), v = *reinterpret_cast<const double2*>(q + 2);
+  a = u.x; b = u.y; c = v.x; d = v.y;
+}
+
+// second half of curve instancing: subtract the chosen instance's position and, for the aligned variants (mode 1), rotate
+// into its frame (rows dx, dy, dz). The 12-scalar records come in as three 128-bit loads; consecutive points mostly share
+// one record. Plain packs are processed two points at a time so that only 24 record registers are live (8 points per
+// thread would otherwise hold 96), duals (at most 2 points per thread) in one go.
+template <typename T, int WC>
+AB_DEV void gather_records(const T* rec, const int* idx, int mode, Pack<T, WC> (&r)[12]) {
+  if (mode) {
+#pragma unroll
+    for (int i = 0; i < WC; i++) {
+      if (i > 0 && idx[i] == idx[i - 1]) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) r[k].v[i] = r[k].v[i - 1];
+      } else {
+        const T* q = rec + idx[i] * 12;
+        load4(q, r[0].v[i], r[1].v[i], r[2].v[i], r[3].v[i]);
+        load4(q + 4, r[4].v[i], r[5].v[i], r[6].v[i], r[7].v[i]);
+        load4(q + 8, r[8].v[i], r[9].v[i], r[10].v[i], r[11].v[i]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < WC; i++) {
+      const T* q = rec + idx[i] * 3;
+      r[0].v[i] = q[0];
+      r[1].v[i] = q[1];
+      r[2].v[i] = q[2];
+    }
+  }
+}
+template <typename S, typename PK>
+AB_DEV void frame_change(Pt<S>& p, const PK (&r)[12], int mode) {
+  S dx = add_lane(p.x, -r[0]), dy = add_lane(p.y, -r[1]), dz = add_lane(p.z, -r[2]);
+  if (mode) {
+    p.x = mul_lane(dx, r[3]) + mul_lane(dy, r[4]) + mul_lane(dz, r[5]);
+    p.y = mul_lane(dx, r[6]) + mul_lane(dy, r[7]) + mul_lane(dz, r[8]);
+    p.z = mul_lane(dx, r[9]) + mul_lane(dy, r[10]) + mul_lane(dz, r[11]);
+  } else {
+    p.x = dx;
+    p.y = dy;
+    p.z = dz;
+  }
+}
+template <typename P, int K>
+AB_DEV void curve_frames(Pt<Dual<P, K>>& p, const typename P::scalar* rec, const int* idx, int mode) {
+  P r[12];
+  gather_records(rec, idx, mode, r);
+  frame_change(p, r, mode);
+}
+template <typename T, int W>
+AB_DEV void curve_frames(Pt<Pack<T, W>>& p, const T* rec, const int* idx, int mode) {
+  constexpr int WC = (W % 2 == 0) ? 2 : 1;
+#pragma unroll
+  for (int c = 0; c < W; c += WC) {
+    Pack<T, WC> r[12];
+    gather_records(rec, idx + c, mode, r);
+    Pt<Pack<T, WC>> q;
+#pragma unroll
+    for (int i = 0; i < WC; i++) {
+      q.x.v[i] = p.x.v[c + i];
+      q.y.v[i] = p.y.v[c + i];
+      q.z.v[i] = p.z.v[c + i];
+    }
+    frame_change(q, r, mode);
+#pragma unroll
+    for (int i = 0; i < WC; i++) {
+      p.x.v[c + i] = q.x.v[i];
+      p.y.v[c + i] = q.y.v[i];
+      p.z.v[c + i] = q.z.v[i];
+    }
+  }
+}
+
 // modifications.py:1120-1127 / 1183-1191 / 1253-1261: nearest instance by position (the reference asks a KD-tree), then
 // subtract its position and, for the aligned variants, rotate into its frame. Record = pos(3) [+ rows dx,dy,dz (9)].
 //
@@ -219,83 +329,67 @@ AB_DEV void op_curve_inst(Pt<S>& p, A a, int mode) {
   const T* tab = raw_args(a);  // instance table: structural (no parameter tangents)
   const int n = (int)tab[0];
   const int stride = mode ? 12 : 3;
-  const T* rec = tab + 4;  // records start on a 16-byte boundary
+  const T* rec = tab + 4;  // records start on a 16-byte boundary (and stay on one for mode 1: 12 scalars each)
   constexpr int W = S::width;
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   auto vx = value_of(p.x), vy = value_of(p.y), vz = value_of(p.z);
-  const T Cx = __shfl_sync(FULL, vx.v[0], 0), Cy = __shfl_sync(FULL, vy.v[0], 0), Cz = __shfl_sync(FULL, vz.v[0], 0);
+  // reference point: the first point of the middle lane (halves the warp radius against taking lane 0's)
+  const T Cx = __shfl_sync(FULL, vx.v[0], 16), Cy = __shfl_sync(FULL, vy.v[0], 16), Cz = __shfl_sync(FULL, vz.v[0], 16);
   T r2 = T(0);
 #pragma unroll
   for (int i = 0; i < W; i++) {
     const T dx = vx.v[i] - Cx, dy = vy.v[i] - Cy, dz = vz.v[i] - Cz;
     r2 = s_max(r2, s_fma(dx, dx, s_fma(dy, dy, dz * dz)));
   }
-  T dmin = T(3.0e38);
-  for (int base = 0; base < n; base += 32) {
-    const int j = base + lane;
-    if (j < n) {
-      const T dx = Cx - rec[j * stride], dy = Cy - rec[j * stride + 1], dz = Cz - rec[j * stride + 2];
-      dmin = s_min(dmin, s_fma(dx, dx, s_fma(dy, dy, dz * dz)));
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    r2 = s_max(r2, __shfl_xor_sync(FULL, r2, off));
-    dmin = s_min(dmin, __shfl_xor_sync(FULL, dmin, off));
-  }
+  // lane l measures instance base + l from the reference point; the first round's distance is kept for the second pass
+  auto lane_d2 = [&](int j) {
+    const T dx = Cx - rec[j * stride], dy = Cy - rec[j * stride + 1], dz = Cz - rec[j * stride + 2];
+    return s_fma(dx, dx, s_fma(dy, dy, dz * dz));
+  };
+  const T d_first = lane < n ? lane_d2(lane) : T(3.0e38);
+  T dmin = d_first;
+  for (int base = 32; base < n; base += 32)
+    if (base + lane < n) dmin = s_min(dmin, lane_d2(base + lane));
+  r2 = warp_max_nonneg(r2);
+  dmin = warp_min_nonneg(dmin);
   // widened a little against rounding: it only admits extra candidates, never drops the true nearest
   const T reach = s_sqrt(dmin) * T(1.00001) + T(2.0001) * s_sqrt(r2) + T(1e-30);
   const T cut = reach * reach;
-  T bst[W];
   int idx[W];
+  unsigned m = __ballot_sync(FULL, d_first <= cut);
+  if (n <= 32 && (m & (m - 1)) == 0) {
+    // one candidate for the whole warp (the common case away from the cell boundaries of the instances): it is the
+    // nearest instance of every point, no distance needs to be evaluated
+    const int j = m ? __ffs(m) - 1 : 0;  // (m == 0 only for NaN coordinates)
 #pragma unroll
-  for (int i = 0; i < W; i++) {
-    bst[i] = T(3.0e38);
-    idx[i] = 0;
-  }
-  for (int base = 0; base < n; base += 32) {
-    const int jl = base + lane;
-    bool in = false;
-    if (jl < n) {
-      const T dx = Cx - rec[jl * stride], dy = Cy - rec[jl * stride + 1], dz = Cz - rec[jl * stride + 2];
-      in = s_fma(dx, dx, s_fma(dy, dy, dz * dz)) <= cut;
+    for (int i = 0; i < W; i++) idx[i] = j;
+  } else {
+    T bst[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+      bst[i] = T(3.0e38);
+      idx[i] = 0;
     }
-    unsigned m = __ballot_sync(FULL, in);
-    while (m) {  // warp-uniform loop over the candidates, in index order (ties resolve to the lowest index)
-      const int j = base + __ffs(m) - 1;
-      m &= m - 1;
-      const T qx = rec[j * stride], qy = rec[j * stride + 1], qz = rec[j * stride + 2];
-      const Pack<T, W> dx = vx - qx, dy = vy - qy, dz = vz - qz;  // packed f32x2 lanes
-      const Pack<T, W> d2 = fma_(dx, dx, fma_(dy, dy, dz * dz));
+    for (int base = 0; base < n; base += 32) {
+      if (base) m = __ballot_sync(FULL, base + lane < n && lane_d2(base + lane) <= cut);
+      while (m) {  // warp-uniform loop over the candidates, in index order (ties resolve to the lowest index)
+        const int j = base + __ffs(m) - 1;
+        m &= m - 1;
+        const T qx = rec[j * stride], qy = rec[j * stride + 1], qz = rec[j * stride + 2];
+        const Pack<T, W> dx = vx - qx, dy = vy - qy, dz = vz - qz;  // packed f32x2 lanes
+        const Pack<T, W> d2 = fma_(dx, dx, fma_(dy, dy, dz * dz));
 #pragma unroll
-      for (int i = 0; i < W; i++) {
-        if (d2.v[i] < bst[i]) {
-          bst[i] = d2.v[i];
-          idx[i] = j;
+        for (int i = 0; i < W; i++) {
+          if (d2.v[i] < bst[i]) {
+            bst[i] = d2.v[i];
+            idx[i] = j;
+          }
         }
       }
     }
   }
-  // gather the chosen record per lane
-  Pack<T, W> r[12];
-#pragma unroll
-  for (int i = 0; i < W; i++) {
-    const T* q = rec + idx[i] * stride;
-#pragma unroll
-    for (int k = 0; k < 12; k++)
-      if (k < stride) r[k].v[i] = q[k];
-  }
-  S dx = add_lane(p.x, -r[0]), dy = add_lane(p.y, -r[1]), dz = add_lane(p.z, -r[2]);
-  if (mode) {
-    p.x = mul_lane(dx, r[3]) + mul_lane(dy, r[4]) + mul_lane(dz, r[5]);
-    p.y = mul_lane(dx, r[6]) + mul_lane(dy, r[7]) + mul_lane(dz, r[8]);
-    p.z = mul_lane(dx, r[9]) + mul_lane(dy, r[10]) + mul_lane(dz, r[11]);
-  } else {
-    p.x = dx;
-    p.y = dy;
-    p.z = dz;
-  }
+  curve_frames(p, rec, idx, mode);
 }
 
 // ---- value ops --------------------------------------------------------------------------------------------------------
@@ -355,6 +449,26 @@ AB_DEV S smin_poly3(const S& x, const S& y, const U& w) {  // combine.py:20-26
   S h = max_(w - abs_(x - y), T(0)) * rcp_arg(w);
   return min_(x, y) - h * h * h * (w * T(1.0 / 6.0));
 }
+// polynomial smooth minima of dual numbers with a plain width, in closed form: with u = x - y, h = max(w - |u|, 0) / w,
+//   d smin_n = d min(x, y) + (n h^(n-1) / (2 n)) sign(u) (dx - dy)        (n = 2: h / 2 ... n = 3: h^2 / 2)
+// (same value expression as the generic form; 3 instructions per tangent component instead of a chain of dual products)
+template <typename P, int K>
+AB_DEV Dual<P, K> smin_poly_dual(const Dual<P, K>& x, const Dual<P, K>& y, const typename P::scalar& w, int order) {
+  typedef typename P::scalar T;
+  const P u = x.v - y.v;
+  const P h = max_(w - abs_(u), T(0)) * s_rcp(w);
+  Dual<P, K> r;
+  const Mask<P::width> xle = le_(x.v, y.v);
+  r.v = order == 2 ? min_(x.v, y.v) - h * h * (w * T(0.25)) : min_(x.v, y.v) - h * h * h * (w * T(1.0 / 6.0));
+  const P g = (order == 2 ? h : h * h) * T(0.5) * sign_(u);  // 0 where h == 0: plain min
+#pragma unroll
+  for (int k = 0; k < K; k++) r.d[k] = fma_(g, x.d[k] - y.d[k], select_(xle, x.d[k], y.d[k]));
+  return r;
+}
+template <typename P, int K>
+AB_DEV Dual<P, K> smin_poly2(const Dual<P, K>& x, const Dual<P, K>& y, const typename P::scalar& w) { return smin_poly_dual(x, y, w, 2); }
+template <typename P, int K>
+AB_DEV Dual<P, K> smin_poly3(const Dual<P, K>& x, const Dual<P, K>& y, const typename P::scalar& w) { return smin_poly_dual(x, y, w, 3); }
 // combine.py:29-34, evaluated in the shifted form (x e^{(x-m)/a} + y e^{(y-m)/a}) / (e^{(x-m)/a} + e^{(y-m)/a}),
 // m = max(x,y): algebraically identical, but does not overflow in fp32 where exp(x/a) would for x/a > 88.
 template <typename S, typename U>

@@ -183,12 +183,13 @@ def bind_to_device_numa(device=0):
 class PinnedArray:
     """Page-locked host buffer exposed as a numpy array (for the D2H leg of create())."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, portable=False, write_combined=False):
         self.dtype = np.dtype(dtype)
         self.shape = tuple(int(s) for s in np.atleast_1d(shape))
         nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
         p = C.c_void_p()
-        cabi.check(cabi.lib().ab_host_alloc_pinned(nbytes, C.byref(p)))
+        cabi.check(cabi.lib().ab_host_alloc_pinned_flags(nbytes, (1 if portable else 0) | (2 if write_combined else 0),
+                                                         C.byref(p)))
         self._ptr = p
         buf = (C.c_char * max(1, nbytes)).from_address(p.value)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
@@ -274,6 +275,16 @@ def create(obj, co, *, dtype="f32", grad=None, device=0, out=None, out_grad=None
     return (field, g_arr) if rows else field
 
 
+def grid_min_step(spec):
+    """min over the axes of |co[i, 1] - co[i, 0]| on generate_grid coordinates (modifications.py:239-240): the threshold
+    below which `signed` calls a sample "boundary". Evaluated like np.linspace does (start + 1 * step)."""
+    seps = []
+    for size, n in zip(spec.size, spec.res):
+        x = np.linspace(-float(size) / 2, float(size) / 2, int(n))
+        seps.append(abs(x[1] - x[0]))
+    return float(min(seps))
+
+
 def _create_staged(prog, spec, code, npdt, device):
     """Programs with grid-stencil stages: for every stage, in program order, the prefix program ops[:k] is evaluated over the
     whole grid on the device, filtered by ab_box_filter / ab_edge_filter, and bound to the P_FIELD op that replaced the
@@ -300,6 +311,10 @@ def _create_staged(prog, spec, code, npdt, device):
             if st["kind"] == 0:
                 ks = (C.c_uint32 * 3)(*st["ksize"])
                 cabi.check(lib.ab_box_filter(d_in.ptr, res3, ks, st["iterations"], code, d_out.ptr, device, None))
+            elif st["kind"] == 2:
+                if min(spec.res) < 3:
+                    raise ValueError("can't extend empty axis using modes other than 'constant' or 'empty'")  # np.pad
+                cabi.check(lib.ab_signed_field(d_in.ptr, res3, grid_min_step(spec), code, d_out.ptr, device, None))
             else:
                 cabi.check(lib.ab_edge_filter(d_in.ptr, res3, code, d_out.ptr, device, None))
             bound[st["blob"]] = (d_out.ptr.value, n)
@@ -338,8 +353,11 @@ def program_tangent(geometry, params, argnum, rel_step=1e-6):
     p0, p_lo, p_hi = flatten(geometry(*params)), flatten(geometry(*lo)), flatten(geometry(*hi))
     if not (np.array_equal(p0.ops, p_lo.ops) and np.array_equal(p0.ops, p_hi.ops)):
         raise ValueError("the program structure changes with the parameter; cannot differentiate through it")
-    p0.dargs = (p_hi.args - p_lo.args) / (2.0 * h)
-    p0.dargs[np.abs(p0.dargs) < 1e-9 * (1.0 + np.abs(p0.args))] = 0.0  # rounding noise of unaffected arguments
+    # arguments the parameter does not reach are bit-identical at theta - h and theta + h: exactly zero tangent, nothing
+    # is thresholded away (a genuinely small derivative stays). The remaining tangents carry the central difference's
+    # ~h^2 truncation error of the HOST-side folding (rotation matrices, frames, sin / cos of constant angles); the kernel
+    # propagates them analytically.
+    p0.dargs = np.where(p_hi.args == p_lo.args, 0.0, (p_hi.args - p_lo.args) / (2.0 * h))
     return p0
 
 
@@ -455,6 +473,63 @@ def create_torch(obj, spec: GridSpec, *, dtype="f32", grad=None, device=0, slab=
     cabi.check(cabi.lib().ab_eval_grid(cp.ref(), C.byref(g), code, gmode, field.data_ptr(), gptr, stride, device,
                                        C.c_void_p(stream)))
     return (field, gbuf[:, :n]) if rows else field
+
+
+def from_sdf_torch(field, co_resolution, *, slab=None, field_plane0=0, normalize=True, device=0, out=None):
+    """from_sdf (vector_functions.py:130-139) on a torch CUDA tensor, on the current torch stream, for a slab of ix planes
+    (multi-GPU: distributed.from_sdf_sharded). `field` holds planes [field_plane0, ...) of the grid and must cover the
+    slab plus one halo plane on each side that exists in the grid (np.gradient's central stencil); returns the
+    (dims, n_slab) view of a row-padded buffer. Concatenating the slabs' results along axis 1 equals the whole-grid call."""
+    import torch
+    res = tuple(int(r) for r in np.asarray(co_resolution).reshape(-1))
+    dims = len(res)
+    if dims not in (2, 3):
+        raise ValueError("co_resolution must have 2 or 3 entries")
+    code = cabi.AB_F32 if field.dtype == torch.float32 else cabi.AB_F64
+    x0, x1 = (0, res[0]) if slab is None else (int(slab[0]), int(slab[1]))
+    per_plane = int(np.prod(res[1:]))
+    lo, hi = max(x0 - 1, 0), min(x1 + 1, res[0])
+    if field_plane0 > lo or field.numel() < (hi - field_plane0) * per_plane:
+        raise ValueError(f"the field must cover planes [{lo}, {hi}) (slab plus halo); it starts at plane {field_plane0} "
+                         f"and holds {field.numel() // per_plane}")
+    n = (x1 - x0) * per_plane
+    stride = (n + 3) // 4 * 4
+    buf = out if out is not None else torch.empty((dims, stride), dtype=field.dtype, device=field.device)
+    g = cabi.make_grid((0.0, 0.0, 0.0), res + ((1,) if dims == 2 else ()), (x0, x1))
+    stream = torch.cuda.current_stream(field.device).cuda_stream
+    cabi.check(cabi.lib().ab_fd_gradient(field.data_ptr(), int(field_plane0), C.byref(g), dims, code, 1 if normalize else 0,
+                                         buf.data_ptr(), buf.stride(0), device, C.c_void_p(stream)))
+    return buf[:, :n]
+
+
+def cloud_records(points, dim=3, dtype="f32", device=0):
+    """(x, y, z, 0) records of the evaluation dtype on the device, as a torch tensor (M, 4): the layout ab_nn_grid /
+    ab_nn_points read. Built once and reused across calls (or broadcast to the other ranks, distributed.py)."""
+    import torch
+    _, npdt = _dtype(dtype)
+    pts = np.asarray(points, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[0] < dim:
+        raise ValueError(f"points must have shape ({dim}, M)")
+    rec = np.zeros((pts.shape[1], 4), dtype=npdt)
+    rec[:, :dim] = pts[:dim].T
+    return torch.from_numpy(rec).to(torch.device("cuda", device))
+
+
+def point_cloud_sdf_torch(spec, records, *, dim=3, slab=None, device=0, out=None):
+    """sdf_point_cloud_3d / _2d on grid samples, device-resident: `records` from cloud_records(); returns a torch tensor
+    of the slab's unsigned distances (current torch stream)."""
+    import torch
+    code = cabi.AB_F32 if records.dtype == torch.float32 else cabi.AB_F64
+    x0, x1 = (0, spec.res[0]) if slab is None else slab
+    n = (x1 - x0) * spec.res[1] * spec.res[2]
+    buf = out if out is not None else torch.empty(n, dtype=records.dtype, device=records.device)
+    if n == 0:
+        return buf
+    g = cabi.make_grid(spec.size, spec.res, (x0, x1))
+    stream = torch.cuda.current_stream(records.device).cuda_stream
+    cabi.check(cabi.lib().ab_nn_grid(records.data_ptr(), records.shape[0], dim, C.byref(g), code, buf.data_ptr(), device,
+                                     C.c_void_p(stream)))
+    return buf
 
 
 # ---- from_sdf ------------------------------------------------------------------------------------------------------------------

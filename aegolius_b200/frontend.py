@@ -352,8 +352,10 @@ class ModifyObject:
     def recover_volume(self, *a, **k):
         self._unsupported("recover_volume")
 
-    def signed(self, *a, **k):
-        self._unsupported("signed")
+    def signed(self, co_resolution):
+        """modifications.py:220-275: unsigned -> signed distance field on a 3D grid (a whole-grid post-pass, like the
+        convolution modifications: flattened into a stencil stage, engine._create_staged)."""
+        return self._add("signed", co_resolution=co_resolution)
 
     # grid stencils (modifications.py:1586-1637): evaluated by separate kernels between two interpreter launches
     def conv_averaging(self, kernel_size, iterations, co_resolution):

@@ -105,7 +105,10 @@ def generate_grid_spec(size, resolution):
 
 def detect_grid(co):
     """Recognises a (3,N) array produced by SPOMSO's own generate_grid (plain ndarray): returns a GridSpec or None.
-    Cheap: reads O(nx+ny+nz) entries to propose (size, res) and O(4096) random entries to confirm."""
+    Arrays that carry their provenance (GridSpec, GridCoords.spec) are taken at their word. For a plain array the grid is
+    proposed from O(nx+ny+nz) entries and then EVERY coordinate is compared with the proposed axes (one pass over the
+    array, chunked: about what the host-to-device upload it replaces would cost) — in grid mode the kernel regenerates the
+    coordinates and never reads the array, so a generate_grid output with a few edited points must not pass."""
     if isinstance(co, GridSpec):
         return co
     spec = getattr(co, "spec", None)
@@ -145,16 +148,24 @@ def detect_grid(co):
         return None
     spec = GridSpec(size, res)
     ax = spec.axes()
-    rng = np.random.default_rng(1234)
-    k = rng.integers(0, n, size=min(n, 4096))
-    iz = k % nz
-    iy = (k // nz) % ny
-    ix = k // (nz * ny)
-    ok = np.array_equal(co[0, k], ax[0][ix]) and np.array_equal(co[1, k], ax[1][iy])
-    if nz > 1:
-        ok = ok and np.array_equal(co[2, k], ax[2][iz])
-    ok = ok and co[0, -1] == ax[0][-1] and co[1, -1] == ax[1][-1]
-    return spec if ok else None
+    if not (co[0, -1] == ax[0][-1] and co[1, -1] == ax[1][-1]):
+        return None
+    # full verification, x-chunks of about 2^22 points: co[0] is constant over each (ny, nz) plane, co[1] over each z row
+    plane = ny * nz
+    step = max(1, (1 << 22) // plane)
+    for x0 in range(0, nx, step):
+        x1 = min(nx, x0 + step)
+        sl = slice(x0 * plane, x1 * plane)
+        if not np.array_equal(co[0, sl].reshape(x1 - x0, plane), np.broadcast_to(ax[0][x0:x1, None], (x1 - x0, plane))):
+            return None
+        if not np.array_equal(co[1, sl].reshape(x1 - x0, ny, nz), np.broadcast_to(ax[1][None, :, None], (x1 - x0, ny, nz))):
+            return None
+        if nz > 1:
+            if not np.array_equal(co[2, sl].reshape(x1 - x0, ny, nz), np.broadcast_to(ax[2][None, None, :], (x1 - x0, ny, nz))):
+                return None
+        elif np.any(co[2, sl]):
+            return None
+    return spec
 
 
 def smarter_reshape(pattern, resolution):

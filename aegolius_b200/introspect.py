@@ -70,7 +70,7 @@ def to_frontend(obj, _stack=()):
             params = {k: v for k, v in cells.items() if k not in ("geo_object", "self")}
             if name not in fe.ModifyObject.__dict__ or name in (
                     "custom_modification", "custom_post_process", "displacement", "define_volume",
-                    "recover_volume", "signed", "signed_old"):
+                    "recover_volume", "signed_old"):
                 raise NotImplementedError(
                     f"modification '{name}' (closure {qn}) takes a Python callable or a grid stencil and cannot "
                     f"enter the GPU op list; evaluate this object with SPOMSO itself")

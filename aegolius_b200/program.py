@@ -398,6 +398,18 @@ class _Builder:
             post.append((oc.PP_GAUSS_BOUNDARY, 0, [p["amplitude"], p["width"]]))
         elif name == "gaussian_falloff":
             post.append((oc.PP_GAUSS_FALLOFF, 0, [p["amplitude"], p["width"]]))
+        elif name == "signed":
+            # modifications.py:220-275: a whole-grid post-pass (scans + box filter), staged like the convolutions below
+            res = tuple(int(r) for r in np.asarray(p["co_resolution"]).reshape(-1))
+            if len(res) != 3:
+                raise IndexError("too many indices for array: signed() slices the reshaped field with three indices "
+                                 "(modifications.py:244), co_resolution must have 3 entries")
+            if len(self.blobs) >= oc.MAX_BLOBS:
+                raise FlattenError(f"more than {oc.MAX_BLOBS} blobs (point clouds + stencil stages) in one tree")
+            self.blobs.append(np.zeros((1, 0)))
+            b = len(self.blobs) - 1
+            self.stages.append(dict(blob=b, kind=2, ksize=(2, 2, 1), iterations=1, res=res))
+            post.append((oc.P_FIELD, b, []))
         elif name in ("conv_averaging", "conv_edge_detection"):
             # grid stencils (modifications.py:1586-1637): the field accumulated so far is filtered over the whole grid by
             # a separate kernel and comes back through a P_FIELD op; engine.create runs the stages in order

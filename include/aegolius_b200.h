@@ -208,10 +208,18 @@ uint64_t ab_spec_hits(void);
 /* Program-compiled kernels (aegolius_b200/codegen.py): ONE straight-line kernel per program structure, generated from
  * the flattened op list (the evaluation order of geom.py:29-60 / modifications.py:88-98 / combine.py:115-163 unrolled
  * on the host), built by nvcc into its own shared object and registered here. `signature[i]` = opcode | a << 16 |
- * b << 24 of op i, for the n_sig ops before the terminator; `flavor` 1 = the binary serves 2D grids, 0 = 3D grids and
- * point lists; `launch_fn` has the ab_spec_launch contract. Arguments still travel with every launch, so one binary
+ * b << 24 of op i, for the n_sig ops before the terminator; `flavor` bit 0 = the binary serves 2D grids (else 3D grids and
+ * point lists), bit 1 = it stores with multimem.st (ab_eval_grid_multicast); `launch_fn` has the ab_spec_launch contract. Arguments still travel with every launch, so one binary
  * serves every parameter value. ab_eval_* prefer a registered program over the interpreter tiers; results are
  * bit-identical. ab_prog_enable(0) makes them ignore the registry (returns the previous setting). */
+/* Multi-GPU field assembly without a gather pass (SURVEY §8e "optional all-gather of the assembled field"): `out_mc` /
+ * `out_grad_mc` are MULTICAST addresses of a symmetric allocation that every rank of the node has mapped (NVLS over
+ * NVSwitch), offset to this rank's slab. The rank evaluates its slab exactly like ab_eval_grid, but the kernel stores
+ * with multimem.st, so each value lands in every GPU's copy of the field. Needs a program-compiled kernel built with the
+ * multicast store path (flavor bit 1); AB_EUNSUPPORTED_OP otherwise. The caller synchronises the ranks afterwards. */
+int ab_eval_grid_multicast(const ab_program* prog, const ab_grid* grid, int dtype, int grad_mode, void* out_mc,
+                           void* out_grad_mc, uint64_t grad_stride, int device, void* stream);
+
 int ab_prog_register(const uint32_t* signature, uint32_t n_sig, int dtype, int grad_mode, int flavor, void* launch_fn,
                      uint64_t kparams_size);
 int ab_prog_clear(void);
@@ -253,6 +261,13 @@ int ab_box_filter(const void* field_dev, const uint32_t res[3], const uint32_t k
                   void* out_dev, int device, void* stream);
 /* Replaces conv_edge_detection (post_processing.py:602-623): 9u - (3x3 sum over the first two axes), 'reflect'. */
 int ab_edge_filter(const void* field_dev, const uint32_t res[3], int dtype, void* out_dev, int device, void* stream);
+/* `signed` (modifications.py:220-275): turns an unsigned distance field on a 3D grid into a signed one. boundary = field <
+ * threshold (the caller passes the smallest grid step, modifications.py:239-240); crossing parities along axes 0 and 1
+ * (forward / flipped cumulative sums, :242-258), conv_averaging((2,2,1), 1) (:260), the outer layer takes its inner
+ * neighbour (:262-263), field * (1 - 2 (interior > 1/2)) (:265-268). A field that already has a negative sample is
+ * copied through (:234-235). Every axis needs >= 3 samples. Asynchronous on `stream`; out_dev != field_dev. */
+int ab_signed_field(const void* field_dev, const uint32_t res[3], double threshold, int dtype, void* out_dev, int device,
+                    void* stream);
 
 /* Vector-field modifiers (vector_modification_functions.py:14-172; methods modifications.py:1712-1971). */
 #define AB_MAX_VEC_OPS 32
@@ -300,6 +315,8 @@ int ab_fd_gradient(const void* field, uint32_t field_plane0, const ab_grid* grid
 int ab_device_alloc(uint64_t bytes, int device, void** out_dev);
 int ab_device_free(void* dev, int device);
 int ab_host_alloc_pinned(uint64_t bytes, void** out_host);
+/* flags: bit 0 = cudaHostAllocPortable, bit 1 = cudaHostAllocWriteCombined. */
+int ab_host_alloc_pinned_flags(uint64_t bytes, unsigned flags, void** out_host);
 int ab_host_free_pinned(void* host);
 int ab_memcpy_d2h(void* dst_host, const void* src_dev, uint64_t bytes, int device, void* stream);
 int ab_memcpy_h2d(void* dst_dev, const void* src_host, uint64_t bytes, int device, void* stream);

@@ -545,6 +545,11 @@ def _run_grid_staged(prog, size, res, dims, axes, x0, x1, return_margin):
         u = u.reshape(shape)
         if st["kind"] == 0:
             u = fields_np.conv_averaging(u, tuple(st["ksize"][:dims]), st["iterations"])
+        elif st["kind"] == 2:  # signed (modifications.py:220-275); threshold = smallest grid step (:239-240)
+            thr = min(abs(a[1] - a[0]) for a in axes[:dims])
+            # a sample whose value sits on the threshold decides a whole row's crossing parity: reported as its margin
+            margin = np.minimum(margin, np.abs(u.reshape(-1) - thr))
+            u = fields_np.signed(u.reshape(-1), shape, thr)
         else:
             u = fields_np.conv_edge_detection(u)
         fields[st["blob"]] = u.reshape(-1)

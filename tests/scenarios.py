@@ -490,6 +490,97 @@ scenario("ex_olympic_rings_2D", (4.0, 2.0), (96, 48))(ex_olympic_rings)
 scenario("ex_water_molecule_2D", (3.0, 3.0), (64, 64))(ex_water_molecule)
 
 
+# the remaining example scripts SURVEY §4 lists (geometry portions, every variant of the script's switch). The repetition
+# objects are nudged off the origin: on a centred grid whole planes of samples sit exactly on the cell edges (x = 0, z = 0,
+# +-0.6 ...), where rounding decides the cell in the reference itself
+def _ex_spiral(kind):  # Code/examples/scalar/3D/spiral_instancing_3D.py:40-49
+    def build(ns):
+        box = ns.Box(0.5, 0.2, 0.3)
+        getattr(box, kind)(spiral, (1, 2, 2), (0, 1, 21))
+        return box
+    return build
+
+
+def _ex_repetition(kind):  # Code/examples/scalar/3D/finite_infinite_repetitions_3D.py:33-42
+    def build(ns):
+        box = ns.Box(1.0, 0.5, 0.25)
+        if kind == "INFINITE":
+            box.infinite_repetition((1.2, 1, 0.5))
+        elif kind == "FINITE":
+            box.finite_repetition((2., 3., 2.), (2, 3, 4))
+        else:
+            box.finite_repetition_rescaled((2., 3., 2.), (2, 3, 5), (1, 0.5, 0.25), (0.2, 0.3, 0.1))
+        box.move((0.013, 0.007, 0.011))  # not in the example: see above
+        return box
+    return build
+
+
+def ex_therefore(ns):  # Code/examples/scalar/2D/therefore_2D.py:30-31
+    thfr = ns.Circle(0.5)
+    thfr.rotational_symmetry(3, 1, np.pi / 6)
+    return thfr
+
+
+def ex_mirror_symmetry(ns):  # Code/examples/scalar/2D/mirror_symmetry_2D.py:30-32
+    circle = ns.Circle(0.5)
+    circle.mirror((-1, 0.6, 0), (1, 0.8, 0))
+    circle.symmetry(1)
+    return circle
+
+
+scenario("ex_spiral_instancing_3D_simple", (3.0, 3.0, 3.0), (20, 20, 20))(_ex_spiral("curve_instancing"))
+scenario("ex_spiral_instancing_3D_aligned", (3.0, 3.0, 3.0), (20, 20, 20))(_ex_spiral("aligned_curve_instancing"))
+scenario("ex_spiral_instancing_3D_fully_aligned", (3.0, 3.0, 3.0), (20, 20, 20))(_ex_spiral("fully_aligned_curve_instancing"))
+scenario("ex_repetitions_3D_infinite", (3.0, 3.0, 3.0), (20, 20, 20))(_ex_repetition("INFINITE"))
+scenario("ex_repetitions_3D_finite", (3.0, 3.0, 3.0), (20, 20, 20))(_ex_repetition("FINITE"))
+scenario("ex_repetitions_3D_finite_rescaled", (3.0, 3.0, 3.0), (20, 20, 20))(_ex_repetition("FINITE_RESCALED"))
+scenario("ex_therefore_2D", (4.0, 4.0), (64, 64))(ex_therefore)
+scenario("ex_mirror_symmetry_2D", (4.0, 4.0), (64, 64))(ex_mirror_symmetry)
+
+
+# signed (modifications.py:220-275): unsigned field -> signed field, a whole-grid post-pass (3D grids only)
+def _signed_sphere(ns):
+    s = ns.Sphere(1.15)
+    s.move((0.23, -0.11, 0.17))
+    s.boundary()
+    s.signed(G3[1])
+    return s
+
+
+def _signed_union(ns):  # two shells: the heuristic sees several boundary crossings per row; more ops on top of the stage
+    a = ns.Sphere(0.9)
+    a.move((-0.52, 0.13, 0.07))
+    b = ns.Box(1.3, 1.1, 1.7)
+    b.move((0.61, -0.17, -0.09))
+    u = ns.CombineGeometry("UNION2").combine(a, b)
+    u.boundary()
+    u.signed(G3B[1])
+    u.rounding(0.03)
+    return u
+
+
+def _signed_passthrough(ns):  # a field that already has negative samples is returned untouched (:234-235)
+    t = ns.Torus(1.1, 0.45)
+    t.rotate(0.6, (1, 0, 0))
+    t.signed(G3[1])
+    return t
+
+
+scenario("stencil_signed_sphere3d", *G3)(_signed_sphere)
+scenario("stencil_signed_union3d", *G3B)(_signed_union)
+scenario("stencil_signed_passthrough3d", *G3)(_signed_passthrough)
+
+
+def ex_pointcloud_terrain(ns):  # Code/examples/scalar/3D/pointcloud_terrain_3D.py:36-47, on the reference's own data file
+    cloud = np.load("/root/reference/Files/point_clouds/terrain_lr.npy")  # (3, 16384); travels inside the golden fixture
+    final = ns.PointCloud3D(cloud)
+    final.onion(0.01)
+    return final
+
+
+scenario("ex_pointcloud_terrain_3D", (2.5, 2.5, 1.5), (30, 30, 20))(ex_pointcloud_terrain)
+
+
 def make_namespace(kind):
     """kind = 'reference' (needs /root/reference or an installed spomso) or 'frontend'."""
     import types

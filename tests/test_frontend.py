@@ -69,11 +69,27 @@ def test_combine_api_errors_match_the_reference():
 
 def test_unflattenable_trees_raise_not_implemented_naming_the_culprit():
     s = ab.Sphere(1.0)
-    for name in ("custom_modification", "displacement", "define_volume", "signed", "custom_post_process"):
+    for name in ("custom_modification", "displacement", "define_volume", "custom_post_process"):
         with pytest.raises(NotImplementedError, match=name):
             getattr(s, name)(lambda *a: 0, ())
     with pytest.raises(NotImplementedError):
         ab.GenericGeometry(lambda co: co[0])
+
+
+def test_signed_becomes_a_stage_and_needs_a_3d_resolution():
+    """signed (modifications.py:220-275): a stage of kind 2 fed by the ops before it; a 2-entry co_resolution fails like the
+    reference's three-index slicing of the reshaped field does."""
+    s = ab.Sphere(1.0)
+    s.boundary()
+    s.signed((16, 12, 20))
+    s.rounding(0.1)
+    prog = ab.flatten(s)
+    assert [oc.NAMES[int(o["opcode"])] for o in prog.ops] == ["P_SPHERE", "ABS", "P_FIELD", "ROUND", "END"]
+    assert [st["kind"] for st in prog.stages] == [2] and prog.stages[0]["res"] == (16, 12, 20)
+    c = ab.Circle(1.0)
+    c.signed((16, 12))
+    with pytest.raises(IndexError):
+        ab.flatten(c)
 
 
 def test_grid_stencil_modifications_become_stages():
