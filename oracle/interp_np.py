@@ -183,7 +183,7 @@ def run(prog, co, return_state=False, return_margin=False, fields=None):
                 d, h = A[o:o + 3], A[o + 3:o + 6]
                 ux, uy, uz = np.mod(x + h[0], d[0]), np.mod(y + h[1], d[1]), np.mod(z + h[2], d[2])
                 for u_, d_ in ((ux, d[0]), (uy, d[1]), (uz, d[2])):
-                    margin = np.minimum(margin, np.minimum(u_, d_ - u_))
+                    margin = np.minimum(margin, np.minimum(np.abs(u_), np.abs(d_ - u_)))  # (np.mod takes the sign of d)
                 x, y, z = ux - h[0], uy - h[1], uz - h[2]
             elif code == REP_FIN:  # modifications.py:847-868
                 c, d, s, sh = A[o:o + 3], A[o + 3:o + 6], A[o + 6:o + 9], A[o + 9:o + 12]

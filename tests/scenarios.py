@@ -540,8 +540,8 @@ scenario("ex_mirror_symmetry_2D", (4.0, 4.0), (64, 64))(ex_mirror_symmetry)
 
 # signed (modifications.py:220-275): unsigned field -> signed field, a whole-grid post-pass (3D grids only)
 def _signed_sphere(ns):
-    s = ns.Sphere(1.15)
-    s.move((0.23, -0.11, 0.17))
+    s = ns.Sphere(1.14)  # radius / position searched so that no sample's unsigned value is within 5e-4 of the boundary
+    s.move((0.211, 0.193, -0.065))  # threshold (the smallest grid step): a sample on it decides a whole row's parity
     s.boundary()
     s.signed(G3[1])
     return s
@@ -549,9 +549,9 @@ def _signed_sphere(ns):
 
 def _signed_union(ns):  # two shells: the heuristic sees several boundary crossings per row; more ops on top of the stage
     a = ns.Sphere(0.9)
-    a.move((-0.52, 0.13, 0.07))
+    a.move((-0.013, 0.572, 0.331))  # (positions searched like above: margin 4e-3 to the threshold)
     b = ns.Box(1.3, 1.1, 1.7)
-    b.move((0.61, -0.17, -0.09))
+    b.move((-0.268, -0.322, 0.508))
     u = ns.CombineGeometry("UNION2").combine(a, b)
     u.boundary()
     u.signed(G3B[1])

@@ -28,8 +28,8 @@ def test_c5_full_1025_cubed_field_and_gradient_f32_headline_kernel():
 
     Gradient bound, fp32: the tangents go through ~15 ops in fp32 (forward mode: the same ~1e-7 relative rounding per
     operation as the value, amplified by the tree's Jacobians: the twist contributes pitch * r ~ 3 * 2, the aligned
-    instancing frames and the bend are rotations, i.e. factor 1); measured max on this sample 1.5e-4, bound 1e-3 on
-    a gradient of norm ~ 1 (the r01 bound on 4 001 random points was 5e-3)."""
+    instancing frames and the bend are rotations, i.e. factor 1); measured on this sample: max 3.1e-5, 99.99 % below
+    6.8e-6; bound 2e-4 on a gradient of norm ~ 1 (the r01 bound on 4 001 random points was 5e-3)."""
     import torch
     import aegolius_b200 as ab
     from aegolius_b200 import cabi, engine
@@ -75,7 +75,7 @@ def test_c5_full_1025_cubed_field_and_gradient_f32_headline_kernel():
     assert ok.mean() > 0.8
     err = np.abs(got_g - fd)[:, ok]
     print(f"C5 gradient vs FD of the oracle on {int(ok.sum())} nodes: max {err.max():.3e}, 99.99 % {np.quantile(err, 0.9999):.3e}")
-    assert err.max() <= 1e-3
+    assert err.max() <= 2e-4
 
 
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
