@@ -159,11 +159,43 @@ def cpu_sample(prog, spec, planes_per_worker, workers):
     return pts, wall
 
 
+def run_reference_c4(args):
+    """The reference's point-cloud path (sdf_3D.py:283-286: scipy cKDTree, one thread) on a bounded sample of C4's queries."""
+    from aegolius_b200 import workloads, GridSpec
+    from oracle import interp_np
+    cfg = workloads.CONFIGS["C4"]
+    spec = GridSpec(cfg["size"], cfg["res"])
+    cloud = cfg["cloud"]()
+    rng = np.random.default_rng(0)
+    nq = 20_000
+    co = rng.uniform(-0.5, 0.5, size=(3, nq)) * np.asarray(spec.size).reshape(3, 1)
+    tot, t_tot = 0, 0.0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        interp_np.point_cloud_distance_kdtree(co, cloud)  # builds the tree and queries, like PointCloud3D.create
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            tot += nq
+            t_tot += dt
+    value = tot / t_tot
+    sample = f"{nq} random queries in the C4 box against the 1 M-point cloud per step (cKDTree build + query, 1 thread)"
+    print(json.dumps({"impl": "reference", "metric": "grid queries/s, point cloud (1 M points) -> unsigned distance field",
+                      "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": "C4", "sample": sample},
+                      "cpu_baseline": {"value": value, "unit": "queries/s", "cores": 1, "kind": "port", "sample": sample},
+                      "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+    return 0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     os.environ.setdefault("OMP_NUM_THREADS", "1")
+    if args.workload == "C4":
+        return run_reference_c4(args)
     obj, prog, spec = _workload(args.workload)
     cores = os.cpu_count() or 1
     planes = 2
@@ -490,18 +522,115 @@ def run_gpu(args):
     return 0
 
 
+def run_gpu_c4(args):
+    """--workload C4 (BASELINE config 4): point cloud (1 M points) -> unsigned distance on the 257^3 grid. The cloud is
+    replicated with one broadcast, the query grid is sharded into x-slabs like any other field; a step is one
+    evaluation of the whole grid (octree build + packet walk per rank). e2e: the same through host buffers (cloud upload
+    and the D2H of the slab inside the timed region)."""
+    import torch
+    import torch.distributed as dist
+    import aegolius_b200 as ab
+    from aegolius_b200 import cabi, engine, workloads, distributed as abd
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    cfg = workloads.CONFIGS["C4"]
+    spec = ab.GridSpec(cfg["size"], cfg["res"])
+    cloud = cfg["cloud"]()
+    m = cloud.shape[1]
+    rec = abd.broadcast_cloud(cloud if rank == 0 else None, dim=3, dtype="f32")
+    x0, x1 = abd.rank_slab(spec.res[0], rank, world)
+    n_local = (x1 - x0) * spec.res[1] * spec.res[2]
+    out = torch.empty(n_local, dtype=torch.float32, device=dev)
+
+    def step():
+        engine.point_cloud_sdf_torch(spec, rec, slab=(x0, x1), device=local, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = cabi.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(tsum[1])
+    ms_per_step = ms / args.steps
+    ab.point_cloud_sdf(spec, cloud, dtype="f32", device=local, slab=(x0, x1))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host = ab.point_cloud_sdf(spec, cloud, dtype="f32", device=local, slab=(x0, x1))
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    cs = torch.tensor([float(host.astype(np.float64).sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        n = spec.n_points
+        print(json.dumps({
+            "metric": "grid queries/s, point cloud (1 M points) -> unsigned distance field", "value": n / (ms_per_step * 1e-3),
+            "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"C4: {m} cloud points -> {spec.res[0]}^3 query grid, exact nearest neighbour (octree packet "
+                                   f"walk, tree rebuilt every step), cloud replicated, query x-slabs", "points": n},
+            "clocks": clocks,
+            "e2e": {"value": n / float(te[0]), "unit": "queries/s", "h2d_bytes_per_step": int(cloud.nbytes),
+                    "d2h_bytes_per_step": 4 * n_local, "ms_per_step": float(te[0]) * 1e3,
+                    "note": "aegolius_b200.point_cloud_sdf(grid, cloud, slab=...) per rank: host cloud in, host field out"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32-issue", "achieved": 4.0 * n_local / (ms_per_step * 1e-3) / 1e9, "peak": _peaks()[0],
+                         "unit": "GB/s", "frac": 4.0 * n_local / (ms_per_step * 1e-3) / 1e9 / _peaks()[0], "traffic": None,
+                         "note": "tree walk: issue-bound (93 % of issue slots busy in profiles/r01_nn_tree_packet_ncu_summary.json); "
+                                 "bytes are negligible"},
+            "checksum": round(float(cs[0]), 4)}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C5", choices=["C5", "C3", "C1"])
+    ap.add_argument("--workload", default="C5", choices=["C5", "C3", "C1", "C4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the shallow-tree roofline probes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "C4":
+        return run_gpu_c4(args)
     return run_gpu(args)
 
 
