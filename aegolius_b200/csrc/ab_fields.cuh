@@ -153,31 +153,41 @@ __global__ void __launch_bounds__(256) ab_edge_kernel(const T* __restrict__ in, 
     for (int db = 0; db < 3; db++) w[da + 1][db] = p[ob[db]];
   }
   constexpr int U = 4;  // outputs per step, loads issued together (latency-bound otherwise)
-  for (uint32_t a = a0; a < a1; a += U) {
+  auto finish = [&](const T (&nw)[3]) {  // shift the window by one march step and write one output
+#pragma unroll
+    for (int db = 0; db < 3; db++) {
+      w[0][db] = w[1][db];
+      w[1][db] = w[2][db];
+      w[2][db] = nw[db];
+    }
+    T s = T(0);
+#pragma unroll
+    for (int da = 0; da < 3; da++)
+#pragma unroll
+      for (int db = 0; db < 3; db++) s = s + w[da][db];
+    *dst = T(9) * w[1][1] - s;
+    dst += sA;
+  };
+  uint32_t a = a0;
+  // whole steps whose look-ahead rows a+1 .. a+U lie inside the field: plain pointer increments, no reflection, no tail tests
+  const T* pn = col + (uint64_t)(a0 + 1) * sA;
+  for (; a + U <= a1 && a + U < nA; a += U) {
     T nw[U][3];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const T* p = col + (uint64_t)reflect_index((int)(a + u) + 1, (int)nA) * sA;
 #pragma unroll
-      for (int db = 0; db < 3; db++) nw[u][db] = a + u < a1 ? p[ob[db]] : T(0);
+      for (int db = 0; db < 3; db++) nw[u][db] = pn[ob[db]];
+      pn += sA;
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (a + u >= a1) break;
+    for (int u = 0; u < U; u++) finish(nw[u]);
+  }
+  for (; a < a1; a++) {  // the last outputs of the chunk / of the axis: reflected look-ahead row
+    const T* p = col + (uint64_t)reflect_index((int)a + 1, (int)nA) * sA;
+    T nw[3];
 #pragma unroll
-      for (int db = 0; db < 3; db++) {
-        w[0][db] = w[1][db];
-        w[1][db] = w[2][db];
-        w[2][db] = nw[u][db];
-      }
-      T s = T(0);
-#pragma unroll
-      for (int da = 0; da < 3; da++)
-#pragma unroll
-        for (int db = 0; db < 3; db++) s = s + w[da][db];
-      *dst = T(9) * w[1][1] - s;
-      dst += sA;
-    }
+    for (int db = 0; db < 3; db++) nw[db] = p[ob[db]];
+    finish(nw);
   }
 }
 

@@ -328,14 +328,11 @@ struct FDParams {
   uint64_t out_stride;
 };
 
-// np.gradient, unit spacing, edge_order=1, from the three samples along one axis
-template <typename T>
-AB_DEV T fd_three(T fm, T fc, T fp, uint32_t i, uint32_t n) {
-  if (n < 2) return T(0);
-  if (i == 0) return fp - fc;
-  if (i == n - 1) return fc - fm;
-  return (fp - fm) * T(0.5);
-}
+// np.gradient, unit spacing, edge_order=1: interior (f[i+1] - f[i-1]) / 2, faces f[1] - f[0] and f[n-1] - f[n-2]. Written as
+// (p - m) * s with the missing neighbour replaced by the centre sample and s = 1 on a face, 1/2 inside (bit-identical to
+// the three-way form, no branches): the face tests depend on the thread's (i1, i2) only and leave the plane loop.
+AB_DEV float fd_rcp(float m) { return s_rcp(m); }        // fp32: MUFU.RCP (<= 1 ulp); the tolerance is 2e-6
+AB_DEV double fd_rcp(double m) { return 1.0 / m; }       // fp64: IEEE, results match np.gradient / norm to 1e-13
 
 template <typename T>
 __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDParams<T> kp) {
@@ -345,14 +342,19 @@ __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDPa
   const uint32_t x_begin = kp.b0 + blockIdx.z * kp.chunk;
   const uint32_t x_end = x_begin + kp.chunk < kp.e0 ? x_begin + kp.chunk : kp.e0;
   const uint32_t w1 = kp.e1 - kp.b1;                  // output rows per plane
-  const uint64_t fplane = (uint64_t)(kp.n1 - kp.o1) * kp.n2;  // the buffer holds rows [o1, n1) of every plane
-  const T* __restrict__ f = kp.field + (uint64_t)(i1 - kp.o1) * kp.n2 + i2;
-  auto at = [&](uint32_t i0) { return f[(uint64_t)(i0 - kp.o0) * fplane]; };
+  const int64_t fplane = (int64_t)(kp.n1 - kp.o1) * kp.n2;  // the buffer holds rows [o1, n1) of every plane
+  // thread-constant face handling for the two in-plane axes: offsets of the neighbours (0 = use the centre) and scales
+  const int64_t d1m = i1 > 0 ? -(int64_t)kp.n2 : 0, d1p = i1 + 1 < kp.n1 ? (int64_t)kp.n2 : 0;
+  const int64_t d2m = i2 > 0 ? -1 : 0, d2p = i2 + 1 < kp.n2 ? 1 : 0;
+  const T s1 = (d1m != 0 && d1p != 0) ? T(0.5) : T(1), s2 = (d2m != 0 && d2p != 0) ? T(0.5) : T(1);
+  const T* __restrict__ pc = kp.field + (int64_t)(i1 - kp.o1) * kp.n2 + i2 + (int64_t)(x_begin - kp.o0) * fplane;  // plane x_begin
+  const uint64_t oplane = (uint64_t)w1 * kp.n2;
+  T* __restrict__ po = kp.out + ((uint64_t)(x_begin - kp.b0) * w1 + (i1 - kp.b1)) * kp.n2 + i2;
   // four planes per step with all their loads issued up front: the march is latency-bound otherwise (one DRAM load in
-  // flight per thread); U centre values ahead + 4 in-plane neighbours each = 20 independent loads per thread (U = 8 is slower: 0.70 ms)
+  // flight per thread); per plane the centre of the next plane + 4 in-plane neighbours = 20 independent loads per thread
   constexpr int U = 4;
-  T fm = T(0), fc = at(x_begin);
-  if (kp.has0 && x_begin > 0) fm = at(x_begin - 1);
+  T fc = pc[0];
+  T fm = (kp.has0 && x_begin > 0) ? pc[-fplane] : fc;  // below the grid: the centre stands in (scale 1 there)
   for (uint32_t i0 = x_begin; i0 < x_end; i0 += U) {
     T c[U + 2];  // planes i0-1 .. i0+U
     c[0] = fm;
@@ -361,42 +363,49 @@ __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDPa
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const uint32_t x = i0 + u;
-      c[u + 2] = (x + 1 < kp.n0 && x < x_end) ? at(x + 1) : T(0);
       const bool live = x < x_end;
-      const T* p = f + (uint64_t)((live ? x : x_begin) - kp.o0) * fplane;
-      a1m[u] = (live && i1 > 0) ? p[-(int64_t)kp.n2] : T(0);
-      a1p[u] = (live && i1 + 1 < kp.n1) ? p[kp.n2] : T(0);
-      a2m[u] = (live && i2 > 0) ? p[-1] : T(0);
-      a2p[u] = (live && i2 + 1 < kp.n2) ? p[1] : T(0);
+      const T* p = live ? pc + (int64_t)u * fplane : pc;  // (dead planes of the last step re-read a valid address)
+      c[u + 2] = (live && x + 1 < kp.n0) ? p[fplane] : T(0);
+      a1m[u] = p[d1m];
+      a1p[u] = p[d1p];
+      a2m[u] = p[d2m];
+      a2p[u] = p[d2p];
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const uint32_t x = i0 + u;
       if (x >= x_end) break;
-      T g0 = kp.has0 ? fd_three(c[u], c[u + 1], c[u + 2], x, kp.n0) : T(0);
-      T g1 = fd_three(a1m[u], c[u + 1], a1p[u], i1, kp.n1);
-      T g2 = fd_three(a2m[u], c[u + 1], a2p[u], i2, kp.n2);
+      const T cc = c[u + 1];
+      T g0 = T(0);
+      if (kp.has0) {
+        const bool lo = x == 0, hi = x + 1 >= kp.n0;
+        g0 = ((hi ? cc : c[u + 2]) - (lo ? cc : c[u])) * ((lo || hi) ? T(1) : T(0.5));
+      }
+      T g1 = (a1p[u] - a1m[u]) * s1;
+      T g2 = (a2p[u] - a2m[u]) * s2;
       if (kp.normalize) {
         const T m = kp.has0 ? s_sqrt(s_fma(g0, g0, s_fma(g1, g1, g2 * g2))) : s_sqrt(s_fma(g1, g1, g2 * g2));
         if (m != T(0)) {
-          const T im = T(1) / m;
+          const T im = fd_rcp(m);
           g0 *= im;
           g1 *= im;
           g2 *= im;
         }
       }
-      const uint64_t l = ((uint64_t)(x - kp.b0) * w1 + (i1 - kp.b1)) * kp.n2 + i2;
+      T* o = po + (uint64_t)u * oplane;
       if (kp.has0) {
-        __stcs(kp.out + l, g0);
-        __stcs(kp.out + kp.out_stride + l, g1);
-        __stcs(kp.out + 2 * kp.out_stride + l, g2);
+        __stcs(o, g0);
+        __stcs(o + kp.out_stride, g1);
+        __stcs(o + 2 * kp.out_stride, g2);
       } else {
-        __stcs(kp.out + l, g1);
-        __stcs(kp.out + kp.out_stride + l, g2);
+        __stcs(o, g1);
+        __stcs(o + kp.out_stride, g2);
       }
     }
     fm = c[U];
     fc = c[U + 1];
+    pc += (int64_t)U * fplane;
+    po += (uint64_t)U * oplane;
   }
 }
 

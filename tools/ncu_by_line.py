@@ -15,7 +15,10 @@ def main():
     import os
     obj = os.path.abspath(obj)
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    import os as _os
+    sel = ["-k", "regex:" + _os.environ["NCU_K"]] if _os.environ.get("NCU_K") else []  # pick one kernel of a multi-kernel report
+    sel += ["--launch-count", "1"] if sel else []
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     iex, isrc, ist = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)")
@@ -28,22 +31,30 @@ def main():
     lines = []
     infunc = False
     cur = "?"
+    fresh, chain = True, []
     for l in dis.splitlines():
         if l.startswith(".text."):
             infunc = kname in l
             continue
         if not infunc:
             continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', l)
+        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
-            inl = re.findall(r'inlined at "([^"]+)", line (\d+)', m.group(3))
-            cur = f"{m.group(1).split('/')[-1]}:{m.group(2)}"
-            if inl:
-                cur += " <- " + " <- ".join(f"{a.split('/')[-1]}:{b}" for a, b in inl[-2:])
+            # one line per frame, innermost first: "File A, line n inlined at B, line m" / "File B, line m inlined at C ..."
+            frame = f"{m.group(1).split('/')[-1]}:{m.group(2)}"
+            if fresh:
+                chain = [frame]
+                fresh = False
+            else:
+                chain.append(frame)
+            tail = re.search(r'inlined at "([^"]+)", line (\d+)', l)
+            outer = f"{tail.group(1).split('/')[-1]}:{tail.group(2)}" if tail else None
+            cur = " <- ".join(chain + ([outer] if outer else []))
             continue
         m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*?);", l)
         if m:
             lines.append((cur, m.group(2).strip()))
+            fresh = True
     if len(lines) != len(counts):
         print(f"warning: {len(lines)} disassembled vs {len(counts)} profiled instructions", file=sys.stderr)
     agg = collections.Counter()
