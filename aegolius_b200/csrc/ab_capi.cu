@@ -1180,7 +1180,11 @@ static int fd_t(const void* field, uint32_t plane0, const ab_grid* grid, int dim
   // odd row lengths (129, 513, 1025 ...): spread the warps of a row evenly over its CTAs
   const uint32_t warps = (kp.n2 + 31) / 32, ctas = (warps + 7) / 8;
   const int nt = (int)((warps + ctas - 1) / ctas) * 32;
-  ab_fd_kernel<T><<<dim3(ctas, rows, chunks), nt, 0, st>>>(kp);
+  const dim3 fgrid(ctas, rows, chunks);
+  if (three && normalize) ab_fd_kernel<T, true, true><<<fgrid, nt, 0, st>>>(kp);
+  else if (three) ab_fd_kernel<T, true, false><<<fgrid, nt, 0, st>>>(kp);
+  else if (normalize) ab_fd_kernel<T, false, true><<<fgrid, nt, 0, st>>>(kp);
+  else ab_fd_kernel<T, false, false><<<fgrid, nt, 0, st>>>(kp);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return AB_OK;

@@ -334,7 +334,8 @@ struct FDParams {
 AB_DEV float fd_rcp(float m) { return s_rcp(m); }        // fp32: MUFU.RCP (<= 1 ulp); the tolerance is 2e-6
 AB_DEV double fd_rcp(double m) { return 1.0 / m; }       // fp64: IEEE, results match np.gradient / norm to 1e-13
 
-template <typename T>
+// HAS0 / NORM: kp.has0 / kp.normalize as compile-time switches (the launcher picks the instantiation)
+template <typename T, bool HAS0, bool NORM>
 __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDParams<T> kp) {
   const uint32_t i2 = blockIdx.x * blockDim.x + threadIdx.x;
   if (i2 >= kp.n2) return;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDPa
   // flight per thread); per plane the centre of the next plane + 4 in-plane neighbours = 20 independent loads per thread
   constexpr int U = 4;
   T fc = pc[0];
-  T fm = (kp.has0 && x_begin > 0) ? pc[-fplane] : fc;  // below the grid: the centre stands in (scale 1 there)
+  T fm = (HAS0 && x_begin > 0) ? pc[-fplane] : fc;  // below the grid: the centre stands in (scale 1 there)
   for (uint32_t i0 = x_begin; i0 < x_end; i0 += U) {
     T c[U + 2];  // planes i0-1 .. i0+U
     c[0] = fm;
@@ -377,14 +378,14 @@ __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDPa
       if (x >= x_end) break;
       const T cc = c[u + 1];
       T g0 = T(0);
-      if (kp.has0) {
+      if (HAS0) {
         const bool lo = x == 0, hi = x + 1 >= kp.n0;
         g0 = ((hi ? cc : c[u + 2]) - (lo ? cc : c[u])) * ((lo || hi) ? T(1) : T(0.5));
       }
       T g1 = (a1p[u] - a1m[u]) * s1;
       T g2 = (a2p[u] - a2m[u]) * s2;
-      if (kp.normalize) {
-        const T m = kp.has0 ? s_sqrt(s_fma(g0, g0, s_fma(g1, g1, g2 * g2))) : s_sqrt(s_fma(g1, g1, g2 * g2));
+      if (NORM) {
+        const T m = HAS0 ? s_sqrt(s_fma(g0, g0, s_fma(g1, g1, g2 * g2))) : s_sqrt(s_fma(g1, g1, g2 * g2));
         if (m != T(0)) {
           const T im = fd_rcp(m);
           g0 *= im;
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDPa
         }
       }
       T* o = po + (uint64_t)u * oplane;
-      if (kp.has0) {
+      if (HAS0) {
         __stcs(o, g0);
         __stcs(o + kp.out_stride, g1);
         __stcs(o + 2 * kp.out_stride, g2);
