@@ -268,6 +268,7 @@ constexpr int kNT = @NT@;
 constexpr bool kTables = @TABLES@;
 constexpr int kIs2D = @IS2D@;  // grid flavour this binary serves: 0 = 3D grids and point lists, 1 = 2D grids
 constexpr int kNP = @NP@, kNV = @NV@;  // shared-memory slot columns (0 when the slots live in registers)
+constexpr bool kCompact = @COMPACT@;  // compact 16 x 16 tiles (3D grids) instead of the flat walk
 constexpr bool kStage8 = @STAGE8@;    // Pack<float, 8> results leave through the per-warp transposition (store_pack_w8_transposed)
 
 __global__ void __launch_bounds__(kNT, @MINCTAS@) ab_prog_kernel(const __grid_constant__ KParams<ProgT> kp) {
@@ -284,16 +285,8 @@ __global__ void __launch_bounds__(kNT, @MINCTAS@) ab_prog_kernel(const __grid_co
     for (uint32_t i = threadIdx.x; i < kp.n_args; i += kNT) s_args[i] = kp.args[i];
     __syncthreads();
   }
-  const uint32_t tile_pts = (uint32_t)kNT * W;
-  const uint32_t n32 = (uint32_t)kp.n;
-  const uint32_t n_tiles = (n32 + tile_pts - 1) / tile_pts;
-  TileWalk walk;
-  tile_walk_begin(kp, tile_pts, (uint32_t)W, walk);
   double loss_sum = 0.0, dloss_sum = 0.0;  // loss mode only (parameter-tangent kernels)
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t idx = tile * tile_pts + threadIdx.x * W;
-    P cx, cy, cz;
-    tile_coords<kIs2D>(kp, walk, idx, n32, cx, cy, cz);
+@LOOPHEAD@
     Pt<S> p;
     seed(p, cx, cy, cz);
     S acc = constant_like(p.x, T(0));
@@ -354,14 +347,24 @@ AB_PROG_EXPORT int ab_prog_launch(const void* kparams, int sms, unsigned long lo
     return (int)cudaSuccess;
   }
   const uint64_t tile_pts = (uint64_t)kNT * ProgS::width;
-  const uint64_t n_tiles = (kp.n + tile_pts - 1) / tile_pts;
+  const uint32_t nb1 = (kp.g.n1 + kTileRows - 1) / kTileRows, nb2 = (kp.g.n2 + kTileCols - 1) / kTileCols;
+  if (kCompact && (!kp.grid_mode || kp.g.is2d || kp.n % kp.g.plane)) {
+    *status = AB_EINVAL;  // (run_program only sends whole planes of 3D grids here)
+    return (int)cudaSuccess;
+  }
+  const uint64_t n_tiles = kCompact ? (kp.n / kp.g.plane) * nb1 * nb2 : (kp.n + tile_pts - 1) / tile_pts;
   const uint64_t resident = (uint64_t)sms * occ;  // persistent CTAs: a whole number of resident waves
   const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
   KParams<ProgT>& k = const_cast<KParams<ProgT>&>(kp);
   k.off_args = (uint32_t)(args_bytes + stack_bytes);  // the staged arguments sit at offset 0; this field carries the store stage
   k.off_pstack = (uint32_t)args_bytes;
   k.off_vstack = (uint32_t)(args_bytes + (size_t)sizeof(typename SK::P) * SK::cols * kNP * 3 * kNT);
-  if (kp.grid_mode) {
+  if (kCompact) {  // gridDim.x tiles decomposed over (planes, row blocks, column blocks)
+    k.tile_stride[0] = grid / (nb1 * nb2);
+    const uint32_t rem = grid % (nb1 * nb2);
+    k.tile_stride[1] = rem / nb2;
+    k.tile_stride[2] = rem % nb2;
+  } else if (kp.grid_mode) {
     const uint64_t d = (uint64_t)grid * tile_pts;
     k.tile_stride[0] = (uint32_t)(d / kp.g.plane);
     const uint64_t rem = d % kp.g.plane;
@@ -385,8 +388,10 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
         raise ValueError("empty program")
     grad = grad or "none"
     kind, T, K, param = KINDS[(dtype, grad)]
-    o = dict(slots="reg", nt=128, is2d=0, store=0, stage8=False, multicast=False)
+    o = dict(slots="reg", nt=128, is2d=0, store=0, stage8=False, multicast=False, compact=False)
     o.update(default_options(sig, dtype, grad))
+    if opts.get("compact"):  # measured (profiles/r02_jit_sweep.md): C5 field + gradient 19.7 -> 18.8 ms, C3 value 1.82 -> 1.44 ms
+        o.update(width=2, min_ctas=8, stage8=False)
     o.update({k: v for k, v in opts.items() if v is not None})
     if o["multicast"]:
         o["store"] = 4  # multimem.st: `out` is a multicast address (ab_eval_grid_multicast)
@@ -411,14 +416,39 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
            "T": T, "S": S, "PARAM": "true" if param else "false", "NT": int(o["nt"]),
            "TABLES": "true" if em.tables else "false", "NP": em.n_p if o["slots"] == "smem" else 0,
            "NV": em.n_v if o["slots"] == "smem" else 0, "MINCTAS": int(o["min_ctas"]), "IS2D": int(bool(o["is2d"])), "STOREPOLICY": int(o["store"]),
-           "FLAVOR": int(bool(o["is2d"])) | (2 if o["multicast"] else 0),
+           "FLAVOR": int(bool(o["is2d"])) | (2 if o["multicast"] else 0) | (4 if o["compact"] else 0),
            "STAGE8": "true" if (o["stage8"] and W == 8 and K == 0 and T == "float") else "false", "DECLS": "\n".join(decls),
            "BODY": "\n".join(em.lines), "KIND": kind}
-    if rep["STAGE8"] == "true":
+    flat_head = """  const uint32_t tile_pts = (uint32_t)kNT * W;
+  const uint32_t n32 = (uint32_t)kp.n;
+  const uint32_t n_tiles = (n32 + tile_pts - 1) / tile_pts;
+  TileWalk walk;
+  tile_walk_begin(kp, tile_pts, (uint32_t)W, walk);
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t idx = tile * tile_pts + threadIdx.x * W;
+    P cx, cy, cz;
+    tile_coords<kIs2D>(kp, walk, idx, n32, cx, cy, cz);"""
+    compact_head = """  // compact tiles: kTileRows x kTileCols points of one i0 plane per CTA (ab_interp.cuh), 3D grids only
+  const uint32_t nb1 = (kp.g.n1 + kTileRows - 1) / kTileRows, nb2 = (kp.g.n2 + kTileCols - 1) / kTileCols;
+  const uint32_t n_tiles = (uint32_t)(kp.n / kp.g.plane) * nb1 * nb2;
+  CompactWalk walk;
+  compact_walk_begin(kp, nb1, nb2, walk);
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t idx;
+    bool valid0, valid1;
+    P cx, cy, cz;
+    compact_coords(kp, walk, nb1, nb2, cx, cy, cz, idx, valid0, valid1);"""
+    rep["LOOPHEAD"] = compact_head if o["compact"] else flat_head
+    rep["COMPACT"] = "true" if o["compact"] else "false"
+    if o["compact"]:
+        rep["EMIT"] = "    emit_compact(kp, acc, idx, valid0, valid1);"
+    elif rep["STAGE8"] == "true":
         rep["EMIT"] = ("    float4* stage = reinterpret_cast<float4*>(smem_raw + kp.off_args) + (threadIdx.x >> 5) * 64;\n"
                        "    store_pack_w8_transposed(kp.out, acc, tile * tile_pts + (threadIdx.x & ~31u) * W, kp.n, aligned, stage);")
     else:
         rep["EMIT"] = "    emit(kp, acc, idx, aligned);"
+    if o["compact"] and not (W == 2 and not param and int(o["nt"]) == 128 and not o["is2d"]):
+        raise ValueError("compact tiles: 2 points per thread, 128 threads, 3D grids, value / spatial-gradient kernels")
     src = _TEMPLATE
     for k, v in rep.items():
         src = src.replace(f"@{k}@", str(v))
@@ -554,6 +584,13 @@ def compilable(prog) -> bool:
                                                     for w in sig)
 
 
+def wants_compact_tiles(sig, dtype, grad, is2d) -> bool:
+    """fp32 programs with a warp-cooperative op (nearest curve instance) on a 3D grid: a compact-tile build (2 points per
+    thread, 16 x 16 tiles) is registered beside the flat one, which keeps serving point lists."""
+    return (dtype == "f32" and grad in ("none", "spatial") and not is2d and
+            any((int(w) & 0xffff) == oc.CURVE_INST for w in sig))
+
+
 def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, multicast=False, **opts):
     """Makes the compiled kernel of `prog`'s structure available to the library. Returns True when it is registered on
     return, False when the interpreter serves this call (build in flight, disabled, too long a program, failed build).
@@ -565,7 +602,14 @@ def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, multicast=False, 
         ("f32" if np.dtype(dtype) == np.float32 else "f64")
     grad = _GRAD_NAMES[grad]
     sig = signature(prog)
-    is2d = int(bool(is2d)) | (2 if multicast else 0)  # from here on: the flavour bits
+    if opts.get("compact") is None and not opts.get("_no_compact") and wants_compact_tiles(sig, dtype, grad, is2d):
+        # two binaries for this structure: compact tiles for 3D grids, the flat walk for point lists
+        ensure(prog, dtype, grad, is2d, how, multicast, compact=True, **opts)
+        opts = dict(opts, _no_compact=True)
+    opts.pop("_no_compact", None)
+    if opts.get("compact") is None:
+        opts.pop("compact", None)
+    is2d = int(bool(is2d)) | (2 if multicast else 0) | (4 if opts.get("compact") else 0)  # from here on: the flavour bits
     if multicast:
         opts = dict(opts, multicast=True)
     key = _key(sig, dtype, grad, is2d)
@@ -639,11 +683,14 @@ def prebuild(items, jobs=None, verbose=False):
         if key in seen:
             continue
         seen.add(key)
-        src = generate(sig, dtype, grad, is2d=is2d)
-        if os.path.exists(binary_path(src)):
-            cached += 1
-        else:
-            todo.append(src)
+        srcs = [generate(sig, dtype, grad, is2d=is2d)]
+        if wants_compact_tiles(sig, dtype, grad, is2d):
+            srcs.append(generate(sig, dtype, grad, is2d=is2d, compact=True))
+        for src in srcs:
+            if os.path.exists(binary_path(src)):
+                cached += 1
+            else:
+                todo.append(src)
     old, _build_slots = _build_slots, threading.Semaphore(jobs)
     failed = []
 

@@ -392,7 +392,8 @@ static int dispatch_spec(ab_spec_fn fn, const KParams<T>& kp, int device, cudaSt
 // run_program prefers it over the interpreter tiers. Same op bodies, same arithmetic: results are bit-identical.
 struct ProgEntry {
   int dtype, grad_mode;  // grad_mode | flavor << 8; flavor bit 0: the binary serves 2D grids (else 3D grids and point lists),
-                         // bit 1: it stores through multimem.st (outputs are multicast addresses, ab_eval_grid_multicast)
+                         // bit 1: it stores through multimem.st (outputs are multicast addresses, ab_eval_grid_multicast),
+                         // bit 2: compact 16 x 16 tiles (whole planes of 3D grids only; preferred there when registered)
   std::vector<uint32_t> sig;
   ab_spec_fn fn;
 };
@@ -423,7 +424,7 @@ extern "C" int ab_prog_register(const uint32_t* signature, uint32_t n_sig, int d
   if (!signature || n_sig == 0 || n_sig > AB_MAX_OPS || !launch_fn) return fail(AB_EINVAL, "bad compiled-program descriptor");
   if (dtype != AB_F32 && dtype != AB_F64) return fail(AB_EINVAL, "bad dtype %d", dtype);
   if (grad_mode != AB_GRAD_NONE && grad_mode != AB_GRAD_SPATIAL && grad_mode != AB_GRAD_PARAM) return fail(AB_EINVAL, "bad grad_mode %d", grad_mode);
-  if (flavor < 0 || flavor > 3) return fail(AB_EINVAL, "bad flavor %d", flavor);
+  if (flavor < 0 || flavor > 7 || ((flavor & 4) && (flavor & 1))) return fail(AB_EINVAL, "bad flavor %d", flavor);
   grad_mode |= flavor << 8;
   const uint64_t want = dtype == AB_F32 ? sizeof(KParams<float>) : sizeof(KParams<double>);
   if (kparams_size != want) return fail(AB_EINVAL, "compiled program built against another library version (KParams %llu != %llu bytes)", (unsigned long long)kparams_size, (unsigned long long)want);
@@ -632,8 +633,11 @@ static int run_program(const ab_program* prog, const EvalTarget<T>& tg, int grad
   }
 
   // a registered program-specialised kernel that covers every op of this program takes precedence over the tiers
-  const ab_spec_fn compiled = find_prog(prog, kp.n_ops, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode,
-                                           ((tg.grid_mode && tg.g.is2d) ? 1 : 0) | (tg.multicast ? 2 : 0));
+  const int base_flavor = ((tg.grid_mode && tg.g.is2d) ? 1 : 0) | (tg.multicast ? 2 : 0);
+  ab_spec_fn compiled = nullptr;
+  if (tg.grid_mode && !tg.g.is2d && !loss_mode)  // whole planes of a 3D grid: the compact-tile build, if there is one
+    compiled = find_prog(prog, kp.n_ops, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode, base_flavor | 4);
+  if (!compiled) compiled = find_prog(prog, kp.n_ops, sizeof(T) == 4 ? AB_F32 : AB_F64, grad_mode, base_flavor);
   if (tg.multicast && !compiled)
     return fail(AB_EUNSUPPORTED_OP, "no multicast-store kernel is registered for this program structure (build it with "
                 "aegolius_b200.codegen.ensure(..., multicast=True)); the interpreter tiers store to one GPU only");

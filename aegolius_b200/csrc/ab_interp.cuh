@@ -441,6 +441,71 @@ AB_DEV void emit(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint32_t 
   for (int k = 0; k < K; k++) store_pack(kp.grad + (uint64_t)k * kp.grad_stride, acc.d[k], idx, kp.n, ga);
 }
 
+// ---- compact tiles (program-compiled kernels with warp-cooperative ops, 3D grids) ---------------------------------------------
+// The flat walk above gives a warp 32 W CONSECUTIVE points: a 0.37-long needle on the 1025^3 headline grid. Warp-
+// cooperative ops (nearest curve instance: candidates = instances within d_min + 2 R of the warp's reference point, R = warp
+// radius) want a small R. Here a CTA of 128 threads owns a tile of TR rows (i1) x TC columns (i2) of one i0 plane, W = 2
+// points per thread along i2; a warp covers 4 rows x 16 columns (R is ~4x smaller), a thread's points never straddle a
+// row, stores are 8-byte (two scalar stores where the row start is odd). Tiles over the edge of the grid are masked.
+constexpr uint32_t kTileRows = 16, kTileCols = 16;
+struct CompactWalk {
+  uint32_t b0, b1, b2;  // tile coordinates: i0 plane (local to the launch), row block, column block
+};
+template <typename T>
+AB_DEV void compact_walk_begin(const KParams<T>& kp, uint32_t nb1, uint32_t nb2, CompactWalk& w) {
+  const uint32_t t = blockIdx.x;
+  w.b0 = t / (nb1 * nb2);
+  const uint32_t rem = t - w.b0 * (nb1 * nb2);
+  w.b1 = rem / nb2;
+  w.b2 = rem - w.b1 * nb2;
+}
+// coordinates of this thread's two points of the current tile, their flat index in the launch's output and validity; then
+// the step to the CTA's next tile (tile_stride[] = gridDim.x decomposed over (plane blocks, row blocks, column blocks))
+template <typename T>
+AB_DEV void compact_coords(const KParams<T>& kp, CompactWalk& w, uint32_t nb1, uint32_t nb2, Pack<T, 2>& cx, Pack<T, 2>& cy,
+                           Pack<T, 2>& cz, uint32_t& idx, bool& valid0, bool& valid1) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i1 = w.b1 * kTileRows + warp * 4 + (lane >> 3), i2 = w.b2 * kTileCols + (lane & 7) * 2;
+  valid0 = i1 < kp.g.n1 && i2 < kp.g.n2;
+  valid1 = valid0 && i2 + 1 < kp.g.n2;
+  const uint32_t c1 = i1 < kp.g.n1 ? i1 : kp.g.n1 - 1, c2 = i2 < kp.g.n2 ? i2 : kp.g.n2 - 1;  // (the run may reach one sample past the row)
+  cx = Pack<T, 2>(grid_coord(kp.g, 0, w.b0 + kp.g.i0_begin, T()));
+  cy = Pack<T, 2>(grid_coord(kp.g, 1, c1, T()));
+  grid_coord_run(kp.g, 2, (int32_t)c2, cz);  // (masked lanes evaluate a clamped, valid position; their results are dropped)
+  idx = (w.b0 * kp.g.n1 + i1) * kp.g.n2 + i2;
+  w.b2 += kp.tile_stride[2];
+  if (w.b2 >= nb2) {
+    w.b2 -= nb2;
+    w.b1++;
+  }
+  w.b1 += kp.tile_stride[1];
+  if (w.b1 >= nb1) {
+    w.b1 -= nb1;
+    w.b0++;
+  }
+  w.b0 += kp.tile_stride[0];
+}
+template <typename T>
+AB_DEV void store2_masked(T* dst, const Pack<T, 2>& v, uint32_t idx, bool valid0, bool valid1) {
+  T* p = dst + idx;
+  if (valid1 && (reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0) {
+    store_pack(dst, v, idx, (uint64_t)idx + 2, true);
+  } else {
+    if (valid0) ab_st(p, v.v[0]);
+    if (valid1) ab_st(p + 1, v.v[1]);
+  }
+}
+template <typename T>
+AB_DEV void emit_compact(const KParams<T>& kp, const Pack<T, 2>& acc, uint32_t idx, bool valid0, bool valid1) {
+  store2_masked(kp.out, acc, idx, valid0, valid1);
+}
+template <typename T, int K>
+AB_DEV void emit_compact(const KParams<T>& kp, const Dual<Pack<T, 2>, K>& acc, uint32_t idx, bool valid0, bool valid1) {
+  store2_masked(kp.out, acc.v, idx, valid0, valid1);
+#pragma unroll
+  for (int k = 0; k < K; k++) store2_masked(kp.grad + (uint64_t)k * kp.grad_stride, acc.d[k], idx, valid0, valid1);
+}
+
 // P_FIELD: the value of a precomputed per-point field (the output of a grid stencil), indexed like `out`
 template <typename T, int W>
 AB_DEV void load_field(const void* field, uint32_t idx, uint64_t n, Pack<T, W>& out) {

@@ -209,7 +209,8 @@ uint64_t ab_spec_hits(void);
  * the flattened op list (the evaluation order of geom.py:29-60 / modifications.py:88-98 / combine.py:115-163 unrolled
  * on the host), built by nvcc into its own shared object and registered here. `signature[i]` = opcode | a << 16 |
  * b << 24 of op i, for the n_sig ops before the terminator; `flavor` bit 0 = the binary serves 2D grids (else 3D grids and
- * point lists), bit 1 = it stores with multimem.st (ab_eval_grid_multicast); `launch_fn` has the ab_spec_launch contract. Arguments still travel with every launch, so one binary
+ * point lists), bit 1 = it stores with multimem.st (ab_eval_grid_multicast), bit 2 = compact 16 x 16 tiles (whole planes of
+ * 3D grids only; preferred there); `launch_fn` has the ab_spec_launch contract. Arguments still travel with every launch, so one binary
  * serves every parameter value. ab_eval_* prefer a registered program over the interpreter tiers; results are
  * bit-identical. ab_prog_enable(0) makes them ignore the registry (returns the previous setting). */
 /* Multi-GPU field assembly without a gather pass (SURVEY §8e "optional all-gather of the assembled field"): `out_mc` /

@@ -30,6 +30,22 @@ def pytest_sessionstart(session):
             build.build(verbose=False)
         except Exception as e:  # pragma: no cover
             print(f"[conftest] could not build libaegolius_b200.so: {e}")
+    # Safety net for the kernel cache (git-ignored build output, normally shipped with the tree by __graft_entry__.build()):
+    # on a GPU box whose snapshot lacks it, build it once here with that box's nvcc instead of letting every test that
+    # expects the program-compiled kernels fail.
+    try:
+        if cabi.device_count() > 0 and _jit_cache_is_missing():
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import prebuild_jit
+            print("[conftest] aegolius_b200/jit/ is empty: building the program-compiled kernels (nvcc) ...")
+            prebuild_jit.main(verbose=True)
+    except Exception as e:  # pragma: no cover
+        print(f"[conftest] could not prebuild the kernel cache: {e}")
+
+
+def _jit_cache_is_missing():
+    d = os.path.join(ROOT, "aegolius_b200", "jit")
+    return not os.path.isdir(d) or sum(f.endswith(".so") for f in os.listdir(d)) < 100
 
 
 def has_cuda():

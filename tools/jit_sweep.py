@@ -175,7 +175,8 @@ def main():
         if not os.path.exists(path):
             print(json.dumps({"case": name, "opts": o, "error": "not prebuilt"}), flush=True)
             continue
-        cg._register(path, sig, dtype, cg._GRAD_NAMES[grad], engine._is_2d(spec))
+        lib.ab_prog_clear()  # one variant at a time (a compact-tile build would otherwise stay preferred)
+        cg._register(path, sig, dtype, cg._GRAD_NAMES[grad], int(engine._is_2d(spec)) | (4 if o.get("compact") else 0))
         h0 = lib.ab_prog_hits()
         try:
             ms, out = timed(prog, spec, dtype, grad)
