@@ -347,7 +347,7 @@ AB_PROG_EXPORT int ab_prog_launch(const void* kparams, int sms, unsigned long lo
     return (int)cudaSuccess;
   }
   const uint64_t tile_pts = (uint64_t)kNT * ProgS::width;
-  const uint32_t nb1 = (kp.g.n1 + kTileRows - 1) / kTileRows, nb2 = (kp.g.n2 + kTileCols - 1) / kTileCols;
+  const uint32_t nb1 = (kp.g.n1 + kTileRows - 1) / kTileRows, nb2 = compact_col_blocks(kp.g.n2);
   if (kCompact && (!kp.grid_mode || kp.g.is2d || kp.n % kp.g.plane)) {
     *status = AB_EINVAL;  // (run_program only sends whole planes of 3D grids here)
     return (int)cudaSuccess;
@@ -429,7 +429,7 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
     P cx, cy, cz;
     tile_coords<kIs2D>(kp, walk, idx, n32, cx, cy, cz);"""
     compact_head = """  // compact tiles: kTileRows x kTileCols points of one i0 plane per CTA (ab_interp.cuh), 3D grids only
-  const uint32_t nb1 = (kp.g.n1 + kTileRows - 1) / kTileRows, nb2 = (kp.g.n2 + kTileCols - 1) / kTileCols;
+  const uint32_t nb1 = (kp.g.n1 + kTileRows - 1) / kTileRows, nb2 = compact_col_blocks(kp.g.n2);
   const uint32_t n_tiles = (uint32_t)(kp.n / kp.g.plane) * nb1 * nb2;
   CompactWalk walk;
   compact_walk_begin(kp, nb1, nb2, walk);
@@ -587,7 +587,7 @@ def compilable(prog) -> bool:
 def wants_compact_tiles(sig, dtype, grad, is2d) -> bool:
     """fp32 programs with a warp-cooperative op (nearest curve instance) on a 3D grid: a compact-tile build (2 points per
     thread, 16 x 16 tiles) is registered beside the flat one, which keeps serving point lists."""
-    return (dtype == "f32" and grad in ("none", "spatial") and not is2d and
+    return (os.environ.get("AB_JIT_COMPACT", "1") != "0" and dtype == "f32" and grad in ("none", "spatial") and not is2d and
             any((int(w) & 0xffff) == oc.CURVE_INST for w in sig))
 
 

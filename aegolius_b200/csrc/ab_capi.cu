@@ -854,7 +854,7 @@ extern "C" int ab_eval_grid_host(const ab_program* prog, const ab_grid* grid, in
   const uint64_t total_planes = grid->slab_end - grid->slab_begin;
   if (planes_per_chunk > total_planes) planes_per_chunk = total_planes;
   const uint64_t chunk_pts = planes_per_chunk * plane;
-  const uint64_t dstride = (chunk_pts + 3) & ~3ull;
+  const uint64_t dstride = (chunk_pts + 7) & ~7ull;  // rows 32-byte aligned against each other (whole-sector stores)
   void* d_out[2] = {nullptr, nullptr};
   void* d_grad[2] = {nullptr, nullptr};
   void* base = nullptr;
@@ -936,7 +936,7 @@ extern "C" int ab_eval_points_host(const ab_program* prog, const double* co_host
   const size_t es = dtype == AB_F32 ? 4 : 8;
   const int rows = grad_rows(grad_mode);
   if (rows && (!out_grad_host || grad_stride < n)) return fail(AB_EINVAL, "gradient output missing or grad_stride < n");
-  const uint64_t dstride = (n + 3) & ~3ull;
+  const uint64_t dstride = (n + 7) & ~7ull;
   void *d_out = nullptr, *d_grad = nullptr, *d_co = nullptr;
   rc = scratch(device, 0, n * es, &d_out);
   if (rc) return rc;

@@ -190,7 +190,7 @@ class MulticastField:
         device = int(os.environ.get("LOCAL_RANK", "0"))
         tdt = torch.float32 if engine._dtype(dtype)[0] == 0 else torch.float64
         n = spec.n_points
-        self.stride = (n + 3) // 4 * 4
+        self.stride = (n + 7) // 8 * 8
         total = self.stride * (4 if grad else 1)
         self.buf = symm.empty(total, dtype=tdt, device=torch.device("cuda", device))
         self.handle = symm.rendezvous(self.buf, self.group.group_name)

@@ -464,7 +464,7 @@ def create_torch(obj, spec: GridSpec, *, dtype="f32", grad=None, device=0, slab=
     field = out if out is not None else torch.empty(n, dtype=tdt, device=dev)
     gbuf, gptr, stride = None, None, 0
     if rows:
-        stride = (n + 3) // 4 * 4
+        stride = (n + 7) // 8 * 8
         gbuf = out_grad if out_grad is not None else torch.empty((rows, stride), dtype=tdt, device=dev)
         gptr, stride = gbuf.data_ptr(), gbuf.stride(0)
     cp = cabi.CProgram(prog)
@@ -493,7 +493,7 @@ def from_sdf_torch(field, co_resolution, *, slab=None, field_plane0=0, normalize
         raise ValueError(f"the field must cover planes [{lo}, {hi}) (slab plus halo); it starts at plane {field_plane0} "
                          f"and holds {field.numel() // per_plane}")
     n = (x1 - x0) * per_plane
-    stride = (n + 3) // 4 * 4
+    stride = (n + 7) // 8 * 8
     buf = out if out is not None else torch.empty((dims, stride), dtype=field.dtype, device=field.device)
     g = cabi.make_grid((0.0, 0.0, 0.0), res + ((1,) if dims == 2 else ()), (x0, x1))
     stream = torch.cuda.current_stream(field.device).cuda_stream
@@ -555,7 +555,7 @@ def from_sdf(sdf_, co_resolution, *, dtype=None, device=0, normalize=True):
                          "required.")
     lib = cabi.lib()
     d_f, d_o = C.c_void_p(), C.c_void_p()
-    stride = (n + 3) // 4 * 4
+    stride = (n + 7) // 8 * 8
     cabi.check(lib.ab_device_alloc(n * f.itemsize, device, C.byref(d_f)))
     try:
         cabi.check(lib.ab_device_alloc(dims * stride * f.itemsize, device, C.byref(d_o)))
@@ -751,7 +751,7 @@ class VectorFieldFromSDF:
             raise ValueError("Shape of array too small to calculate a numerical gradient, at least 2 elements are "
                              "required.")
         lib = cabi.lib()
-        stride = (n + 3) // 4 * 4
+        stride = (n + 7) // 8 * 8
         keep = []
         d_f, d_v = _DevBuf.upload(f, device), _DevBuf(3 * stride * f.itemsize, device)
         keep += [d_f, d_v]

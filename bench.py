@@ -266,7 +266,7 @@ def _secondary(ab, engine, cabi, prog, spec, dev, local):
         tdt = torch.float32 if dt == "f32" else torch.float64
         es = 4 if dt == "f32" else 8
         buf = torch.empty(sp.n_points, dtype=tdt, device=dev)
-        gb = torch.empty((3, (sp.n_points + 3) // 4 * 4), dtype=tdt, device=dev) if gr else None
+        gb = torch.empty((3, (sp.n_points + 7) // 8 * 8), dtype=tdt, device=dev) if gr else None
         engine.create_torch(pg, sp, dtype=dt, grad=gr, device=local, out=buf, out_grad=gb)
         engine.wait_for_compilations()
         h0 = lib.ab_prog_hits()
@@ -281,7 +281,7 @@ def _secondary(ab, engine, cabi, prog, spec, dev, local):
         torch.cuda.empty_cache()
     # the interpreter on the headline step (what runs while a new structure's kernel is being built)
     fbuf = torch.empty(n5, dtype=torch.float32, device=dev)
-    gbuf = torch.empty((3, (n5 + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    gbuf = torch.empty((3, (n5 + 7) // 8 * 8), dtype=torch.float32, device=dev)
     old = lib.ab_prog_enable(0)
     try:
         t = _time_device(lambda: engine.create_torch(prog, spec, dtype="f32", grad="spatial", device=local, out=fbuf,
@@ -296,7 +296,7 @@ def _secondary(ab, engine, cabi, prog, spec, dev, local):
     # whole-field kernels on a 513^3 fp32 field, algorithmic bytes per point in the key
     res = (513, 513, 513)
     n = res[0] * res[1] * res[2]
-    stride = (n + 3) // 4 * 4
+    stride = (n + 7) // 8 * 8
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     f = torch.randn(n, dtype=torch.float32, device=dev)
     o = torch.empty(n, dtype=torch.float32, device=dev)
@@ -387,7 +387,7 @@ def run_gpu(args):
     x0, x1 = slabs[rank]
     n_local = (x1 - x0) * spec.res[1] * spec.res[2]
     n_total = spec.n_points
-    stride = (n_local + 3) // 4 * 4
+    stride = (n_local + 7) // 8 * 8
     field = torch.empty(n_local, dtype=torch.float32, device=dev)
     grad = torch.empty((3, stride), dtype=torch.float32, device=dev)
     lib = cabi.lib()

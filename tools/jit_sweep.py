@@ -130,7 +130,7 @@ def main():
             bufs.clear()
             torch.cuda.empty_cache()
             bufs[key] = (torch.empty(n, dtype=tdt, device="cuda"),
-                         torch.empty((3, (n + 3) // 4 * 4), dtype=tdt, device="cuda") if grad else None)
+                         torch.empty((3, (n + 7) // 8 * 8), dtype=tdt, device="cuda") if grad else None)
         field, gbuf = bufs[key]
         out = None
         for _ in range(args.reps + 2):

@@ -74,7 +74,7 @@ def main():
             lib = cabi.lib()
             res = (513, 513, 513)
             n = res[0] * res[1] * res[2]
-            stride = (n + 3) // 4 * 4
+            stride = (n + 7) // 8 * 8
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             f = torch.randn(n, dtype=torch.float32, device=dev)
             o = torch.empty(n, dtype=torch.float32, device=dev)
@@ -116,7 +116,7 @@ def main():
         tdt = torch.float32 if dt == "f32" else torch.float64
         n = spec.n_points
         field = torch.empty(n, dtype=tdt, device=dev)
-        gbuf = torch.empty((3, (n + 3) // 4 * 4), dtype=tdt, device=dev) if grad else None
+        gbuf = torch.empty((3, (n + 7) // 8 * 8), dtype=tdt, device=dev) if grad else None
 
         def run():
             engine.create_torch(prog, spec, dtype=dt, grad=grad, out=field, out_grad=gbuf)

@@ -34,7 +34,7 @@ def main():
     torch.cuda.empty_cache()
     res = (513, 513, 513)
     n = res[0] * res[1] * res[2]
-    stride = (n + 3) // 4 * 4
+    stride = (n + 7) // 8 * 8
     f = torch.randn(n, dtype=torch.float32, device=dev)
     o = torch.empty(n, dtype=torch.float32, device=dev)
     v = torch.randn(3, stride, dtype=torch.float32, device=dev)

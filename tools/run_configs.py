@@ -54,7 +54,7 @@ def main():
                 continue
             tdt = torch.float32 if dt == "f32" else torch.float64
             field = torch.empty(n, dtype=tdt, device=dev)
-            gbuf = torch.empty((3, (n + 3) // 4 * 4), dtype=tdt, device=dev) if grad else None
+            gbuf = torch.empty((3, (n + 7) // 8 * 8), dtype=tdt, device=dev) if grad else None
             ms = gpu_time(lambda: engine.create_torch(prog, spec, dtype=dt, grad=grad, out=field, out_grad=gbuf))
             bpp = (4 if dt == "f32" else 8) * (4 if grad else 1)
             entry[f"gpu_{dt}{'_grad' if grad else ''}"] = {
