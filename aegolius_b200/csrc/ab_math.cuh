@@ -673,6 +673,18 @@ AB_DEV Dual<P, K> add_lane(const Dual<P, K>& a, const P& c) {
 }
 template <typename P, int K>
 AB_DEV P value_sign(const Dual<P, K>& a) { return sign_(a.v); }
+// a * c + b with a per-lane constant c, as explicit FMAs (written as mul_lane + operator+ the adds stay separate
+// instructions whenever the product has a second use)
+template <typename T, int W>
+AB_DEV Pack<T, W> fma_lane(const Pack<T, W>& a, const Pack<T, W>& c, const Pack<T, W>& b) { return fma_(a, c, b); }
+template <typename P, int K>
+AB_DEV Dual<P, K> fma_lane(const Dual<P, K>& a, const P& c, const Dual<P, K>& b) {
+  Dual<P, K> r;
+  r.v = fma_(a.v, c, b.v);
+#pragma unroll
+  AB_DK r.d[k] = fma_(a.d[k], c, b.d[k]);
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // shared helpers written once for both kinds of S

@@ -158,8 +158,8 @@ AB_DEV void op_rotsym(Pt<S>& p, A a) {
     c.v[i] = tab[4 + 2 * k];
     s.v[i] = tab[5 + 2 * k];
   }
-  S nx = mul_lane(p.x, c) + mul_lane(p.y, s) - rad;
-  S ny = mul_lane(p.y, c) - mul_lane(p.x, s);
+  S nx = fma_lane(p.y, s, mul_lane(p.x, c)) - rad;
+  S ny = fma_lane(p.x, -s, mul_lane(p.y, c));
   p.x = nx;
   p.y = ny;
 }
@@ -276,9 +276,9 @@ template <typename S, typename PK>
 AB_DEV void frame_change(Pt<S>& p, const PK (&r)[12], int mode) {
   S dx = add_lane(p.x, -r[0]), dy = add_lane(p.y, -r[1]), dz = add_lane(p.z, -r[2]);
   if (mode) {
-    p.x = mul_lane(dx, r[3]) + mul_lane(dy, r[4]) + mul_lane(dz, r[5]);
-    p.y = mul_lane(dx, r[6]) + mul_lane(dy, r[7]) + mul_lane(dz, r[8]);
-    p.z = mul_lane(dx, r[9]) + mul_lane(dy, r[10]) + mul_lane(dz, r[11]);
+    p.x = fma_lane(dz, r[5], fma_lane(dy, r[4], mul_lane(dx, r[3])));
+    p.y = fma_lane(dz, r[8], fma_lane(dy, r[7], mul_lane(dx, r[6])));
+    p.z = fma_lane(dz, r[11], fma_lane(dy, r[10], mul_lane(dx, r[9])));
   } else {
     p.x = dx;
     p.y = dy;
