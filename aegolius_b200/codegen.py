@@ -36,7 +36,7 @@ CSRC = os.path.join(HERE, "csrc")
 JIT_DIR = os.path.join(HERE, "jit")
 CODEGEN_VERSION = 1
 
-TABLE_OPS = (oc.ROTSYM, oc.CURVE_INST, oc.P_SEGLINE, oc.P_SEGLINE2D, oc.P_POLYGON2D)  # is_table_op() in ab_interp.cuh
+TABLE_OPS = (oc.ROTSYM, oc.CURVE_INST, oc.P_SEGLINE, oc.P_SEGLINE2D, oc.P_POLYGON2D, oc.POLY_SIGN)  # is_table_op() in ab_interp.cuh
 
 # ops without transcendental functions or tables (is_lite_op() in ab_interp.cuh): cheap per point, so more points per thread
 LITE_OPS = frozenset((
@@ -232,6 +232,12 @@ class _Emitter:
             e(f"    {{ auto a = {A}; {self.store_v(a, 'abs_(p.z) - a[0]')} p.z = constant_like(p.z, T(0)); }}")
         elif code == oc.EXTRUDE_END:
             e(f"    acc = op_extrude_end<S, T>(acc, {self.get_v(a)});")
+        elif code == oc.POLY_SIGN:
+            self.n_p = max(self.n_p, a + 1)
+            if self.slots == "smem":
+                e(f"    acc = op_poly_sign(acc, SK::ld(pstack, {3 * a}, kNT), SK::ld(pstack, {3 * a + 1}, kNT), {A}, {b});")
+            else:
+                e(f"    acc = op_poly_sign(acc, P{a}.x, P{a}.y, {A}, {b});")
         elif code in pps:
             e(f"    acc = {pps[code]}(acc, {A});")
         elif code in combines:

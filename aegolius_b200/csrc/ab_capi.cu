@@ -122,11 +122,12 @@ static int op_arg_count(const ab_op& op, const double* args, uint32_t n_args, in
       if (!(c >= 1) || c > 1024 || c != (double)(int)c) return fail(AB_EINVAL, "bad ROTSYM sector count %g", c);
       n = 4 + 2 * (int)c;
     } break;
-    case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D: {
+    case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D: case AB_OP_POLY_SIGN: {
       if (op.arg >= n_args) return fail(AB_EINVAL, "op argument offset out of range");
       double c = args[op.arg];
       if (!(c >= 0) || c > 1e6) return fail(AB_EINVAL, "bad element count %g", c);
       int per = op.opcode == AB_OP_CURVE_INST ? (op.a ? 12 : 3) : (op.opcode == AB_OP_P_SEGLINE ? 3 : 2);
+      if (op.opcode == AB_OP_POLY_SIGN) per = op.b ? 6 : 2;
       n = (op.opcode == AB_OP_CURVE_INST ? 4 : 1) + (int)c * per;
     } break;
     default: return fail(AB_EUNSUPPORTED_OP, "opcode %u is not supported by this build", (unsigned)op.opcode);
@@ -154,6 +155,10 @@ static int validate(const ab_program* prog) {
     switch (op.opcode) {
       case AB_OP_SAVE_P: case AB_OP_LOAD_P:
         if (op.a >= prog->n_pslots) return fail(AB_EINVAL, "op %u: P slot %u >= n_pslots %u", i, op.a, prog->n_pslots);
+        break;
+      case AB_OP_POLY_SIGN:
+        if (op.a >= prog->n_pslots) return fail(AB_EINVAL, "op %u: P slot %u >= n_pslots %u", i, op.a, prog->n_pslots);
+        if (op.b > 1) return fail(AB_EINVAL, "op %u: POLY_SIGN rule %u", i, op.b);
         break;
       case AB_OP_NEXT_AFFINE: case AB_OP_NEXT_TRANSLATE: case AB_OP_NEXT_LOAD:
         if (op.a >= prog->n_pslots) return fail(AB_EINVAL, "op %u: P slot %u >= n_pslots %u", i, op.a, prog->n_pslots);
@@ -276,7 +281,7 @@ static int build_tree(const typename Vec4<T>::type* cloud, uint32_t m, int dim, 
 static bool structural_arg(int opcode, int k) {
   switch (opcode) {
     case AB_OP_ROTSYM: return k != 1;  // everything but the radius
-    case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D: case AB_OP_P_TRIANGLE3D:
+    case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D: case AB_OP_POLY_SIGN: case AB_OP_P_TRIANGLE3D:
     case AB_OP_P_QUAD3D: case AB_OP_P_TRIANGLE2D: case AB_OP_P_RBOX2D:
       return true;
     case AB_OP_P_NEU_CIRCLE: return k == 1;  // the norm order

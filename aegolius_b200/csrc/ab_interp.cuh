@@ -51,7 +51,7 @@ AB_DEV void divmod_small(uint32_t t, uint32_t n, uint32_t magic, uint32_t& q, ui
 #define AB_OPLIST(X)                                                                                                   \
   X(END) X(SAVE_P) X(LOAD_P) X(PUSH_V) X(NEXT_AFFINE) X(NEXT_TRANSLATE) X(NEXT_LOAD) X(AFFINE) X(TRANSLATE) X(SCALE_P) X(ELONGATE) X(TWIST) X(BEND) X(ABSX_SUB)        \
   X(SYMMETRY) X(ROTSYM) X(REVOLVE) X(AXIS_REVOLVE) X(REP_INF) X(REP_FIN) X(LIN_INST) X(CURVE_INST) X(ZERO_Z) X(ROUND)  \
-  X(ABS) X(NEG) X(SIGN) X(ONION) X(CONCENTRIC) X(SCALE_V) X(EXTRUDE_BEGIN) X(EXTRUDE_END) X(PP_SIGMOID)                \
+  X(ABS) X(NEG) X(SIGN) X(ONION) X(CONCENTRIC) X(SCALE_V) X(EXTRUDE_BEGIN) X(EXTRUDE_END) X(POLY_SIGN) X(PP_SIGMOID)                \
   X(PP_POS_SIGMOID) X(PP_CAPPED_EXP) X(PP_HARD_BIN) X(PP_LINEAR) X(PP_RELU) X(PP_SMOOTH_RELU) X(PP_SLOWSTART)          \
   X(PP_GAUSS_BOUNDARY) X(PP_GAUSS_FALLOFF) X(C_UNION) X(C_INTERSECT) X(C_SUBTRACT) X(C_SUM) X(C_DIFF) X(C_SMIN2)       \
   X(C_SMIN3) X(C_SMAX3) X(C_SSUB3) X(C_BOLTZ_INT) X(C_BOLTZ_SUB) X(P_SPHERE) X(P_CYLINDER) X(P_BOX) X(P_TORUS)         \
@@ -834,6 +834,11 @@ __global__ void __launch_bounds__((max_threads<S, TIER>()), (big_cta<S, TIER>() 
 #if AB_SPEC_EXTRUDE_END
         case D_EXTRUDE_END: acc = op_extrude_end<S, T>(acc, SK::ld(vstack, sa, NT)); break;
 #endif
+#if AB_TIER_FULL >= 2
+        case D_POLY_SIGN:
+          acc = op_poly_sign(acc, SK::ld(pstack, sa * 3 + 0, NT), SK::ld(pstack, sa * 3 + 1, NT), a, sb);
+          break;
+#endif
         // post-processing (post_processing.py:380-560)
 #if AB_TIER_FULL
 #if AB_SPEC_PP_SIGMOID
@@ -1088,7 +1093,8 @@ cudaError_t launch_interp(const KParams<T>& kp, const LaunchCfg& cfg, cudaStream
 // ops whose argument count depends on the program (tables): the launcher packs them after the fixed-size arguments
 inline bool is_table_op(int ab_opcode) {
   switch (ab_opcode) {
-    case AB_OP_ROTSYM: case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D: return true;
+    case AB_OP_ROTSYM: case AB_OP_CURVE_INST: case AB_OP_P_SEGLINE: case AB_OP_P_SEGLINE2D: case AB_OP_P_POLYGON2D:
+    case AB_OP_POLY_SIGN: return true;
     default: return false;
   }
 }
@@ -1117,7 +1123,7 @@ inline int op_tier(int ab_opcode) {
   if (is_lite_op(ab_opcode)) return 0;
   switch (ab_opcode) {
     case AB_OP_P_SOLID_ANGLE: case AB_OP_P_SECTOR: case AB_OP_P_TRIANGLE3D: case AB_OP_P_QUAD3D: case AB_OP_P_SEGLINE:
-    case AB_OP_P_SEGLINE2D: case AB_OP_P_POINT_CLOUD: case AB_OP_P_TRIANGLE2D: case AB_OP_P_POLYGON2D:
+    case AB_OP_P_SEGLINE2D: case AB_OP_P_POINT_CLOUD: case AB_OP_P_TRIANGLE2D: case AB_OP_P_POLYGON2D: case AB_OP_POLY_SIGN:
       return 2;
     default: return 1;
   }

@@ -744,29 +744,15 @@ AB_DEV S prim_ngon(const Pt<S>& p, A a) { typedef typename S::scalar T;  // :153
   return mul_lane(len, value_sign(fma_(q0, a[4], q1 * a[5])));
 }
 
-// sdf_polygon_2d (sdf_2D.py:201-218) for simple polygons: unsigned distance = min over the closed edge loop, interior
-// by the crossing-number rule (equals the union of the reference's ear-clipping triangles,
-// triangulation_functions.py:390-430). args: n, then n (x, y) vertices.
-template <typename S, typename A>
-AB_DEV S prim_polygon2d(const Pt<S>& p, A a_) {
-  typedef typename S::scalar T;
-  constexpr int W = S::width;
-  const T* a = raw_args(a_);  // vertex table: structural
-  const int n = (int)a[0];
-  const T* pts = a + 1;
-  auto vx = value_of(p.x), vy = value_of(p.y);
-  S best = constant_like(p.x, T(1e32));
-  bool inside[W];
+// interior of a simple closed polygon by the crossing-number rule (horizontal ray towards +x, half-open in y): equals the
+// union of the reference's ear-clipping triangles (triangulation_functions.py:390-430) off the boundary
+template <typename T, int W>
+AB_DEV void polygon_inside(const Pack<T, W>& vx, const Pack<T, W>& vy, const T* pts, int n, bool (&inside)[W]) {
 #pragma unroll
-  for (int i = 0; i < W; i++) inside[i] = false;
+  for (int j = 0; j < W; j++) inside[j] = false;
   for (int i = 0; i < n; i++) {
     const int k = (i + 1 == n) ? 0 : i + 1;
     const T ax = pts[2 * i], ay = pts[2 * i + 1], bx = pts[2 * k] - ax, by = pts[2 * k + 1] - ay;
-    const T bb = s_fma(bx, bx, by * by);
-    S px = p.x - ax, py = p.y - ay;
-    S h = clamp_(fma_(px, bx, py * by) * s_rcp(bb), T(0), T(1));
-    S t0 = px - h * bx, t1 = py - h * by;
-    best = min_(best, fma_(t0, t0, t1 * t1));
 #pragma unroll
     for (int j = 0; j < W; j++) {
       const bool ca = ay > vy.v[j], cb = (ay + by) > vy.v[j];
@@ -776,10 +762,71 @@ AB_DEV S prim_polygon2d(const Pt<S>& p, A a_) {
       }
     }
   }
+}
+
+// sdf_polygon_2d (sdf_2D.py:201-218) for simple polygons: unsigned distance = min over the closed edge loop, interior
+// by the crossing-number rule. args: n, then n (x, y) vertices.
+template <typename S, typename A>
+AB_DEV S prim_polygon2d(const Pt<S>& p, A a_) {
+  typedef typename S::scalar T;
+  constexpr int W = S::width;
+  const T* a = raw_args(a_);  // vertex table: structural
+  const int n = (int)a[0];
+  const T* pts = a + 1;
+  auto vx = value_of(p.x), vy = value_of(p.y);
+  S best = constant_like(p.x, T(1e32));
+  for (int i = 0; i < n; i++) {
+    const int k = (i + 1 == n) ? 0 : i + 1;
+    const T ax = pts[2 * i], ay = pts[2 * i + 1], bx = pts[2 * k] - ax, by = pts[2 * k + 1] - ay;
+    const T bb = s_fma(bx, bx, by * by);
+    S px = p.x - ax, py = p.y - ay;
+    S h = clamp_(fma_(px, bx, py * by) * s_rcp(bb), T(0), T(1));
+    S t0 = px - h * bx, t1 = py - h * by;
+    best = min_(best, fma_(t0, t0, t1 * t1));
+  }
+  bool inside[W];
+  polygon_inside(vx, vy, pts, n, inside);
   Pack<T, W> sg;
 #pragma unroll
   for (int j = 0; j < W; j++) sg.v[j] = inside[j] ? T(-1) : T(1);
   return mul_lane(sqrt_(best), sg);
+}
+
+// POLY_SIGN: acc * interior sign evaluated at saved coordinates (x, y).
+//   rule 0: SegmentedLine.polygon() / SegmentedParametricCurve.polygon() (geom_2d.py:530-555, 601-626): interior_polygon of
+//           the control points, -1 inside / +1 outside; table: n, then n (x, y) vertices;
+//   rule 1: ParametricCurve.shape() (geom_2d.py:440-452), term by term: for every segment i of the sampled curve whose
+//           half-open x interval [lx, ux) holds the point, multiply by sign(dot(p - P_i, n_i)), n_i = (-t_y, |t_x|) (the
+//           reference takes the absolute value of the normal's y component only); table: n, then n records
+//           (P_ix, P_iy, lx, ux, n_ix, n_iy).
+template <typename S, typename A>
+AB_DEV S op_poly_sign(const S& acc, const S& sx, const S& sy, A a_, int rule) {
+  typedef typename S::scalar T;
+  constexpr int W = S::width;
+  const T* a = raw_args(a_);
+  const int n = (int)a[0];
+  auto vx = value_of(sx), vy = value_of(sy);
+  Pack<T, W> sg;
+  if (rule == 0) {
+    bool inside[W];
+    polygon_inside(vx, vy, a + 1, n, inside);
+#pragma unroll
+    for (int j = 0; j < W; j++) sg.v[j] = inside[j] ? T(-1) : T(1);
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; j++) sg.v[j] = T(1);
+    for (int i = 0; i < n; i++) {
+      const T* r = a + 1 + 6 * i;
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        if (vx.v[j] >= r[2] && vx.v[j] < r[3]) {
+          const T d = s_fma(vx.v[j] - r[0], r[4], (vy.v[j] - r[1]) * r[5]);
+          sg.v[j] = sg.v[j] * (d > T(0) ? T(1) : (d < T(0) ? T(-1) : T(0)));
+        }
+      }
+    }
+  }
+  return mul_lane(acc, sg);
 }
 
 }  // namespace ab

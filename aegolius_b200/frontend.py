@@ -637,8 +637,14 @@ class _SegmentedParametricBase(GenericGeometry):
 
 
 class SegmentedParametricCurve(_SegmentedParametricBase):
-    """geom_2d.py:460-528 (without .polygon(), which needs a grid-wide test)."""
+    """geom_2d.py:460-555."""
     _dim = 2
+
+    def polygon(self):
+        """geom_2d.py:530-555: closed curve -> polygon, d * interior_polygon(co, control points)."""
+        if not self.closed:
+            return self
+        return self._add("polygon", points=self._points.copy())
 
     @property
     def ts(self):  # geom_2d.py:519-523
@@ -741,7 +747,7 @@ class Polygon(GenericGeometry):
 
 
 class ParametricCurve(GenericGeometry):
-    """geom_2d.py:340-457 (without .shape(), which needs a grid-wide test)."""
+    """geom_2d.py:340-457."""
 
     def __init__(self, parametric_curve, parametric_curve_parameters, t_range, closed=False):
         self._curve, self._c_params, self._t_range, self._closed = parametric_curve, parametric_curve_parameters, \
@@ -757,6 +763,19 @@ class ParametricCurve(GenericGeometry):
     def closed(self):
         return self._closed
 
+    @property
+    def steps(self):
+        return self._t_range[2]
+
+    def shape(self):
+        """geom_2d.py:415-457: closed curve -> shape. The sign comes from the curve sampled at ts followed by t = 0
+        (ts_ = zeros(steps + 1); ts_[:steps] = ts)."""
+        if not self.closed:
+            return self
+        ts_ = np.zeros(self.steps + 1)
+        ts_[:self.steps] = self.ts
+        return self._add("shape", points=np.asarray(self._curve(ts_, *self._c_params), dtype=np.float64))
+
 
 class SegmentedLine(GenericGeometry):
     def __init__(self, points, closed=False):
@@ -768,6 +787,12 @@ class SegmentedLine(GenericGeometry):
     @property
     def closed(self):
         return self._closed
+
+    def polygon(self):
+        """geom_2d.py:601-626: closed segmented line -> polygon, d * interior_polygon(co, points)."""
+        if not self.closed:
+            return self
+        return self._add("polygon", points=self._points.copy())
 
 
 class PointCloud2D(GenericGeometry):

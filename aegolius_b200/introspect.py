@@ -84,6 +84,17 @@ def to_frontend(obj, _stack=()):
             node.combine_op = cells["self"].operation_type
             node.children = tuple(to_frontend(c, _stack) for c in cells["combined_objects"])
             node.combine_parameter = cells.get("parameters")
+        elif qn in ("SegmentedLine.polygon.<locals>.new_geo_object", "SegmentedParametricCurve.polygon.<locals>.new_geo_object"):
+            cells = _cells(fn)  # geom_2d.py:530-555, 601-626
+            mods_outer_first.append(("polygon", {"points": np.asarray(cells["self"]._points).copy()}))
+            fn = cells["geo_object"]
+        elif qn == "ParametricCurve.shape.<locals>.new_geo_object":
+            cells = _cells(fn)  # geom_2d.py:415-457
+            src = cells["self"]
+            ts_ = np.zeros(src.steps + 1)
+            ts_[:src.steps] = src.ts
+            mods_outer_first.append(("shape", {"points": np.asarray(src._curve(ts_, *src._c_params), dtype=np.float64)}))
+            fn = cells["geo_object"]
         elif qn in ("SegmentedLine.sdf_closed_curve.<locals>.new_geo_object",
                     "SegmentedLine3D.sdf_closed_curve.<locals>.new_geo_object"):
             node = _blank("leaf")

@@ -129,6 +129,13 @@ def _segment_frame(a, b, what):
     return rot, c, l
 
 
+# modifications without a value part (they only warp the coordinates handed to the inner SDF)
+_COORD_ONLY_MODS = frozenset((
+    "elongation", "twist", "bend", "shear", "shear_xz", "shear_yz", "shear_xy", "shear_zy", "shear_yx", "shear_zx",
+    "infinite_repetition", "finite_repetition", "symmetry", "mirror", "rotational_symmetry", "linear_instancing",
+    "curve_instancing", "aligned_curve_instancing", "fully_aligned_curve_instancing", "revolution", "axis_revolution",
+    "move_sdf", "rotate_sdf"))
+
 _SHEAR = {  # name -> (matrix builder as in modifications.py:579-774, transpose?)
     "shear_xz": ((1, 0), True), "shear_yz": ((1, 0), False),
     "shear_xy": ((2, 0), True), "shear_zy": ((2, 0), False),
@@ -207,7 +214,17 @@ class _Builder:
         self.affine(rm / s, -rm.dot(t))
 
         posts = []
-        for name, p in reversed(n._mods):
+        self.cur_pd = pd
+        for k in range(len(n._mods) - 1, -1, -1):
+            name, p = n._mods[k]
+            if name in ("polygon", "shape"):
+                # d * interior (geom_2d.py:415-457, 530-555): the reference first returns the field untouched if it has a
+                # negative sample (a grid-wide test). The modifications applied BEFORE this one must therefore keep the
+                # unsigned curve distance non-negative, i.e. be pure coordinate warps.
+                bad = [m for m, _ in n._mods[:k] if m not in _COORD_ONLY_MODS]
+                if bad or n.kind != "leaf":
+                    raise FlattenError(f"{name}() after {bad or n.kind}: the reference decides by a grid-wide sign test "
+                                       f"(np.any(d < 0)) whether to apply it; only coordinate modifications may precede it")
             post, vd = self.mod_pre(name, p, vd)
             posts.append(post)
 
@@ -225,6 +242,8 @@ class _Builder:
             for (code, a, args) in post:
                 if code == oc.P_FIELD:
                     self.emit(code, b=a)
+                elif code == oc.POLY_SIGN:
+                    self.emit(code, a=a[0], b=a[1], args=args)
                 else:
                     self.emit(code, a=a, args=args)
         if s != 1.0:
@@ -398,6 +417,34 @@ class _Builder:
             post.append((oc.PP_GAUSS_BOUNDARY, 0, [p["amplitude"], p["width"]]))
         elif name == "gaussian_falloff":
             post.append((oc.PP_GAUSS_FALLOFF, 0, [p["amplitude"], p["width"]]))
+        elif name in ("polygon", "shape"):
+            slot = self.cur_pd
+            self.use_p(slot)
+            self.emit(oc.SAVE_P, a=slot)  # the coordinates this closure receives (after the outer warps, before the inner ones)
+            if name == "polygon":  # interior_polygon(co, self._points): triangulation_functions.py:390-430
+                pts = np.asarray(p["points"], dtype=np.float64)
+                if pts.ndim != 2 or pts.shape[0] != 3:
+                    raise ValueError("operands could not be broadcast together: polygon() subtracts the control points "
+                                     "from 3-row coordinates (triangulation_functions.py:385), points must have shape (3, N)")
+                pts = pts[:2]
+                if pts.shape[1] < 3:
+                    raise ValueError("polygon() needs at least 3 points")
+                if _polygon_self_intersects(pts):
+                    raise FlattenError("self-intersecting polygons (split into loops by the reference, "
+                                       "triangulation_functions.py:413-419) are not supported on the GPU path")
+                post.append((oc.POLY_SIGN, (slot, 0), [float(pts.shape[1])] + list(pts.T.reshape(-1))))
+            else:  # ParametricCurve.shape(): geom_2d.py:435-452, segment by segment
+                pts = np.asarray(p["points"], dtype=np.float64)
+                rec = []
+                for i in range(pts.shape[1] - 1):
+                    t = pts[:, i + 1] - pts[:, i]
+                    t = t / np.linalg.norm(t)
+                    nx, ny = -t[1], abs(t[0])  # n[1] = n[1] - 2 (n[1] < 0) n[1]: only the y component is made positive
+                    lx, ux = min(pts[0, i], pts[0, i + 1]), max(pts[0, i], pts[0, i + 1])
+                    rec += [pts[0, i], pts[1, i], lx, ux, nx, ny]
+                if not np.all(np.isfinite(rec)):
+                    raise ValueError("shape(): the sampled curve has a zero-length segment (NaN normal in the reference)")
+                post.append((oc.POLY_SIGN, (slot, 1), [float(pts.shape[1] - 1)] + rec))
         elif name == "signed":
             # modifications.py:220-275: a whole-grid post-pass (scans + box filter), staged like the convolutions below
             res = tuple(int(r) for r in np.asarray(p["co_resolution"]).reshape(-1))
@@ -728,6 +775,8 @@ def _peephole(ops, args):
                 n = 1 + cnt * 3
             elif code in (oc.P_SEGLINE2D, oc.P_POLYGON2D):
                 n = 1 + cnt * 2
+            elif code == oc.POLY_SIGN:
+                n = 1 + cnt * (6 if b else 2)
         put(code, a, b, args[off:off + n])
     flush()
     return out_ops, out_args

@@ -105,6 +105,11 @@ typedef enum ab_opcode {
   AB_OP_SCALE_V = 38,    /* acc *= k (node scale, transformations.py:242) */
   AB_OP_EXTRUDE_BEGIN = 39, /* a = V slot; 1 arg h/2: V[a] = |z| - h/2 ; z = 0 (extrusion :474-500) */
   AB_OP_EXTRUDE_END = 40,   /* a = V slot */
+  AB_OP_POLY_SIGN = 41,     /* acc *= interior sign of a planar polygon / polyline at the coordinates saved in P[a]; table: n, then
+                               b = 0: n (x, y) vertices of a simple closed polygon, crossing-number rule (SegmentedLine.polygon(),
+                               geom_2d.py:530-555, 601-626, triangulation_functions.py:390-430); b = 1: n segment records
+                               (px, py, lx, ux, nx, ny), the x-interval / side-of-segment product of ParametricCurve.shape()
+                               (geom_2d.py:415-457) restated term by term */
   /* post-processing value maps (post_processing.py:380-560; wrappers modifications.py:1361-1587) */
   AB_OP_PP_SIGMOID = 48, AB_OP_PP_POS_SIGMOID = 49, AB_OP_PP_CAPPED_EXP = 50, AB_OP_PP_HARD_BIN = 51,
   AB_OP_PP_LINEAR = 52, AB_OP_PP_RELU = 53, AB_OP_PP_SMOOTH_RELU = 54, AB_OP_PP_SLOWSTART = 55,

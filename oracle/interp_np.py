@@ -21,7 +21,7 @@ import numpy as np
 (AFFINE, TRANSLATE, SCALE_P, ELONGATE, TWIST, BEND, ABSX_SUB, SYMMETRY, ROTSYM, REVOLVE, AXIS_REVOLVE, REP_INF,
  REP_FIN, LIN_INST, CURVE_INST, ZERO_Z) = range(8, 24)
 (NEXT_AFFINE, NEXT_TRANSLATE, NEXT_LOAD) = (24, 25, 26)  # fused PUSH_V + LOAD_P + transform (program.py peephole)
-(ROUND, ABS, NEG, SIGN, ONION, CONCENTRIC, SCALE_V, EXTRUDE_BEGIN, EXTRUDE_END) = range(32, 41)
+(ROUND, ABS, NEG, SIGN, ONION, CONCENTRIC, SCALE_V, EXTRUDE_BEGIN, EXTRUDE_END, POLY_SIGN) = range(32, 42)
 (PP_SIGMOID, PP_POS_SIGMOID, PP_CAPPED_EXP, PP_HARD_BIN, PP_LINEAR, PP_RELU, PP_SMOOTH_RELU, PP_SLOWSTART,
  PP_GAUSS_BOUNDARY, PP_GAUSS_FALLOFF) = range(48, 58)
 (C_UNION, C_INTERSECT, C_SUBTRACT, C_SUM, C_DIFF, C_SMIN2, C_SMIN3, C_SMAX3, C_SSUB3, C_BOLTZ_INT,
@@ -466,6 +466,29 @@ def run(prog, co, return_state=False, return_margin=False, fields=None):
                     ba = pts[i + 1] - pts[i]
                     out = np.minimum(out, _segment((x - pts[i, 0], y - pts[i, 1]), ba, np.dot(ba, ba)))
                 acc = out
+            elif code == POLY_SIGN:  # d * interior at the coordinates saved in P[a]
+                sx, sy, _ = P[a]
+                n = int(A[o])
+                if b == 0:  # .polygon(): geom_2d.py:530-555 / 601-626, interior_polygon == crossing number for simple polygons
+                    pts = A[o + 1:o + 1 + 2 * n].reshape(n, 2)
+                    inside = np.zeros(sx.shape, dtype=bool)
+                    for i in range(n):
+                        pa, pb = pts[i], pts[(i + 1) % n]
+                        cond = (pa[1] > sy) != (pb[1] > sy)
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            xi = (pb[0] - pa[0]) * (sy - pa[1]) / (pb[1] - pa[1]) + pa[0]
+                        inside ^= cond & (sx < xi)
+                    acc = acc * np.where(inside, -1.0, 1.0)
+                else:  # .shape(): geom_2d.py:440-452 term by term
+                    rec = A[o + 1:o + 1 + 6 * n].reshape(n, 6)
+                    interior = np.ones(sx.shape)
+                    for px, py, lx, ux, nx, ny in rec:
+                        mask = (sx >= lx) * (sx < ux)
+                        sgn = np.sign((sx - px) * nx + (sy - py) * ny)
+                        interior = np.where(mask, interior * sgn, interior)
+                        # a sample on an interval end switches segments: decided by rounding in fp32
+                        margin = np.minimum(margin, np.minimum(np.abs(sx - lx), np.abs(sx - ux)))
+                    acc = acc * interior
             elif code == P_POLYGON2D:  # sdf_2D.py:201-218; interior of a SIMPLE polygon (triangulation_functions.py:390-430
                 # builds it as the union of the ear-clipping triangles, boundary included) == crossing-number rule
                 n = int(A[o])

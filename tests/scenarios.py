@@ -581,6 +581,39 @@ def ex_pointcloud_terrain(ns):  # Code/examples/scalar/3D/pointcloud_terrain_3D.
 scenario("ex_pointcloud_terrain_3D", (2.5, 2.5, 1.5), (30, 30, 20))(ex_pointcloud_terrain)
 
 
+# closed curves turned into filled shapes: d * interior (geom_2d.py:415-457 shape(), :530-555 / :601-626 polygon())
+_POLY3 = np.array([[-1.6, 0.0, 1.7, 1.2, 0.1, -1.1], [-1.2, -0.3, -1.3, 1.4, 0.4, 1.5], [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]])
+
+
+def _closed_line_polygon(ns):
+    s = ns.SegmentedLine(_POLY3, closed=True)
+    s.polygon()
+    s.rounding(0.07)
+    return _xf2(s, 1)
+
+
+def _closed_spc_polygon(ns):  # the sign comes from the control polygon, the distance from the sampled curve
+    c = ns.SegmentedParametricCurve(_POLY3, (0, 6, 64), closed=True)
+    c.polygon()
+    return _xf2(c, 2)
+
+
+def ellipse_curve(t, a, b):
+    return np.asarray((a * np.cos(2 * np.pi * t), b * np.sin(2 * np.pi * t)))
+
+
+def _closed_curve_shape(ns):  # the reference's per-segment rule, restated term by term (its normals are only half flipped)
+    c = ns.ParametricCurve(ellipse_curve, (2.3, 1.4), (0, 1, 40), closed=True)
+    c.shape()
+    c.symmetry(0)
+    return _xf2(c, 0)
+
+
+scenario("shape_closed_segmented_line_polygon", *G2)(_closed_line_polygon)
+scenario("shape_closed_segmented_parametric_curve_polygon", *G2)(_closed_spc_polygon)
+scenario("shape_closed_parametric_curve_shape", *G2)(_closed_curve_shape)
+
+
 def make_namespace(kind):
     """kind = 'reference' (needs /root/reference or an installed spomso) or 'frontend'."""
     import types
