@@ -414,8 +414,7 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
             decls.append("    Pt<S> " + ", ".join(f"P{i}" for i in range(em.n_p)) + ";")
         if em.n_v:
             decls.append("    S " + ", ".join(f"V{i}" for i in range(em.n_v)) + ";")
-    from .engine import _DT  # dtype codes
-    dcode = _DT[dtype][0]
+    dcode = {"f32": 0, "f64": 1}[dtype]  # AB_F32 / AB_F64
     gcode = {"none": 0, "spatial": 1, "param": 2}[grad]
     rep = {"VERSION": CODEGEN_VERSION, "HASH": signature_hash(sig, dcode, gcode), "NOPS": len(sig),
            "KINDNAME": f"{dtype}, grad={grad}", "WIDTH": W, "SLOTS": "registers" if o["slots"] == "reg" else "shared memory",
@@ -565,10 +564,10 @@ def _key(sig, dtype, grad, flavor):
     return (np.asarray(sig, dtype=np.uint32).tobytes(), dtype, grad, int(flavor))
 
 
-def _register(path, sig, dtype, grad, is2d):  # is2d: the flavour bits (bit 0 2D grid, bit 1 multicast stores)
+def _register(path, sig, dtype, grad, is2d):  # is2d: the flavour bits (bit 0 2D grid, bit 1 multicast stores, bit 2 compact tiles)
     import ctypes as C
     from . import cabi
-    from .engine import _DT
+    _DT = {"f32": (cabi.AB_F32,), "f64": (cabi.AB_F64,)}
     lib = _loaded.get(path)
     if lib is None:
         lib = C.CDLL(path)
@@ -598,9 +597,12 @@ def wants_compact_tiles(sig, dtype, grad, is2d) -> bool:
 
 
 def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, multicast=False, **opts):
-    """Makes the compiled kernel of `prog`'s structure available to the library. Returns True when it is registered on
-    return, False when the interpreter serves this call (build in flight, disabled, too long a program, failed build).
-    how: None = mode(); 'sync' blocks on the build."""
+    """Makes the compiled kernel(s) of `prog`'s structure available to the library. Returns True when the kernel that will
+    serve this (dtype, grad, grid kind) is registered on return, False when the interpreter serves the call (build in
+    flight, disabled, too long a program, failed build). how: None = mode(); 'sync' blocks on the build.
+
+    A structure with a warp-cooperative op gets two binaries: compact tiles for 3D grids (wants_compact_tiles) and the flat
+    walk, which keeps serving point lists."""
     how = how or mode()
     if how == "off" or not compilable(prog):
         return False
@@ -608,17 +610,16 @@ def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, multicast=False, 
         ("f32" if np.dtype(dtype) == np.float32 else "f64")
     grad = _GRAD_NAMES[grad]
     sig = signature(prog)
-    if opts.get("compact") is None and not opts.get("_no_compact") and wants_compact_tiles(sig, dtype, grad, is2d):
-        # two binaries for this structure: compact tiles for 3D grids, the flat walk for point lists
-        ensure(prog, dtype, grad, is2d, how, multicast, compact=True, **opts)
-        opts = dict(opts, _no_compact=True)
-    opts.pop("_no_compact", None)
-    if opts.get("compact") is None:
-        opts.pop("compact", None)
-    is2d = int(bool(is2d)) | (2 if multicast else 0) | (4 if opts.get("compact") else 0)  # from here on: the flavour bits
-    if multicast:
-        opts = dict(opts, multicast=True)
-    key = _key(sig, dtype, grad, is2d)
+    compact = opts.pop("compact", None)
+    variants = [bool(compact)] if compact is not None else \
+        ([True, False] if wants_compact_tiles(sig, dtype, grad, is2d) else [False])
+    ok = [_ensure_one(sig, dtype, grad, bool(is2d), how, multicast, c, opts) for c in variants]
+    return ok[0]
+
+
+def _ensure_one(sig, dtype, grad, is2d, how, multicast, compact, opts):
+    flavor = int(is2d) | (2 if multicast else 0) | (4 if compact else 0)
+    key = _key(sig, dtype, grad, flavor)
     if key in _registered:
         return True
     if key in _failed:
@@ -628,10 +629,10 @@ def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, multicast=False, 
             return True
         th = _pending.get(key)
         if th is None:
-            src = generate(sig, dtype, grad, is2d=is2d & 1, **opts)
+            src = generate(sig, dtype, grad, is2d=is2d, multicast=multicast, compact=compact, **opts)
             path = binary_path(src)
             if os.path.exists(path):  # built earlier (this process, another one, or shipped with the tree): just load it
-                _register(path, sig, dtype, grad, is2d)
+                _register(path, sig, dtype, grad, flavor)
                 _registered.add(key)
                 return True
             if how == "cache":
@@ -641,10 +642,11 @@ def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, multicast=False, 
                 try:
                     p = build_source(src)
                     with _lock:
-                        _register(p, sig, dtype, grad, is2d)
+                        _register(p, sig, dtype, grad, flavor)
                         _registered.add(key)
                 except Exception as exc:  # no nvcc / compile error: this structure stays on the interpreter
-                    _failed[key] = str(exc)
+                    with _lock:
+                        _failed[key] = str(exc)
                 finally:
                     with _lock:
                         _pending.pop(key, None)

@@ -127,9 +127,12 @@ __global__ void ab_scale_copy_kernel(const T* __restrict__ in, T* __restrict__ o
 }
 
 // 9 u - sum of the 3x3 neighbourhood over the two axes (0, 1) of a 3D field or (1, 2) of the (1, nx, ny) view of a 2D one.
-// A thread marches along the first stencil axis over `chunk` outputs with the 3x3 window in registers: three loads per
-// output. The sum runs in the oracle's order (first axis outer, second inner).
-template <typename T>
+// A thread marches along the first stencil axis over `chunk` outputs. The 3x3 sum is kept as three ROW sums (one per march
+// position: left + centre + right along the cross axis) plus the three centre samples: a step loads the three samples of
+// the look-ahead row, forms its row sum (2 adds), and writes 9 c - (r0 + r1 + r2): 5 arithmetic instructions per output
+// instead of 10, no window shuffling. (The sum is associated row-wise, the reference's convolution tap by tap: the results
+// differ in the last bits only, tests/test_gpu_fields.py bounds it at 1e-12.)
+template <typename T, int U>
 __global__ void __launch_bounds__(256) ab_edge_kernel(const T* __restrict__ in, T* __restrict__ out, Field3 f, int is2d, uint32_t chunk) {
   const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= f.n2) return;
@@ -140,55 +143,47 @@ __global__ void __launch_bounds__(256) ab_edge_kernel(const T* __restrict__ in, 
   const uint32_t bpos = is2d ? z : blockIdx.y;
   const uint32_t a0 = (is2d ? blockIdx.y : blockIdx.z) * chunk;
   const uint32_t a1 = a0 + chunk < nA ? a0 + chunk : nA;
-  // offsets of the three cross-axis taps relative to the column of this thread
-  const int64_t ob[3] = {((int64_t)reflect_index((int)bpos - 1, (int)nB) - (int64_t)bpos) * (int64_t)sB, 0,
-                         ((int64_t)reflect_index((int)bpos + 1, (int)nB) - (int64_t)bpos) * (int64_t)sB};
+  // offsets of the two outer cross-axis taps relative to the column of this thread ('reflect' at the faces)
+  const int64_t om = ((int64_t)reflect_index((int)bpos - 1, (int)nB) - (int64_t)bpos) * (int64_t)sB;
+  const int64_t op = ((int64_t)reflect_index((int)bpos + 1, (int)nB) - (int64_t)bpos) * (int64_t)sB;
   const T* col = in + (is2d ? (uint64_t)z : (uint64_t)blockIdx.y * f.n2 + z);
   T* dst = out + (is2d ? (uint64_t)z : (uint64_t)blockIdx.y * f.n2 + z) + (uint64_t)a0 * sA;
-  T w[3][3];
-#pragma unroll
-  for (int da = 0; da < 2; da++) {
-    const T* p = col + (uint64_t)reflect_index((int)a0 - 1 + da, (int)nA) * sA;
-#pragma unroll
-    for (int db = 0; db < 3; db++) w[da + 1][db] = p[ob[db]];
-  }
-  constexpr int U = 4;  // outputs per step, loads issued together (latency-bound otherwise)
-  auto finish = [&](const T (&nw)[3]) {  // shift the window by one march step and write one output
-#pragma unroll
-    for (int db = 0; db < 3; db++) {
-      w[0][db] = w[1][db];
-      w[1][db] = w[2][db];
-      w[2][db] = nw[db];
-    }
-    T s = T(0);
-#pragma unroll
-    for (int da = 0; da < 3; da++)
-#pragma unroll
-      for (int db = 0; db < 3; db++) s = s + w[da][db];
-    *dst = T(9) * w[1][1] - s;
-    dst += sA;
+  auto row = [&](const T* p, T& sum, T& centre) {
+    centre = p[0];
+    sum = (p[om] + centre) + p[op];
   };
+  T r0, r1, r2, c0, c1, c2;  // rows a-1, a, a+1 of the output being written
+  row(col + (uint64_t)reflect_index((int)a0 - 1, (int)nA) * sA, r1, c1);
+  row(col + (uint64_t)a0 * sA, r2, c2);
+  // U outputs per step, their 3 U loads issued together: the march is latency-bound (ncu: 82 % long-scoreboard stalls at U = 4)
   uint32_t a = a0;
-  // whole steps whose look-ahead rows a+1 .. a+U lie inside the field: plain pointer increments, no reflection, no tail tests
   const T* pn = col + (uint64_t)(a0 + 1) * sA;
+  // whole steps whose look-ahead rows a+1 .. a+U lie inside the field: plain pointer increments, no reflection, no tail tests
   for (; a + U <= a1 && a + U < nA; a += U) {
-    T nw[U][3];
+    T nm[U], nc[U], np_[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-#pragma unroll
-      for (int db = 0; db < 3; db++) nw[u][db] = pn[ob[db]];
+      nm[u] = pn[om];
+      nc[u] = pn[0];
+      np_[u] = pn[op];
       pn += sA;
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) finish(nw[u]);
+    for (int u = 0; u < U; u++) {
+      r0 = r1; c0 = c1; r1 = r2; c1 = c2;
+      c2 = nc[u];
+      r2 = (nm[u] + c2) + np_[u];
+      *dst = T(9) * c1 - ((r0 + r1) + r2);
+      dst += sA;
+    }
   }
   for (; a < a1; a++) {  // the last outputs of the chunk / of the axis: reflected look-ahead row
-    const T* p = col + (uint64_t)reflect_index((int)a + 1, (int)nA) * sA;
-    T nw[3];
-#pragma unroll
-    for (int db = 0; db < 3; db++) nw[db] = p[ob[db]];
-    finish(nw);
+    r0 = r1; c0 = c1; r1 = r2; c1 = c2;
+    row(col + (uint64_t)reflect_index((int)a + 1, (int)nA) * sA, r2, c2);
+    *dst = T(9) * c1 - ((r0 + r1) + r2);
+    dst += sA;
   }
+  (void)c0;
 }
 
 // ---- signed: unsigned distance field -> signed distance field (modifications.py:220-275) -----------------------------------------

@@ -331,11 +331,17 @@ struct FDParams {
 // np.gradient, unit spacing, edge_order=1: interior (f[i+1] - f[i-1]) / 2, faces f[1] - f[0] and f[n-1] - f[n-2]. Written as
 // (p - m) * s with the missing neighbour replaced by the centre sample and s = 1 on a face, 1/2 inside (bit-identical to
 // the three-way form, no branches): the face tests depend on the thread's (i1, i2) only and leave the plane loop.
-AB_DEV float fd_rcp(float m) { return s_rcp(m); }        // fp32: MUFU.RCP (<= 1 ulp); the tolerance is 2e-6
-AB_DEV double fd_rcp(double m) { return 1.0 / m; }       // fp64: IEEE, results match np.gradient / norm to 1e-13
+// 1 / |g| from |g|^2: fp32 one MUFU.RSQ (<= 2 ulp; the tolerance is 2e-6), fp64 IEEE sqrt + division (results match
+// np.gradient / norm to 1e-13)
+AB_DEV float fd_inv_norm(float m2) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m2));
+  return r;
+}
+AB_DEV double fd_inv_norm(double m2) { return 1.0 / sqrt(m2); }
 
 // HAS0 / NORM: kp.has0 / kp.normalize as compile-time switches (the launcher picks the instantiation)
-template <typename T, bool HAS0, bool NORM>
+template <typename T, bool HAS0, bool NORM, int U = 4>
 __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDParams<T> kp) {
   const uint32_t i2 = blockIdx.x * blockDim.x + threadIdx.x;
   if (i2 >= kp.n2) return;
@@ -353,7 +359,6 @@ __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDPa
   T* __restrict__ po = kp.out + ((uint64_t)(x_begin - kp.b0) * w1 + (i1 - kp.b1)) * kp.n2 + i2;
   // four planes per step with all their loads issued up front: the march is latency-bound otherwise (one DRAM load in
   // flight per thread); per plane the centre of the next plane + 4 in-plane neighbours = 20 independent loads per thread
-  constexpr int U = 4;
   T fc = pc[0];
   T fm = (HAS0 && x_begin > 0) ? pc[-fplane] : fc;  // below the grid: the centre stands in (scale 1 there)
   for (uint32_t i0 = x_begin; i0 < x_end; i0 += U) {
@@ -385,9 +390,9 @@ __global__ void __launch_bounds__(256) ab_fd_kernel(const __grid_constant__ FDPa
       T g1 = (a1p[u] - a1m[u]) * s1;
       T g2 = (a2p[u] - a2m[u]) * s2;
       if (NORM) {
-        const T m = HAS0 ? s_sqrt(s_fma(g0, g0, s_fma(g1, g1, g2 * g2))) : s_sqrt(s_fma(g1, g1, g2 * g2));
-        if (m != T(0)) {
-          const T im = fd_rcp(m);
+        const T m2 = HAS0 ? s_fma(g0, g0, s_fma(g1, g1, g2 * g2)) : s_fma(g1, g1, g2 * g2);
+        if (m2 > T(0)) {  // zero vectors stay zero (batch_normalize)
+          const T im = fd_inv_norm(m2);
           g0 *= im;
           g1 *= im;
           g2 *= im;
