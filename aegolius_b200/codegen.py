@@ -96,7 +96,10 @@ def default_options(sig, dtype, grad):
     Measured on B200 (profiles/r02_jit_sweep.md): write-bound programs (a handful of cheap ops) want 8 points per thread
     with the warp-transposed store (every STG.128 of a warp covers 512 contiguous bytes; direct 8-wide stores half-fill
     each sector and run at 52 % of the HBM peak instead of 84 %); issue-bound cheap programs want 8 points and direct
-    stores; programs with transcendentals want fewer registers per thread the longer they are."""
+    stores; programs with transcendentals want fewer registers per thread the longer they are. `rowsplit` (the body a second
+    time for warps whose threads each stay inside one grid row: x and y become per-thread scalars and the compiler drops
+    the lane-redundant packed work) pays with 8 points per thread: sphere 81 -> 94 %, C1 42 -> 48 % of the HBM peak, a
+    36-op union of boxes and spheres 4.58 -> 3.80 ms; nothing at 4 points (C1 field + gradient) and a loss on C2."""
     lite = all((int(w) & 0xffff) in LITE_OPS for w in sig)
     n = len(sig)
     if grad == "param":
@@ -104,8 +107,12 @@ def default_options(sig, dtype, grad):
     if dtype == "f32":
         if grad == "none":
             if lite:
-                return dict(width=8, min_ctas=8, stage8=True, store=1) if n <= 4 else dict(width=8, min_ctas=8)
-            return dict(width=8, min_ctas=5) if n <= 32 else dict(width=4, min_ctas=5)
+                if n <= 4:
+                    return dict(width=8, min_ctas=6, stage8=True, store=1, rowsplit=True)
+                return dict(width=8, min_ctas=8, rowsplit=n <= 64)
+            if n <= 8:
+                return dict(width=8, min_ctas=8, rowsplit=True)
+            return dict(width=8, min_ctas=5, rowsplit=True) if n <= 32 else dict(width=4, min_ctas=5)
         return dict(width=4, min_ctas=4) if lite else dict(width=2, min_ctas=7)
     if grad == "none":
         return dict(width=2, min_ctas=6)
@@ -293,19 +300,7 @@ __global__ void __launch_bounds__(kNT, @MINCTAS@) ab_prog_kernel(const __grid_co
   }
   double loss_sum = 0.0, dloss_sum = 0.0;  // loss mode only (parameter-tangent kernels)
 @LOOPHEAD@
-    Pt<S> p;
-    seed(p, cx, cy, cz);
-    S acc = constant_like(p.x, T(0));
-@DECLS@
-@BODY@
-    if constexpr (kParam) {
-      if (kp.loss_accum) {
-        accumulate_loss(kp, acc, idx, loss_sum, dloss_sum);
-        continue;
-      }
-    }
-    const bool aligned = ((reinterpret_cast<uintptr_t>(kp.out) & 15) == 0);
-@EMIT@
+@BODYALL@
   }
   if constexpr (kParam) {
     if (kp.loss_accum) {
@@ -394,7 +389,7 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
         raise ValueError("empty program")
     grad = grad or "none"
     kind, T, K, param = KINDS[(dtype, grad)]
-    o = dict(slots="reg", nt=128, is2d=0, store=0, stage8=False, multicast=False, compact=False)
+    o = dict(slots="reg", nt=128, is2d=0, store=0, stage8=False, multicast=False, compact=False, rowsplit=False)
     o.update(default_options(sig, dtype, grad))
     if opts.get("compact"):  # measured (profiles/r02_jit_sweep.md): C5 field + gradient 19.7 -> 18.8 ms, C3 value 1.82 -> 1.44 ms
         o.update(width=2, min_ctas=8, stage8=False)
@@ -443,7 +438,15 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
     bool valid0, valid1;
     P cx, cy, cz;
     compact_coords(kp, walk, nb1, nb2, cx, cy, cz, idx, valid0, valid1);"""
-    rep["LOOPHEAD"] = compact_head if o["compact"] else flat_head
+    split_head = """  const uint32_t tile_pts = (uint32_t)kNT * W;
+  const uint32_t n32 = (uint32_t)kp.n;
+  const uint32_t n_tiles = (n32 + tile_pts - 1) / tile_pts;
+  TileWalk walk;
+  tile_walk_begin(kp, tile_pts, (uint32_t)W, walk);
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t idx = tile * tile_pts + threadIdx.x * W;
+    P cx, cy, cz;"""
+    rep["LOOPHEAD"] = compact_head if o["compact"] else (split_head if o["rowsplit"] else flat_head)
     rep["COMPACT"] = "true" if o["compact"] else "false"
     if o["compact"]:
         rep["EMIT"] = "    emit_compact(kp, acc, idx, valid0, valid1);"
@@ -454,7 +457,32 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
         rep["EMIT"] = "    emit(kp, acc, idx, aligned);"
     if o["compact"] and not (W == 2 and not param and int(o["nt"]) == 128 and not o["is2d"]):
         raise ValueError("compact tiles: 2 points per thread, 128 threads, 3D grids, value / spatial-gradient kernels")
+    body_one = """    Pt<S> p;
+    seed(p, cx, cy, cz);
+    S acc = constant_like(p.x, T(0));
+@DECLS@
+@BODY@
+    if constexpr (kParam) {
+      if (kp.loss_accum) {
+        accumulate_loss(kp, acc, idx, loss_sum, dloss_sum);
+        continue;
+      }
+    }
+    const bool aligned = ((reinterpret_cast<uintptr_t>(kp.out) & 15) == 0);
+@EMIT@"""
+    if o["rowsplit"] and not o["compact"]:
+        # the body twice: behind the warp-wide "every run stays in its row" test the slow coordinates are broadcasts
+        indent = lambda t: "\n".join(("  " + ln if ln else ln) for ln in t.split("\n"))
+        rep["BODYALL"] = ("    if (__all_sync(0xffffffffu, tile_run_in_one_row<T, W>(kp, walk))) {\n"
+                          "      tile_coords_uniform<kIs2D>(kp, walk, cx, cy, cz);\n" + indent(body_one) + "\n"
+                          "    } else {\n"
+                          "      tile_coords<kIs2D>(kp, walk, idx, n32, cx, cy, cz);\n" + indent(body_one) + "\n"
+                          "    }")
+    else:
+        rep["BODYALL"] = body_one
     src = _TEMPLATE
+    for k in ("BODYALL",):  # nested placeholders first
+        src = src.replace(f"@{k}@", str(rep.pop(k)))
     for k, v in rep.items():
         src = src.replace(f"@{k}@", str(v))
     return src

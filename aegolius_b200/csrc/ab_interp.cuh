@@ -251,6 +251,41 @@ AB_DEV void tile_coords(const KParams<T>& kp, TileWalk& w, uint32_t idx, uint32_
   }
 }
 
+// The common case of tile_coords for a whole warp at once: every thread's W points share one row, so the two slow
+// coordinates are per-thread broadcasts and only the fast one varies along the run. Program-compiled kernels of short
+// programs emit their body twice (codegen.py, `rowsplit`): in the copy behind this function the compiler sees that all W
+// lanes of x and y hold one value and evaluates everything that depends on them alone once per thread instead of W times
+// (common-subexpression elimination does it: the general path merges two coordinate branches and hides that).
+template <typename T, int W>
+AB_DEV bool tile_run_in_one_row(const KParams<T>& kp, const TileWalk& w) { return kp.grid_mode && w.i2 + W <= kp.g.n2; }
+template <int IS2D, typename T, int W>
+AB_DEV void tile_coords_uniform(const KParams<T>& kp, TileWalk& w, Pack<T, W>& cx, Pack<T, W>& cy, Pack<T, W>& cz) {
+  typedef Pack<T, W> P;
+  const T a0 = grid_coord(kp.g, 0, w.i0 + kp.g.i0_begin, T()), a1 = grid_coord(kp.g, 1, w.i1 + kp.g.i1_begin, T());
+  P uc;
+  grid_coord_run(kp.g, 2, (int32_t)w.i2, uc);
+  if (IS2D) {
+    cx = P(a1);
+    cy = uc;
+    cz = P(T(0));
+  } else {
+    cx = P(a0);
+    cy = P(a1);
+    cz = uc;
+  }
+  w.i2 += kp.tile_stride[2];
+  if (w.i2 >= kp.g.n2) {
+    w.i2 -= kp.g.n2;
+    w.i1++;
+  }
+  w.i1 += kp.tile_stride[1];
+  if (w.i1 >= kp.g.n1) {
+    w.i1 -= kp.g.n1;
+    w.i0++;
+  }
+  w.i0 += kp.tile_stride[0];
+}
+
 // ---- stack in shared memory: element [slot][tid] is one 16-byte Pack column --------------------------------------------
 template <typename P>
 AB_DEV void st_pack(P* base, int slot, int nt, const P& v) { base[slot * nt + threadIdx.x] = v; }

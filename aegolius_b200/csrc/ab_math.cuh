@@ -694,7 +694,7 @@ AB_DEV S clamp_(const S& a, const L& lo, const H& hi) { return min_(max_(a, lo),
 template <typename S>
 AB_DEV S norm2_(const S& a, const S& b) { return sqrt_(fma_(a, a, b * b)); }
 template <typename S>
-AB_DEV S norm3_(const S& a, const S& b, const S& c) { return sqrt_(fma_(a, a, fma_(b, b, c * c))); }
+AB_DEV S norm3_(const S& a, const S& b, const S& c) { return sqrt_(fma_(c, c, fma_(b, b, a * a))); }  // (z last, see op_affine)
 // Euclidean norms of dual numbers in closed form: d|v| = (a da + b db [+ c dc]) / |v| (0 at the kink |v| = 0). Same value
 // expression as the generic form; the tangents take 3 instructions per component instead of squaring duals and scaling
 // by 1 / (2 sqrt) afterwards (about half the instructions of a sphere / torus / box tangent).
@@ -710,10 +710,10 @@ AB_DEV Dual<P, K> norm2_(const Dual<P, K>& a, const Dual<P, K>& b) {
 template <typename P, int K>
 AB_DEV Dual<P, K> norm3_(const Dual<P, K>& a, const Dual<P, K>& b, const Dual<P, K>& c) {
   Dual<P, K> r;
-  r.v = sqrt_(fma_(a.v, a.v, fma_(b.v, b.v, c.v * c.v)));
+  r.v = sqrt_(fma_(c.v, c.v, fma_(b.v, b.v, a.v * a.v)));
   const P inv = select_(gt_(r.v, AB_DUAL_T(0)), rcp_(r.v), P(AB_DUAL_T(0)));
 #pragma unroll
-  AB_DK r.d[k] = fma_(a.v, a.d[k], fma_(b.v, b.d[k], c.v * c.d[k])) * inv;
+  AB_DK r.d[k] = fma_(c.v, c.d[k], fma_(b.v, b.d[k], a.v * a.d[k])) * inv;
   return r;
 }
 

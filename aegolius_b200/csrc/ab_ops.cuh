@@ -48,9 +48,11 @@ AB_DEV Dual<P, K> rcp_arg(const Dual<P, K>& x) { return div_(Dual<P, K>(typename
 template <typename S, typename A>
 AB_DEV void op_affine(Pt<S>& p, A a) {
   typedef typename S::scalar T;
-  S nx = fma_(p.x, a[0], fma_(p.y, a[1], fma_(p.z, a[2], a[9])));
-  S ny = fma_(p.x, a[3], fma_(p.y, a[4], fma_(p.z, a[5], a[10])));
-  S nz = fma_(p.x, a[6], fma_(p.y, a[7], fma_(p.z, a[8], a[11])));
+  // z (the fastest grid axis, the one that varies along a thread's run of points) enters last: on a grid the x / y part of
+  // the first transform of a tree is then the same for all W points of a thread and is evaluated once (codegen.py, rowsplit)
+  S nx = fma_(p.z, a[2], fma_(p.y, a[1], fma_(p.x, a[0], a[9])));
+  S ny = fma_(p.z, a[5], fma_(p.y, a[4], fma_(p.x, a[3], a[10])));
+  S nz = fma_(p.z, a[8], fma_(p.y, a[7], fma_(p.x, a[6], a[11])));
   p.x = nx;
   p.y = ny;
   p.z = nz;

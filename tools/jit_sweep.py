@@ -23,7 +23,19 @@ def cases():
     sph = ab.Sphere(1.0)
     sph.move((0.3, 0.1, -0.2))
     sph0 = ab.Sphere(1.0)
+    # a short program with transcendentals (twist + torus) and a long cheap one (union of 12 moved boxes / spheres)
+    tw = ab.Torus(1.0, 0.3)
+    tw.twist(1.5)
+    tw.move((0.1, -0.2, 0.05))
+    parts = []
+    for i in range(12):
+        g = ab.Sphere(0.3 + 0.02 * i) if i % 2 else ab.Box(0.4, 0.3 + 0.02 * i, 0.5)
+        g.move((-1.5 + 0.27 * i, 0.3 * ((i * 5) % 7) - 0.9, 0.25 * ((i * 3) % 5) - 0.5))
+        parts.append(g)
+    un = ab.CombineGeometry("UNION").combine(*parts)
     return {
+        "twist": (tw, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
+        "union12": (un, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
         "sphere0": (sph0, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
         "sphere": (sph, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
         "c1": (workloads.build_c1(), ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
