@@ -267,11 +267,178 @@ class _Emitter:
             raise NotImplementedError(f"codegen: opcode {code} ({name})")
 
 
+
+class _NoAdjoint(Exception):
+    """The program holds an op without a pull-back: the forward-mode build serves it."""
+
+
+class _AdjointEmitter(_Emitter):
+    """Field + spatial gradient with the chain rule applied backwards through the coordinate ops (csrc/ab_adjoint.cuh):
+    coordinate ops run on plain points and leave their Jacobian's ingredients in registers, primitives are evaluated on an
+    identity-seeded dual point (value + gradient in local coordinates), and a gradient is pulled back to the frame it is
+    needed in — the common frame of two values at a combine, the grid's at the end. Frames form a tree (SAVE_P / LOAD_P
+    branch it); a node = (parent, pull-back statement)."""
+
+    def __init__(self, sig):
+        super().__init__(sig, False, "reg")
+        self.nodes = [(None, None)]
+        self.cur = 0          # frame of `p`
+        self.acc_node = 0     # frame of `acc`
+        self.slot_node = {}   # P slot -> frame
+        self.v_node = {}      # V slot -> frame
+
+    def node(self, pb):
+        self.nodes.append((self.cur, pb))
+        self.cur = len(self.nodes) - 1
+
+    def _chain(self, n):
+        out = []
+        while n is not None:
+            out.append(n)
+            n = self.nodes[n][0]
+        return out
+
+    def lca(self, a, b):
+        ca = self._chain(a)
+        sb = set(self._chain(b))
+        return next(n for n in ca if n in sb)
+
+    def pull(self, var, n, to):
+        while n != to:
+            parent, pb = self.nodes[n]
+            self.lines.append("    " + pb.format(v=var))
+            n = parent
+
+    def save_p(self, s):
+        self.slot_node[s] = self.cur
+        return super().save_p(s)
+
+    def load_p(self, s):
+        self.cur = self.slot_node[s]
+        return super().load_p(s)
+
+    def store_v(self, s, expr="acc"):
+        self.v_node[s] = self.acc_node
+        return super().store_v(s, expr)
+
+    def finish(self):
+        self.lines.append("    // gradient back to grid coordinates")
+        self.pull("acc", self.acc_node, 0)
+
+    def op(self, i):
+        w = self.sig[i]
+        code, a, b = w & 0xffff, (w >> 16) & 0xff, (w >> 24) & 0xff
+        A = self.arg(i)
+        e = self.lines.append
+        head = f"    // {i}: {oc.NAMES[code]} a={a} b={b}"
+        identity_jacobian = {oc.TRANSLATE: "op_translate", oc.REP_INF: "op_rep_inf", oc.REP_FIN: "op_rep_fin"}
+        taped = {oc.ELONGATE: ("TapeElongate<P>", "fwd_elongate(p, {A}, {t});", "pb_elongate({{v}}, {t});"),
+                 oc.TWIST: ("TapeTwist<P>", "fwd_twist(p, {A}, {t});", "pb_twist({{v}}, {A}, {t});"),
+                 oc.BEND: ("TapeBend<P>", "fwd_bend(p, {A}, {t});", "pb_bend({{v}}, {A}, {t});"),
+                 oc.ROTSYM: ("TapeRot<P>", "fwd_rotsym(p, {A}, {t});", "pb_rot({{v}}, {t});"),
+                 oc.REVOLVE: ("TapeRevolve<P>", "fwd_revolve(p, {A}, {t});", "pb_revolve({{v}}, {t});"),
+                 oc.AXIS_REVOLVE: ("TapeRevolve<P>", "fwd_axis_revolve(p, {A}, {t});", "pb_axis_revolve({{v}}, {A}, {t});")}
+        local_gradient = {oc.P_SPHERE: "grad_sphere", oc.P_TORUS: "grad_torus", oc.P_BOX: "grad_box", oc.P_CYLINDER: "grad_cylinder"}
+        t = f"t{i}"
+        if code in (oc.SAVE_P, oc.LOAD_P, oc.PUSH_V):
+            super().op(i)
+        elif code in (oc.NEXT_AFFINE, oc.NEXT_TRANSLATE, oc.NEXT_LOAD):
+            e(head)
+            if b:
+                e("    " + self.store_v(b - 1))
+            e("    " + self.load_p(a))
+            if code == oc.NEXT_AFFINE:
+                e(f"    op_affine(p, {A});")
+                self.node(f"pb_affine({{v}}, {A});")
+            elif code == oc.NEXT_TRANSLATE:
+                e(f"    op_translate(p, {A});")
+        elif code == oc.AFFINE:
+            e(head)
+            e(f"    op_affine(p, {A});")
+            self.node(f"pb_affine({{v}}, {A});")
+        elif code in identity_jacobian:
+            e(head)
+            e(f"    {identity_jacobian[code]}(p, {A});")
+        elif code == oc.LIN_INST:
+            e(head)
+            e(f"    op_lin_inst(p, {A}, {a});")
+        elif code == oc.SCALE_P:
+            e(head)
+            e(f"    op_scale_p(p, {A});")
+            self.node(f"pb_scale({{v}}, ({A})[0]);")
+        elif code in taped:
+            ty, fwd, pb = taped[code]
+            e(head)
+            e(f"    {ty} {t};")
+            e("    " + fwd.format(A=A, t=t))
+            self.node(pb.format(A=A, t=t))
+        elif code in (oc.ABSX_SUB, oc.SYMMETRY):
+            ax = 0 if code == oc.ABSX_SUB else a
+            c = "xyz"[ax]
+            e(head)
+            e(f"    const Mask<W> {t} = lt_(p.{c}, T(0));")
+            e(f"    op_absx_sub(p, {A});" if code == oc.ABSX_SUB else f"    p.{c} = abs_(p.{c});")
+            self.node(f"pb_flip<{ax}>({{v}}, {t});")
+        elif code == oc.CURVE_INST:
+            e(head)
+            e(f"    int {t}[W];")
+            e(f"    fwd_curve_inst(p, {A}, {a}, {t});")
+            if a:  # aligned variants rotate into the instance's frame; the plain one only translates
+                self.node(f"pb_curve_inst({{v}}, {A}, {t});")
+        elif code == oc.ZERO_Z:
+            e(head)
+            e("    p.z = P(T(0));")
+            self.node("pb_zero_z({v});")
+        elif code == oc.EXTRUDE_BEGIN:
+            e(head)
+            self.n_v = max(self.n_v, a + 1)
+            self.v_node[a] = self.cur
+            e(f"    {{ auto a = {A}; Pt<S> q; seed_local(q, p); V{a} = abs_(q.z) - a[0]; }}")
+            e("    p.z = P(T(0));")
+            self.node("pb_zero_z({v});")
+        elif code == oc.EXTRUDE_END:
+            e(head)
+            to = self.lca(self.acc_node, self.v_node[a])
+            self.pull(f"V{a}", self.v_node[a], to)
+            self.pull("acc", self.acc_node, to)
+            e(f"    acc = op_extrude_end<S, T>(acc, V{a});")
+            self.acc_node = to
+        elif code in (oc.ROUND, oc.ABS, oc.NEG, oc.SIGN, oc.ONION, oc.CONCENTRIC, oc.SCALE_V) or oc.PP_SIGMOID <= code <= oc.PP_GAUSS_FALLOFF:
+            super().op(i)  # value ops: the dual number keeps its frame
+        elif oc.C_UNION <= code <= oc.C_BOLTZ_SUB:
+            to = self.lca(self.acc_node, self.v_node[a])
+            e(f"    // {i}: operands of the combine into their common frame")
+            self.pull(f"V{a}", self.v_node[a], to)
+            self.pull("acc", self.acc_node, to)
+            self.acc_node = to
+            super().op(i)
+        elif code in local_gradient:
+            e(head)
+            e(f"    acc = {local_gradient[code]}(p, {A});")
+            self.acc_node = self.cur
+        elif (oc.P_SPHERE <= code <= oc.P_AXIS and code not in (oc.P_POINT_CLOUD, oc.P_FIELD)) or oc.P_CIRCLE <= code <= oc.P_POLYGON2D:
+            # the primitive on an identity-seeded dual point: value + gradient in local coordinates
+            n0 = len(self.lines)
+            super().op(i)
+            body = self.lines[n0 + 1:]
+            del self.lines[n0 + 1:]
+            e("    {")
+            e("      Pt<S> q;")
+            e("      seed_local(q, p);")
+            for ln in body:
+                e("  " + ln.replace("(p, ", "(q, ").replace("= p.", "= q."))
+            e("    }")
+            self.acc_node = self.cur
+        else:
+            raise _NoAdjoint(oc.NAMES.get(code, str(code)))
+
+
 _TEMPLATE = r'''// generated by aegolius_b200/codegen.py (version @VERSION@) — do not edit.
 // program signature hash @HASH@, @NOPS@ ops; @KINDNAME@; @WIDTH@ points per thread, slots in @SLOTS@, 2D-grid flavour @IS2D@.
 #define AB_TIER_FULL 2
 #define AB_STORE_POLICY @STOREPOLICY@
 #include "ab_interp.cuh"
+#include "ab_adjoint.cuh"
 
 namespace ab {
 typedef @T@ ProgT;
@@ -389,30 +556,46 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
         raise ValueError("empty program")
     grad = grad or "none"
     kind, T, K, param = KINDS[(dtype, grad)]
-    o = dict(slots="reg", nt=128, is2d=0, store=0, stage8=False, multicast=False, compact=False, rowsplit=False)
+    o = dict(slots="reg", nt=128, is2d=0, store=0, stage8=False, multicast=False, compact=False, rowsplit=False,
+             adjoint=os.environ.get("AB_JIT_ADJOINT", "1") != "0")
     o.update(default_options(sig, dtype, grad))
     if opts.get("compact"):  # measured (profiles/r02_jit_sweep.md): C5 field + gradient 19.7 -> 18.8 ms, C3 value 1.82 -> 1.44 ms
         o.update(width=2, min_ctas=8, stage8=False)
     o.update({k: v for k, v in opts.items() if v is not None})
+    em = None
+    adjoint = bool(o["adjoint"]) and grad == "spatial" and o["slots"] == "reg"
+    if adjoint:  # gradient by pull-backs (ab_adjoint.cuh) when every op of the program has one
+        try:
+            em = _AdjointEmitter(sig)
+            for i in range(len(sig)):
+                em.op(i)
+            em.finish()
+        except _NoAdjoint:
+            em, adjoint = None, False
+    if adjoint and dtype == "f32":  # fewer live registers than three tangents per coordinate: one more CTA per SM fits
+        lite = all((int(w) & 0xffff) in LITE_OPS for w in sig)
+        tuned = dict(width=2, min_ctas=9) if opts.get("compact") else (dict(width=4, min_ctas=6, rowsplit=True) if lite else {})
+        o.update({k: v for k, v in tuned.items() if opts.get(k) is None})
     if o["multicast"]:
         o["store"] = 4  # multimem.st: `out` is a multicast address (ab_eval_grid_multicast)
     W = int(o["width"])
     if (T, W) not in (("float", 1), ("float", 2), ("float", 4), ("float", 8), ("double", 1), ("double", 2)):
         raise ValueError(f"no {W}-wide store for {T}")
     S = f"Pack<{T}, {W}>" if K == 0 else f"Dual<Pack<{T}, {W}>, {K}>"
-    em = _Emitter(sig, param, o["slots"])
-    for i in range(len(sig)):
-        em.op(i)
+    if em is None:
+        em = _Emitter(sig, param, o["slots"])
+        for i in range(len(sig)):
+            em.op(i)
     decls = []
     if o["slots"] == "reg":
         if em.n_p:
-            decls.append("    Pt<S> " + ", ".join(f"P{i}" for i in range(em.n_p)) + ";")
+            decls.append(f"    Pt<{'P' if adjoint else 'S'}> " + ", ".join(f"P{i}" for i in range(em.n_p)) + ";")
         if em.n_v:
             decls.append("    S " + ", ".join(f"V{i}" for i in range(em.n_v)) + ";")
     dcode = {"f32": 0, "f64": 1}[dtype]  # AB_F32 / AB_F64
     gcode = {"none": 0, "spatial": 1, "param": 2}[grad]
     rep = {"VERSION": CODEGEN_VERSION, "HASH": signature_hash(sig, dcode, gcode), "NOPS": len(sig),
-           "KINDNAME": f"{dtype}, grad={grad}", "WIDTH": W, "SLOTS": "registers" if o["slots"] == "reg" else "shared memory",
+           "KINDNAME": f"{dtype}, grad={grad}" + (" (gradient by pull-backs, ab_adjoint.cuh)" if adjoint else ""), "WIDTH": W, "SLOTS": "registers" if o["slots"] == "reg" else "shared memory",
            "T": T, "S": S, "PARAM": "true" if param else "false", "NT": int(o["nt"]),
            "TABLES": "true" if em.tables else "false", "NP": em.n_p if o["slots"] == "smem" else 0,
            "NV": em.n_v if o["slots"] == "smem" else 0, "MINCTAS": int(o["min_ctas"]), "IS2D": int(bool(o["is2d"])), "STOREPOLICY": int(o["store"]),
@@ -457,10 +640,13 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
         rep["EMIT"] = "    emit(kp, acc, idx, aligned);"
     if o["compact"] and not (W == 2 and not param and int(o["nt"]) == 128 and not o["is2d"]):
         raise ValueError("compact tiles: 2 points per thread, 128 threads, 3D grids, value / spatial-gradient kernels")
-    body_one = """    Pt<S> p;
+    body_one = ("""    Pt<P> p;  // plain coordinates: the gradient is pulled back through the coordinate ops afterwards (ab_adjoint.cuh)
+    seed(p, cx, cy, cz);
+    S acc(T(0));
+""" if adjoint else """    Pt<S> p;
     seed(p, cx, cy, cz);
     S acc = constant_like(p.x, T(0));
-@DECLS@
+""") + """@DECLS@
 @BODY@
     if constexpr (kParam) {
       if (kp.loss_accum) {
@@ -499,6 +685,7 @@ _build_slots = threading.Semaphore(int(os.environ.get("AB_JIT_JOBS", "2")))  # b
 # what a generated translation unit includes (directly or through ab_interp.cuh): only these decide whether a cached binary
 # is still valid, so unrelated edits elsewhere in csrc/ do not throw the cache away
 _INCLUDED = (os.path.join(CSRC, "ab_interp.cuh"), os.path.join(CSRC, "ab_ops.cuh"), os.path.join(CSRC, "ab_math.cuh"),
+             os.path.join(CSRC, "ab_adjoint.cuh"),
              os.path.join(CSRC, "ab_tree.cuh"), os.path.join(CSRC, "ab_spec_default.h"),
              os.path.join(os.path.dirname(HERE), "include", "aegolius_b200.h"))
 

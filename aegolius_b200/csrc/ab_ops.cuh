@@ -137,7 +137,7 @@ AB_DEV void op_absx_sub(Pt<S>& p, A a) { typedef typename S::scalar T; p.x = abs
 // -theta_k, theta_k = k*angle + angle/2, k = floor(phi/angle): the sector comes from atan2, the rotation from the
 // host-computed table (fewer roundings than the polar round trip, no sqrt / sincos / mod).
 template <typename S, typename A>
-AB_DEV void op_rotsym(Pt<S>& p, A a) {
+AB_DEV void op_rotsym(Pt<S>& p, A a, Pack<typename S::scalar, S::width>& c, Pack<typename S::scalar, S::width>& s) {
   typedef typename S::scalar T;
   constexpr int W = S::width;
   const T* tab = raw_args(a);  // angle and sector table are structural: no parameter tangent flows through them
@@ -147,7 +147,6 @@ AB_DEV void op_rotsym(Pt<S>& p, A a) {
   const T inv = s_rcp(ang);
   auto vx = value_of(p.x), vy = value_of(p.y);
   const Pack<T, W> ph = atan2_(vy, vx);
-  Pack<T, W> c, s;
 #pragma unroll
   for (int i = 0; i < W; i++) {
     T phi = ph.v[i];
@@ -164,6 +163,11 @@ AB_DEV void op_rotsym(Pt<S>& p, A a) {
   S ny = fma_lane(p.x, -s, mul_lane(p.y, c));
   p.x = nx;
   p.y = ny;
+}
+template <typename S, typename A>
+AB_DEV void op_rotsym(Pt<S>& p, A a) {
+  Pack<typename S::scalar, S::width> c, s;
+  op_rotsym(p, a, c, s);
 }
 // modifications.py:427-431
 template <typename S, typename A>
@@ -326,7 +330,7 @@ AB_DEV void curve_frames(Pt<Pack<T, W>>& p, const T* rec, const int* idx, int mo
 // d(C, j) <= min_j d(C, j) + 2R (triangle inequality). Every thread then scans just that candidate list for its W points.
 // Cost ~ n/32 + (#candidates) per point instead of n; scattered point sets degrade gracefully to the full scan.
 template <typename S, typename A>
-AB_DEV void op_curve_inst(Pt<S>& p, A a, int mode) {
+AB_DEV void curve_search(const Pt<S>& p, A a, int mode, int (&idx)[S::width]) {
   typedef typename S::scalar T;
   const T* tab = raw_args(a);  // instance table: structural (no parameter tangents)
   const int n = (int)tab[0];
@@ -358,7 +362,6 @@ AB_DEV void op_curve_inst(Pt<S>& p, A a, int mode) {
   // widened a little against rounding: it only admits extra candidates, never drops the true nearest
   const T reach = s_sqrt(dmin) * T(1.00001) + T(2.0001) * s_sqrt(r2) + T(1e-30);
   const T cut = reach * reach;
-  int idx[W];
   unsigned m = __ballot_sync(FULL, d_first <= cut);
   if (n <= 32 && (m & (m - 1)) == 0) {
     // one candidate for the whole warp (the common case away from the cell boundaries of the instances): it is the
@@ -391,7 +394,12 @@ AB_DEV void op_curve_inst(Pt<S>& p, A a, int mode) {
       }
     }
   }
-  curve_frames(p, rec, idx, mode);
+}
+template <typename S, typename A>
+AB_DEV void op_curve_inst(Pt<S>& p, A a, int mode) {
+  int idx[S::width];
+  curve_search(p, a, mode, idx);
+  curve_frames(p, raw_args(a) + 4, idx, mode);
 }
 
 // ---- value ops --------------------------------------------------------------------------------------------------------

@@ -81,3 +81,17 @@ def load_case(golden, name):
     prog = Program.from_arrays(keys, prefix="prog_")
     return dict(prog=prog, expected=keys["expected"], size=tuple(float(s) for s in keys["size"]),
                 res=tuple(int(r) for r in keys["res"]), extent=float(keys["extent"]))
+
+
+# golden scenarios whose field + gradient kernels are prebuilt (tools/prebuild_jit.py) and checked on point lists
+# (tests/test_gpu_jit.py): every coordinate op with a gradient pull-back (csrc/ab_adjoint.cuh), the primitives with a
+# written-out local gradient, and the combine / value ops on top of them
+GRADIENT_CASES = (
+    "c1_sphere_box_smooth_union", "c3_deep_tree", "mod_twist", "mod_bend", "prim3_torus", "comb_SMOOTH_INTERSECT2_BOLTZMANN",
+    "struct_extruded_combo", "prim3_sphere", "prim3_box", "prim3_cylinder", "prim3_cone", "mod_elongation", "mod_revolution",
+    "mod_axis_revolution", "mod_extrusion", "mod_shear_generic", "mod_infinite_repetition", "mod_finite_repetition_rescaled",
+    "mod_symmetry", "mod_mirror", "mod_rotational_symmetry", "mod_linear_instancing", "mod_curve_instancing",
+    "mod_aligned_curve_instancing", "mod_fully_aligned_curve_instancing", "mod_scale_sdf", "mod_rotate_sdf",
+    "mod_chain_twist_elong_round", "mod_onion", "comb_UNION_3", "comb_SMOOTH_SUBTRACT2", "struct_plate_revolved_union",
+    "struct_deep_combines", "struct_2d_mirror_rotsym", "ex_pawn_3D", "ex_rod_3D", "ex_chip_3D",
+)

@@ -17,7 +17,7 @@ import shutil
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_case
+from conftest import GRADIENT_CASES, golden_names, load_case
 from oracle import interp_np
 from test_gpu_parity import _compare, _spec, F32_TOL, F64_TOL
 
@@ -61,22 +61,30 @@ def test_compiled_kernels_match_reference_and_interpreter(golden, name):
     assert d.size == 0 or d.max() <= 2e-6 * ext, f"{name}: fp32 compiled vs interpreter max |d| = {d.max():.3e}"
 
 
-@pytest.mark.parametrize("name", ["c1_sphere_box_smooth_union", "c3_deep_tree", "mod_twist", "mod_bend", "prim3_torus",
-                                  "comb_SMOOTH_INTERSECT2_BOLTZMANN", "struct_extruded_combo"])
+@pytest.mark.parametrize("name", GRADIENT_CASES)
 def test_compiled_gradient_kernels_on_point_lists(golden, name):
-    """Spatial-gradient kernels, points mode, ragged size: compiled vs interpreter (fp64 to the bit, fp32 to a few ulp)."""
+    """Field + gradient kernels, points mode, ragged size: compiled vs interpreter. The compiled kernels pull the gradient
+    back through the coordinate ops (csrc/ab_adjoint.cuh) where the interpreter pushes three tangents forward: the FIELD is
+    the same arithmetic (fp64 to the bit), the GRADIENT the same derivative in another association order (fp64 within
+    1e-11, fp32 within 2e-5, both relative to the largest gradient component of the scenario, away from the kinks the
+    oracle reports). Measured over all 134 single-stage golden scenarios (tools/check_adjoint.py): 2.8e-14 / 3.8e-6."""
     c = load_case(golden, name)
     rng = np.random.default_rng(5)
-    co = rng.uniform(-0.45, 0.45, size=(3, 10007)) * np.asarray(c["size"]).reshape(3, 1)
-    (fa, ga), (fb, gb), hits = _both(c["prog"], co, "f64", grad="spatial")
-    assert hits >= 1
-    assert np.array_equal(fa, fb, equal_nan=True) and np.array_equal(ga, gb, equal_nan=True)
-    (fa, ga), (fb, gb), hits = _both(c["prog"], co, "f32", grad="spatial")
-    assert hits >= 1
+    size3 = np.ones(3)
+    size3[:len(c["size"])] = c["size"]
+    co = rng.uniform(-0.45, 0.45, size=(3, 10007)) * size3.reshape(3, 1)
     _, margin = interp_np.run(c["prog"], co, return_margin=True)
     keep = margin > 1e-4 * c["extent"]
+    assert keep.mean() > 0.5
+    (fa, ga), (fb, gb), hits = _both(c["prog"], co, "f64", grad="spatial")
+    assert hits >= 1, f"{name}: no compiled fp64 gradient kernel (python tools/prebuild_jit.py)"
+    assert np.array_equal(fa, fb, equal_nan=True)
+    scale = max(1.0, float(np.max(np.abs(gb[:, keep]))))
+    assert np.max(np.abs(ga - gb)[:, keep]) <= 1e-11 * scale
+    (fa, ga), (fb, gb), hits = _both(c["prog"], co, "f32", grad="spatial")
+    assert hits >= 1
     assert np.max(np.abs(fa - fb)[keep]) <= 2e-6 * c["extent"]
-    assert np.max(np.abs(ga - gb)[:, keep]) <= 2e-5
+    assert np.max(np.abs(ga - gb)[:, keep]) <= 2e-5 * scale
 
 
 def test_compiled_slabs_concatenate_bit_identically(golden):

@@ -18,8 +18,8 @@ def items():
     from aegolius_b200.program import Program
     out = []
     path = os.path.join(ROOT, "tests", "golden", "scenarios.npz")
-    grad_cases = {"c1_sphere_box_smooth_union", "c3_deep_tree", "mod_twist", "mod_bend", "prim3_torus",
-                  "comb_SMOOTH_INTERSECT2_BOLTZMANN", "struct_extruded_combo"}
+    from conftest import GRADIENT_CASES
+    grad_cases = set(GRADIENT_CASES)
     with np.load(path, allow_pickle=False) as d:
         for name in [str(n) for n in d["__names__"]]:
             keys = {k[len(name) + 1:]: d[k] for k in d.files if k.startswith(name + "/")}
