@@ -515,7 +515,7 @@ AB_PROG_EXPORT int ab_prog_launch(const void* kparams, int sms, unsigned long lo
     return (int)cudaSuccess;
   }
   const uint64_t tile_pts = (uint64_t)kNT * ProgS::width;
-  const uint32_t nb1 = (kp.g.n1 + kTileRows - 1) / kTileRows, nb2 = compact_col_blocks(kp.g.n2);
+  const uint32_t nb1 = (kp.g.n1 + compact_tile_rows(ProgS::width) - 1) / compact_tile_rows(ProgS::width), nb2 = compact_col_blocks(kp.g.n2);
   if (kCompact && (!kp.grid_mode || kp.g.is2d || kp.n % kp.g.plane)) {
     *status = AB_EINVAL;  // (run_program only sends whole planes of 3D grids here)
     return (int)cudaSuccess;
@@ -561,6 +561,8 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
     o.update(default_options(sig, dtype, grad))
     if opts.get("compact"):  # measured (profiles/r02_jit_sweep.md): C5 field + gradient 19.7 -> 18.8 ms, C3 value 1.82 -> 1.44 ms
         o.update(width=2, min_ctas=8, stage8=False)
+        if dtype == "f32" and grad == "none":  # 4 points per thread halve the per-thread share of the search: 1.54 -> 1.36 ms
+            o.update(width=4, min_ctas=7)
     o.update({k: v for k, v in opts.items() if v is not None})
     em = None
     adjoint = bool(o["adjoint"]) and grad == "spatial" and o["slots"] == "reg"
@@ -574,7 +576,8 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
             em, adjoint = None, False
     if adjoint and dtype == "f32":  # fewer live registers than three tangents per coordinate: one more CTA per SM fits
         lite = all((int(w) & 0xffff) in LITE_OPS for w in sig)
-        tuned = dict(width=2, min_ctas=9) if opts.get("compact") else (dict(width=4, min_ctas=6, rowsplit=True) if lite else {})
+        # (C5 field + gradient on compact tiles: 2 points per thread 15.4 ms, 4 points 13.8 ms at 6 CTAs / SM, 79 registers)
+        tuned = dict(width=4, min_ctas=6) if opts.get("compact") else (dict(width=4, min_ctas=5, rowsplit=True) if lite else {})
         o.update({k: v for k, v in tuned.items() if opts.get(k) is None})
     if o["multicast"]:
         o["store"] = 4  # multimem.st: `out` is a multicast address (ab_eval_grid_multicast)
@@ -611,16 +614,16 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
     const uint32_t idx = tile * tile_pts + threadIdx.x * W;
     P cx, cy, cz;
     tile_coords<kIs2D>(kp, walk, idx, n32, cx, cy, cz);"""
-    compact_head = """  // compact tiles: kTileRows x kTileCols points of one i0 plane per CTA (ab_interp.cuh), 3D grids only
-  const uint32_t nb1 = (kp.g.n1 + kTileRows - 1) / kTileRows, nb2 = compact_col_blocks(kp.g.n2);
+    compact_head = """  // compact tiles: compact_tile_rows(W) x 16 points of one i0 plane per CTA (ab_interp.cuh), 3D grids only
+  const uint32_t nb1 = (kp.g.n1 + compact_tile_rows(ProgS::width) - 1) / compact_tile_rows(ProgS::width), nb2 = compact_col_blocks(kp.g.n2);
   const uint32_t n_tiles = (uint32_t)(kp.n / kp.g.plane) * nb1 * nb2;
   CompactWalk walk;
   compact_walk_begin(kp, nb1, nb2, walk);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     uint32_t idx;
-    bool valid0, valid1;
+    uint32_t valid;
     P cx, cy, cz;
-    compact_coords(kp, walk, nb1, nb2, cx, cy, cz, idx, valid0, valid1);"""
+    compact_coords(kp, walk, nb1, nb2, cx, cy, cz, idx, valid);"""
     split_head = """  const uint32_t tile_pts = (uint32_t)kNT * W;
   const uint32_t n32 = (uint32_t)kp.n;
   const uint32_t n_tiles = (n32 + tile_pts - 1) / tile_pts;
@@ -632,14 +635,14 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
     rep["LOOPHEAD"] = compact_head if o["compact"] else (split_head if o["rowsplit"] else flat_head)
     rep["COMPACT"] = "true" if o["compact"] else "false"
     if o["compact"]:
-        rep["EMIT"] = "    emit_compact(kp, acc, idx, valid0, valid1);"
+        rep["EMIT"] = "    emit_compact(kp, acc, idx, valid);"
     elif rep["STAGE8"] == "true":
         rep["EMIT"] = ("    float4* stage = reinterpret_cast<float4*>(smem_raw + kp.off_args) + (threadIdx.x >> 5) * 64;\n"
                        "    store_pack_w8_transposed(kp.out, acc, tile * tile_pts + (threadIdx.x & ~31u) * W, kp.n, aligned, stage);")
     else:
         rep["EMIT"] = "    emit(kp, acc, idx, aligned);"
-    if o["compact"] and not (W == 2 and not param and int(o["nt"]) == 128 and not o["is2d"]):
-        raise ValueError("compact tiles: 2 points per thread, 128 threads, 3D grids, value / spatial-gradient kernels")
+    if o["compact"] and not ((W == 2 or (W == 4 and T == "float")) and not param and int(o["nt"]) == 128 and not o["is2d"]):
+        raise ValueError("compact tiles: 2 (or, fp32, 4) points per thread, 128 threads, 3D grids, value / spatial-gradient kernels")
     body_one = ("""    Pt<P> p;  // plain coordinates: the gradient is pulled back through the coordinate ops afterwards (ab_adjoint.cuh)
     seed(p, cx, cy, cz);
     S acc(T(0));

@@ -479,14 +479,17 @@ AB_DEV void emit(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint32_t 
 // ---- compact tiles (program-compiled kernels with warp-cooperative ops, 3D grids) ---------------------------------------------
 // The flat walk above gives a warp 32 W CONSECUTIVE points: a 0.37-long needle on the 1025^3 headline grid. Warp-
 // cooperative ops (nearest curve instance: candidates = instances within d_min + 2 R of the warp's reference point, R = warp
-// radius) want a small R. Here a CTA of 128 threads owns a tile of TR rows (i1) x TC columns (i2) of one i0 plane, W = 2
-// points per thread along i2; a warp covers 4 rows x 16 columns (R is ~4x smaller) and a thread's points never straddle a
-// row. SPOMSO rows have an odd length, so a fixed column grid would start every row segment at a different offset inside
+// radius) want a small R. Here a CTA of 128 threads owns a tile of TR rows (i1) x 16 columns (i2) of one i0 plane, W = 2 or
+// 4 points per thread along i2; a warp covers 4 (8) rows x 16 columns (R is ~4x smaller) and a thread's points never
+// straddle a row. SPOMSO rows have an odd length, so a fixed column grid would start every row segment at a different offset inside
 // its 32-byte sector (measured: 37 % more DRAM traffic than the algorithmic bytes, read-modify-write of half-written
 // sectors). The column blocks are therefore anchored per ROW at the row's first 32-byte boundary in the OUTPUT buffer:
 // every 64-byte segment a warp stores is two whole sectors and every thread's pair is 8-byte aligned; the price is one
 // extra, partly masked column block per row.
-constexpr uint32_t kTileRows = 16, kTileCols = 16;
+constexpr uint32_t kTileCols = 16;
+// rows of a tile for W points per thread: a warp covers 32 W / 16 rows x 16 columns (W = 2: 4 x 16, W = 4: 8 x 16, about the
+// same warp radius), a CTA of 4 warps stacks them: 16 rows (W = 2) or 32 rows (W = 4)
+__host__ __device__ constexpr uint32_t compact_tile_rows(int W) { return 8u * (uint32_t)W; }
 struct CompactWalk {
   uint32_t b0, b1, b2;  // tile coordinates: i0 plane (local to the launch), row block, column block
 };
@@ -499,26 +502,31 @@ AB_DEV void compact_walk_begin(const KParams<T>& kp, uint32_t nb1, uint32_t nb2,
   w.b1 = rem / nb2;
   w.b2 = rem - w.b1 * nb2;
 }
-// coordinates of this thread's two points of the current tile, their flat index in the launch's output and validity; then
-// the step to the CTA's next tile (tile_stride[] = gridDim.x decomposed over (plane blocks, row blocks, column blocks))
-template <typename T>
-AB_DEV void compact_coords(const KParams<T>& kp, CompactWalk& w, uint32_t nb1, uint32_t nb2, Pack<T, 2>& cx, Pack<T, 2>& cy,
-                           Pack<T, 2>& cz, uint32_t& idx, bool& valid0, bool& valid1) {
+// coordinates of this thread's W points of the current tile, their flat index in the launch's output and validity (bit j of
+// `valid` = point j is inside the grid); then the step to the CTA's next tile (tile_stride[] = gridDim.x decomposed over
+// (plane blocks, row blocks, column blocks))
+template <typename T, int W>
+AB_DEV void compact_coords(const KParams<T>& kp, CompactWalk& w, uint32_t nb1, uint32_t nb2, Pack<T, W>& cx, Pack<T, W>& cy,
+                           Pack<T, W>& cz, uint32_t& idx, uint32_t& valid) {
+  constexpr uint32_t per_row = kTileCols / W;   // threads along a row segment
+  constexpr uint32_t warp_rows = 32 / per_row;  // rows of one warp
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t i1 = w.b1 * kTileRows + warp * 4 + (lane >> 3);
+  const uint32_t i1 = w.b1 * compact_tile_rows(W) + warp * warp_rows + lane / per_row;
   const uint32_t row0 = (w.b0 * kp.g.n1 + i1) * kp.g.n2;  // flat index of the row's first sample
   // samples of this row before its first 32-byte boundary in the output buffer (0 .. 32 / sizeof(T) - 1)
   constexpr uint32_t per_sector = 32 / sizeof(T);
   const uint32_t lead = (per_sector - (uint32_t)((reinterpret_cast<uintptr_t>(kp.out) / sizeof(T) + row0) % per_sector)) % per_sector;
   // block b2 holds columns [lead + 16 (b2 - 1), lead + 16 b2): block 0 is the (short) lead-in up to the boundary
-  const int32_t i2 = (int32_t)(lead + w.b2 * kTileCols + (lane & 7) * 2) - (int32_t)kTileCols;
+  const int32_t i2 = (int32_t)(lead + w.b2 * kTileCols + (lane % per_row) * W) - (int32_t)kTileCols;
   const bool row_ok = i1 < kp.g.n1;
-  valid0 = row_ok && i2 >= 0 && i2 < (int32_t)kp.g.n2;
-  valid1 = row_ok && i2 + 1 >= 0 && i2 + 1 < (int32_t)kp.g.n2;
+  valid = 0;
+#pragma unroll
+  for (int j = 0; j < W; j++) valid |= (row_ok && i2 + j >= 0 && i2 + j < (int32_t)kp.g.n2) ? (1u << j) : 0u;
   const uint32_t c1 = row_ok ? i1 : kp.g.n1 - 1;
-  const int32_t c2 = i2 < -1 ? -1 : (i2 >= (int32_t)kp.g.n2 ? (int32_t)kp.g.n2 - 1 : i2);  // masked lanes: a nearby valid position
-  cx = Pack<T, 2>(grid_coord(kp.g, 0, w.b0 + kp.g.i0_begin, T()));
-  cy = Pack<T, 2>(grid_coord(kp.g, 1, c1, T()));
+  // masked lanes: a nearby position (their coordinates only have to be finite)
+  const int32_t c2 = i2 < -(W - 1) ? -(W - 1) : (i2 >= (int32_t)kp.g.n2 ? (int32_t)kp.g.n2 - 1 : i2);
+  cx = Pack<T, W>(grid_coord(kp.g, 0, w.b0 + kp.g.i0_begin, T()));
+  cy = Pack<T, W>(grid_coord(kp.g, 1, c1, T()));
   grid_coord_run(kp.g, 2, c2, cz);
   idx = row0 + (uint32_t)i2;  // (wraps for masked lanes, which never store)
   w.b2 += kp.tile_stride[2];
@@ -533,25 +541,26 @@ AB_DEV void compact_coords(const KParams<T>& kp, CompactWalk& w, uint32_t nb1, u
   }
   w.b0 += kp.tile_stride[0];
 }
-template <typename T>
-AB_DEV void store2_masked(T* dst, const Pack<T, 2>& v, uint32_t idx, bool valid0, bool valid1) {
+template <typename T, int W>
+AB_DEV void store_masked(T* dst, const Pack<T, W>& v, uint32_t idx, uint32_t valid) {
   T* p = dst + idx;
-  if (valid0 && valid1 && (reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0) {
-    store_pack(dst, v, idx, (uint64_t)idx + 2, true);
+  if (valid == (1u << W) - 1 && (reinterpret_cast<uintptr_t>(p) & (W * sizeof(T) - 1)) == 0) {
+    store_pack(dst, v, idx, (uint64_t)idx + W, true);
   } else {
-    if (valid0) ab_st(p, v.v[0]);
-    if (valid1) ab_st(p + 1, v.v[1]);
+#pragma unroll
+    for (int j = 0; j < W; j++)
+      if (valid & (1u << j)) ab_st(p + j, v.v[j]);
   }
 }
-template <typename T>
-AB_DEV void emit_compact(const KParams<T>& kp, const Pack<T, 2>& acc, uint32_t idx, bool valid0, bool valid1) {
-  store2_masked(kp.out, acc, idx, valid0, valid1);
+template <typename T, int W>
+AB_DEV void emit_compact(const KParams<T>& kp, const Pack<T, W>& acc, uint32_t idx, uint32_t valid) {
+  store_masked(kp.out, acc, idx, valid);
 }
-template <typename T, int K>
-AB_DEV void emit_compact(const KParams<T>& kp, const Dual<Pack<T, 2>, K>& acc, uint32_t idx, bool valid0, bool valid1) {
-  store2_masked(kp.out, acc.v, idx, valid0, valid1);
+template <typename T, int W, int K>
+AB_DEV void emit_compact(const KParams<T>& kp, const Dual<Pack<T, W>, K>& acc, uint32_t idx, uint32_t valid) {
+  store_masked(kp.out, acc.v, idx, valid);
 #pragma unroll
-  for (int k = 0; k < K; k++) store2_masked(kp.grad + (uint64_t)k * kp.grad_stride, acc.d[k], idx, valid0, valid1);
+  for (int k = 0; k < K; k++) store_masked(kp.grad + (uint64_t)k * kp.grad_stride, acc.d[k], idx, valid);
 }
 
 // P_FIELD: the value of a precomputed per-point field (the output of a grid stencil), indexed like `out`
