@@ -26,6 +26,9 @@
 #ifndef AB_FAST_ATAN2
 #define AB_FAST_ATAN2 1 /* packed polynomial atan2 for fp32 (see atan2_ below) instead of atan2f */
 #endif
+#ifndef AB_FAST_SINCOS
+#define AB_FAST_SINCOS 1 /* packed Cody-Waite + polynomial sincos for fp32 (see sincos_ below) instead of sincosf per lane */
+#endif
 #ifndef AB_FAST_DIV
 #define AB_FAST_DIV 1 /* rcp.approx-based division (<=2 ulp) instead of the IEEE sequence (~14 issue slots) */
 #endif
@@ -358,8 +361,47 @@ AB_DEV Pack<T, W> operator/(const Pack<T, W>& a, const Pack<T, W>& b) { return d
 template <typename T, int W>
 AB_DEV Pack<T, W> operator/(const Pack<T, W>& a, T b) { return a * s_rcp(b); }
 
-template <typename T, int W>
-AB_DEV void sincos_(const Pack<T, W>& a, Pack<T, W>& s, Pack<T, W>& c) {
+template <int W>
+AB_DEV void sincos_(const Pack<double, W>& a, Pack<double, W>& s, Pack<double, W>& c) {
+#pragma unroll
+  AB_PACK_LOOP s_sincos(a.v[i], s.v[i], c.v[i]);
+}
+// sincos — fp32: q = rint(a 2/pi) by the 1.5 * 2^23 trick (its low mantissa bits are the quadrant), r = a - q pi/2 in three
+// FMA steps (pi/2 split into three floats), sin r = r + r^3 S(r^2), cos r = 1 - r^2/2 + r^4 C(r^2) (degree-2 S and C, the
+// Cephes single-precision sets), quadrant swap / signs per lane. All the arithmetic runs packed (two points per issue
+// slot): ~17 packed + 9 per-lane instructions per pair instead of two ~35-instruction sincosf calls. Error <= 1.6 ulp for
+// |a| <= 2000 (checked against fp64 on 8 M samples); larger arguments take sincosf.
+template <int W>
+AB_DEV void sincos_(const Pack<float, W>& a, Pack<float, W>& s, Pack<float, W>& c) {
+#if AB_FAST_SINCOS
+  typedef Pack<float, W> P;
+  bool small = true;
+#pragma unroll
+  AB_PACK_LOOP small = small && (fabsf(a.v[i]) <= 2000.0f);
+  if (small) {
+    const P t = fma_(a, 0.636619772367581343f, P(12582912.0f));
+    const P q = t - 12582912.0f;
+    P r = fma_(q, -1.57079637050628662109375f, a);
+    r = fma_(q, 4.37113900018624283e-8f, r);
+    r = fma_(q, 1.71512449173013125e-15f, r);
+    const P r2 = r * r;
+    P sp = fma_(r2, -1.9515295891e-4f, P(8.3321608736e-3f));
+    sp = fma_(sp, r2, P(-1.6666654611e-1f));
+    sp = fma_(r * r2, sp, r);
+    P cp = fma_(r2, 2.443315711809948e-5f, P(-1.388731625493765e-3f));
+    cp = fma_(cp, r2, P(4.166664568298827e-2f));
+    cp = fma_(r2 * r2, cp, fma_(r2, -0.5f, P(1.0f)));
+#pragma unroll
+    AB_PACK_LOOP {
+      const unsigned n = __float_as_uint(t.v[i]);
+      const bool swap = n & 1u;
+      const float ss = swap ? cp.v[i] : sp.v[i], cc = swap ? sp.v[i] : cp.v[i];
+      s.v[i] = __uint_as_float(__float_as_uint(ss) ^ ((n & 2u) << 30));
+      c.v[i] = __uint_as_float(__float_as_uint(cc) ^ (((n + 1u) & 2u) << 30));
+    }
+    return;
+  }
+#endif
 #pragma unroll
   AB_PACK_LOOP s_sincos(a.v[i], s.v[i], c.v[i]);
 }

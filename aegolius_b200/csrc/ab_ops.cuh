@@ -150,12 +150,22 @@ AB_DEV void op_rotsym(Pt<S>& p, A a, Pack<typename S::scalar, S::width>& c, Pack
 #pragma unroll
   for (int i = 0; i < W; i++) {
     T phi = ph.v[i];
-    if (phi < T(0)) phi += T(6.283185307179586476925286766559);
-    int k = (int)(phi * inv);
-    k = k < 0 ? 0 : (k >= nsec ? nsec - 1 : k);
-    // one more exact step: phi*inv may round across an integer
-    if (phi < (T)k * ang && k > 0) k--;
-    else if (phi >= (T)(k + 1) * ang && k + 1 < nsec) k++;
+    int k;
+    if constexpr (sizeof(T) == 4) {
+      // fp32: the angle itself carries ~1e-7 of rounding, so a sector decision that close to a boundary is arbitrary either
+      // way (the parity tests mask it through the oracle's margin): no exact re-check of the quotient
+      T t = phi * inv;
+      if (phi < T(0)) t += (T)nsec;
+      k = (int)t;
+      k = k < 0 ? 0 : (k >= nsec ? nsec - 1 : k);
+    } else {
+      if (phi < T(0)) phi += T(6.283185307179586476925286766559);
+      k = (int)(phi * inv);
+      k = k < 0 ? 0 : (k >= nsec ? nsec - 1 : k);
+      // one more exact step: phi*inv may round across an integer
+      if (phi < (T)k * ang && k > 0) k--;
+      else if (phi >= (T)(k + 1) * ang && k + 1 < nsec) k++;
+    }
     c.v[i] = tab[4 + 2 * k];
     s.v[i] = tab[5 + 2 * k];
   }
