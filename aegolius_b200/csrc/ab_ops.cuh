@@ -334,11 +334,15 @@ AB_DEV void curve_frames(Pt<Pack<T, W>>& p, const T* rec, const int* idx, int mo
 // modifications.py:1120-1127 / 1183-1191 / 1253-1261: nearest instance by position (the reference asks a KD-tree), then
 // subtract its position and, for the aligned variants, rotate into its frame. Record = pos(3) [+ rows dx,dy,dz (9)].
 //
-// Warp-cooperative exact search. A warp's 32*W points are spatially close (consecutive grid points), so the few instances
+// Warp-cooperative exact search. A warp's 32*W points are spatially close (a tile of grid points), so the few instances
 // that can be nearest for ANY of them are found once per warp: lane l measures instance l (32 per round) from a warp
-// reference point C; with R = max distance of the warp's points from C, instance j can only win if
-// d(C, j) <= min_j d(C, j) + 2R (triangle inequality). Every thread then scans just that candidate list for its W points.
-// Cost ~ n/32 + (#candidates) per point instead of n; scattered point sets degrade gracefully to the full scan.
+// reference point C; i* = the instance nearest to C, R = max distance of the warp's points from C. Instance j can only
+// win at a point of the ball B(C, R) if the bisector plane of (i*, j) cuts the ball:
+//     (d(C, j)^2 - d(C, i*)^2) / (2 |q_j - q_i*|) <= R,   tested squared (no square root),
+// which is exact and much tighter than the triangle inequality d(C, j) <= d(C, i*) + 2R far from the curve, where many
+// instances are almost equidistant (that test kept 2-3 candidates for most warps of the headline grid). Every thread then
+// scans just the candidate list for its W points. Cost ~ n/32 + (#candidates) per point instead of n; scattered point
+// sets degrade gracefully to the full scan.
 template <typename S, typename A>
 AB_DEV void curve_search(const Pt<S>& p, A a, int mode, int (&idx)[S::width]) {
   typedef typename S::scalar T;
@@ -363,16 +367,32 @@ AB_DEV void curve_search(const Pt<S>& p, A a, int mode, int (&idx)[S::width]) {
     const T dx = Cx - rec[j * stride], dy = Cy - rec[j * stride + 1], dz = Cz - rec[j * stride + 2];
     return s_fma(dx, dx, s_fma(dy, dy, dz * dz));
   };
+  // lane l measures instances l, l + 32, ... from the reference point and keeps its nearest
   const T d_first = lane < n ? lane_d2(lane) : T(3.0e38);
-  T dmin = d_first;
+  T dl = d_first;
+  int jl = lane;
   for (int base = 32; base < n; base += 32)
-    if (base + lane < n) dmin = s_min(dmin, lane_d2(base + lane));
+    if (base + lane < n) {
+      const T d = lane_d2(base + lane);
+      if (d < dl) {
+        dl = d;
+        jl = base + lane;
+      }
+    }
   r2 = warp_max_nonneg(r2);
-  dmin = warp_min_nonneg(dmin);
-  // widened a little against rounding: it only admits extra candidates, never drops the true nearest
-  const T reach = s_sqrt(dmin) * T(1.00001) + T(2.0001) * s_sqrt(r2) + T(1e-30);
-  const T cut = reach * reach;
-  unsigned m = __ballot_sync(FULL, d_first <= cut);
+  const T dmin = warp_min_nonneg(dl);
+  const unsigned who = __ballot_sync(FULL, dl == dmin);
+  const int istar = __shfl_sync(FULL, jl, who ? __ffs(who) - 1 : 0);  // (who == 0 only for NaN coordinates)
+  const T sx = rec[istar * stride], sy = rec[istar * stride + 1], sz = rec[istar * stride + 2];
+  // widened a little against rounding (of the squared distances and of R): it only admits extra candidates
+  const T lo = dmin * T(1.000002), r2w = T(4.002) * r2;
+  auto candidate = [&](int j, T dj) {
+    const T ex = rec[j * stride] - sx, ey = rec[j * stride + 1] - sy, ez = rec[j * stride + 2] - sz;
+    const T e2 = s_fma(ex, ex, s_fma(ey, ey, ez * ez));
+    const T diff = s_fma(dj, T(0.999998), -lo);
+    return diff <= T(0) || diff * diff <= s_fma(r2w, e2, T(1e-30));
+  };
+  unsigned m = __ballot_sync(FULL, lane < n && candidate(lane, d_first));
   if (n <= 32 && (m & (m - 1)) == 0) {
     // one candidate for the whole warp (the common case away from the cell boundaries of the instances): it is the
     // nearest instance of every point, no distance needs to be evaluated
@@ -387,7 +407,7 @@ AB_DEV void curve_search(const Pt<S>& p, A a, int mode, int (&idx)[S::width]) {
       idx[i] = 0;
     }
     for (int base = 0; base < n; base += 32) {
-      if (base) m = __ballot_sync(FULL, base + lane < n && lane_d2(base + lane) <= cut);
+      if (base) m = __ballot_sync(FULL, base + lane < n && candidate(base + lane, lane_d2(base + lane)));
       while (m) {  // warp-uniform loop over the candidates, in index order (ties resolve to the lowest index)
         const int j = base + __ffs(m) - 1;
         m &= m - 1;

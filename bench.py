@@ -40,12 +40,12 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_c5_compiled_kernel_ncu_summary.json")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_c5_adjoint_kernel_ncu_summary.json")
 
 
 def _ncu_summary():
     """Counters of the dominant kernel from the committed `ncu --set full` capture of this same command
-    (profiles/r02_c5_compiled_kernel_ncu_summary.json: one launch over the whole 1025^3 grid)."""
+    (profiles/r02_c5_adjoint_kernel_ncu_summary.json: one launch over the whole 1025^3 grid)."""
     try:
         with open(NCU_SUMMARY) as fh:
             return json.load(fh)
@@ -500,7 +500,7 @@ def run_gpu(args):
             "gpu_launches": launches, "compiled_kernel_launches": compiled_launches,
             "roofline": {"bound": "fp32-issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(n_local), "peak_source": peak_src,
-                         "kernel": "ab_prog_kernel (program-compiled, Dual<Pack<float,2>,3>)" if compiled_launches else
+                         "kernel": "ab_prog_kernel (program-compiled: compact tiles, 4 points per thread, gradient by pull-backs)" if compiled_launches else
                                    "ab_interp_kernel<Dual<Pack<float,2>,3>,float>",
                          "algorithmic_bytes_per_point": 16, "issue": issue,
                          "note": "deep tree: FP32-issue-bound, not HBM-bound (SURVEY §8d). achieved/peak/frac = algorithmic "

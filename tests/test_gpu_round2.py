@@ -22,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_c5_full_1025_cubed_field_and_gradient_f32_headline_kernel():
-    """What bench.py times: create_torch(C5, grad='spatial', f32) = the program-compiled Dual<Pack<float,2>,3> kernel.
+    """What bench.py times: create_torch(C5, grad='spatial', f32) = the program-compiled kernel (compact tiles, 4 points per
+    thread, gradient pulled back through the coordinate ops: csrc/ab_adjoint.cuh).
     300 000 sampled nodes: values within 1e-5 * extent with the sign mask, gradient against fp64 central differences of
     the oracle (h = 1e-6 * extent) away from kinks and branch boundaries.
 
