@@ -188,6 +188,15 @@ AB_DEV void fwd_curve_inst(Pt<Pack<T, W>>& p, const T* a, int mode, int (&idx)[W
 template <typename T, int W>
 AB_DEV void pb_curve_inst(Dual<Pack<T, W>, 3>& v, const T* a, const int (&idx)[W]) {
   typedef Pack<T, W> P;
+  if (same_index<W>(idx)) {  // one instance for the thread's points: broadcast record (curve_frames)
+    P r[12];
+    broadcast_record(a + 4, idx[0], 1, r);
+    const P gx = v.d[0], gy = v.d[1], gz = v.d[2];
+    v.d[0] = fma_(gz, r[9], fma_(gy, r[6], gx * r[3]));
+    v.d[1] = fma_(gz, r[10], fma_(gy, r[7], gx * r[4]));
+    v.d[2] = fma_(gz, r[11], fma_(gy, r[8], gx * r[5]));
+    return;
+  }
   constexpr int WC = (W % 2 == 0) ? 2 : 1;  // two points at a time, like curve_frames
 #pragma unroll
   for (int c0 = 0; c0 < W; c0 += WC) {

@@ -301,14 +301,46 @@ AB_DEV void frame_change(Pt<S>& p, const PK (&r)[12], int mode) {
     p.z = dz;
   }
 }
+// all W points of a thread in one instance (the rule: a thread's points are neighbours): the record is loaded once as
+// scalars and enters the packed arithmetic as a broadcast operand (no per-lane register shuffling)
+template <int W>
+AB_DEV bool same_index(const int* idx) {
+  bool same = true;
+#pragma unroll
+  for (int i = 1; i < W; i++) same = same && (idx[i] == idx[0]);
+  return same;
+}
+template <typename T, int W>
+AB_DEV void broadcast_record(const T* rec, int j, int mode, Pack<T, W> (&r)[12]) {
+  T q[12];
+  if (mode) {
+    load4(rec + j * 12, q[0], q[1], q[2], q[3]);
+    load4(rec + j * 12 + 4, q[4], q[5], q[6], q[7]);
+    load4(rec + j * 12 + 8, q[8], q[9], q[10], q[11]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k] = rec[j * 3 + k];
+#pragma unroll
+    for (int k = 3; k < 12; k++) q[k] = T(0);
+  }
+#pragma unroll
+  for (int k = 0; k < 12; k++) r[k] = Pack<T, W>(q[k]);
+}
 template <typename P, int K>
 AB_DEV void curve_frames(Pt<Dual<P, K>>& p, const typename P::scalar* rec, const int* idx, int mode) {
   P r[12];
-  gather_records(rec, idx, mode, r);
+  if (same_index<P::width>(idx)) broadcast_record(rec, idx[0], mode, r);
+  else gather_records(rec, idx, mode, r);
   frame_change(p, r, mode);
 }
 template <typename T, int W>
 AB_DEV void curve_frames(Pt<Pack<T, W>>& p, const T* rec, const int* idx, int mode) {
+  if (same_index<W>(idx)) {
+    Pack<T, W> r[12];
+    broadcast_record(rec, idx[0], mode, r);
+    frame_change(p, r, mode);
+    return;
+  }
   constexpr int WC = (W % 2 == 0) ? 2 : 1;
 #pragma unroll
   for (int c = 0; c < W; c += WC) {
