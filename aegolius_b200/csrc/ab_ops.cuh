@@ -44,6 +44,16 @@ AB_DEV Dual<P, K> rcp_arg(const Dual<P, K>& x) { return div_(Dual<P, K>(typename
 
 // ---- coordinate ops -------------------------------------------------------------------------------------------------
 
+// do the W points of a thread share one table index (instance, sector)? Then the entry is read once and enters the packed
+// arithmetic as a broadcast operand.
+template <int W>
+AB_DEV bool same_index(const int* idx) {
+  bool same = true;
+#pragma unroll
+  for (int i = 1; i < W; i++) same = same && (idx[i] == idx[0]);
+  return same;
+}
+
 // p = M p + b : folded apply_ec_transforms (transformations.py:232-242), shears, frames
 template <typename S, typename A>
 AB_DEV void op_affine(Pt<S>& p, A a) {
@@ -147,6 +157,7 @@ AB_DEV void op_rotsym(Pt<S>& p, A a, Pack<typename S::scalar, S::width>& c, Pack
   const T inv = s_rcp(ang);
   auto vx = value_of(p.x), vy = value_of(p.y);
   const Pack<T, W> ph = atan2_(vy, vx);
+  int ks[W];
 #pragma unroll
   for (int i = 0; i < W; i++) {
     T phi = ph.v[i];
@@ -166,8 +177,17 @@ AB_DEV void op_rotsym(Pt<S>& p, A a, Pack<typename S::scalar, S::width>& c, Pack
       if (phi < (T)k * ang && k > 0) k--;
       else if (phi >= (T)(k + 1) * ang && k + 1 < nsec) k++;
     }
-    c.v[i] = tab[4 + 2 * k];
-    s.v[i] = tab[5 + 2 * k];
+    ks[i] = k;
+  }
+  if (same_index<W>(ks)) {  // the thread's points share the sector: one table read, broadcast operands
+    c = Pack<T, W>(tab[4 + 2 * ks[0]]);
+    s = Pack<T, W>(tab[5 + 2 * ks[0]]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+      c.v[i] = tab[4 + 2 * ks[i]];
+      s.v[i] = tab[5 + 2 * ks[i]];
+    }
   }
   S nx = fma_lane(p.y, s, mul_lane(p.x, c)) - rad;
   S ny = fma_lane(p.x, -s, mul_lane(p.y, c));
@@ -303,13 +323,6 @@ AB_DEV void frame_change(Pt<S>& p, const PK (&r)[12], int mode) {
 }
 // all W points of a thread in one instance (the rule: a thread's points are neighbours): the record is loaded once as
 // scalars and enters the packed arithmetic as a broadcast operand (no per-lane register shuffling)
-template <int W>
-AB_DEV bool same_index(const int* idx) {
-  bool same = true;
-#pragma unroll
-  for (int i = 1; i < W; i++) same = same && (idx[i] == idx[0]);
-  return same;
-}
 template <typename T, int W>
 AB_DEV void broadcast_record(const T* rec, int j, int mode, Pack<T, W> (&r)[12]) {
   T q[12];

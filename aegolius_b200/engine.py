@@ -350,7 +350,7 @@ def program_tangent(geometry, params, argnum, rel_step=1e-6):
     h = rel_step * max(1.0, abs(theta))
     lo, hi = list(params), list(params)
     lo[argnum], hi[argnum] = theta - h, theta + h
-    p0, p_lo, p_hi = flatten(geometry(*params)), flatten(geometry(*lo)), flatten(geometry(*hi))
+    p0, p_lo, p_hi = (flatten(geometry(*q), fold_frames=False) for q in (params, lo, hi))
     if not (np.array_equal(p0.ops, p_lo.ops) and np.array_equal(p0.ops, p_hi.ops)):
         raise ValueError("the program structure changes with the parameter; cannot differentiate through it")
     # arguments the parameter does not reach are bit-identical at theta - h and theta + h: exactly zero tangent, nothing

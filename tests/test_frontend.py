@@ -230,3 +230,34 @@ def test_patch_rebinds_spomso_create_and_has_no_silent_fallback():
     finally:
         engine.unpatch()
     assert np.array_equal(s.create(co), ref)
+
+
+def test_affine_after_aligned_instancing_is_folded_into_the_frames():
+    """program._peephole(fold_frames): p' = M R_j (p - o_j) + b keeps only the translation as an op. Same field as the
+    unfolded program (oracle, fp64 rounding), one op less in C3; program_tangent keeps the affine (tables carry no
+    parameter tangents)."""
+    import numpy as np
+    import aegolius_b200 as ab
+    from aegolius_b200 import opcodes as oc, engine
+    from aegolius_b200.program import flatten
+    from oracle import interp_np
+    obj = ab.workloads.build_c3()
+    folded, plain = flatten(obj), flatten(obj, fold_frames=False)
+    codes = lambda p: [int(c) for c in p.ops["opcode"]]
+    assert len(codes(folded)) == len(codes(plain)) - 1
+    i = codes(plain).index(oc.CURVE_INST)
+    assert codes(plain)[i + 1] == oc.AFFINE and codes(folded)[i + 1] != oc.AFFINE
+    co = np.random.default_rng(3).uniform(-3, 3, size=(3, 5000))
+    assert np.max(np.abs(interp_np.run(folded, co) - interp_np.run(plain, co))) <= 1e-13
+
+    def build(angle):
+        t = ab.Torus(0.4, 0.1)
+        t.shear_xz(angle)  # modifications run outermost first: the instancing, then the shear (an AFFINE op)
+        t.aligned_curve_instancing(lambda s: np.stack([np.cos(s), np.sin(s), 0 * s]), (), (0.0, 2 * np.pi, 9))
+        return t
+
+    assert oc.AFFINE not in codes(flatten(build(0.3)))[1:]  # folded on the default path
+
+    prog = engine.program_tangent(build, [0.3], 0)
+    k = codes(prog).index(oc.CURVE_INST)
+    assert codes(prog)[k + 1] == oc.AFFINE and np.any(prog.dargs != 0)
