@@ -110,6 +110,10 @@ def default_options(sig, dtype, grad):
                 if n <= 4:
                     return dict(width=8, min_ctas=6, stage8=True, store=1, rowsplit=True)
                 return dict(width=8, min_ctas=8, rowsplit=n <= 64)
+            if any((int(w) & 0xffff) == oc.CURVE_INST for w in sig):
+                # flat walk with the warp-cooperative instance search: the fewer points a thread owns, the smaller the
+                # warp's needle (C3 513^3: 2 points 1.69 ms, 4 points 1.82, 8 points 1.90, 8 + second body 2.23)
+                return dict(width=2, min_ctas=7)
             if n <= 8:
                 return dict(width=8, min_ctas=8, rowsplit=True)
             return dict(width=8, min_ctas=5, rowsplit=True) if n <= 32 else dict(width=4, min_ctas=5)
@@ -583,6 +587,8 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
         o.update(min_ctas=8)
     if o["multicast"]:
         o["store"] = 4  # multimem.st: `out` is a multicast address (ab_eval_grid_multicast)
+        if dtype == "f32" and grad == "none" and opts.get("width") is None and int(o["width"]) < 4:
+            o.update(width=4, min_ctas=5)  # 128-bit multimem stores, a warp's store = 512 contiguous bytes
     W = int(o["width"])
     if (T, W) not in (("float", 1), ("float", 2), ("float", 4), ("float", 8), ("double", 1), ("double", 2)):
         raise ValueError(f"no {W}-wide store for {T}")
@@ -831,8 +837,10 @@ def ensure(prog, dtype="f32", grad=None, is2d=False, how=None, multicast=False, 
     grad = _GRAD_NAMES[grad]
     sig = signature(prog)
     compact = opts.pop("compact", None)
+    # (multicast stores: flat walk only — the 64-byte row segments of the compact tiles make poor NVLink packets: C5 field
+    # assembly on 8 GPUs 8.1 ms flat, 11.9 ms compact)
     variants = [bool(compact)] if compact is not None else \
-        ([True, False] if wants_compact_tiles(sig, dtype, grad, is2d) else [False])
+        ([True, False] if wants_compact_tiles(sig, dtype, grad, is2d) and not multicast else [False])
     ok = [_ensure_one(sig, dtype, grad, bool(is2d), how, multicast, c, opts) for c in variants]
     return ok[0]
 
