@@ -54,10 +54,11 @@ struct TapeElongate {
 };
 template <typename P, typename T>
 AB_DEV void fwd_elongate(Pt<P>& p, const T* a, TapeElongate<P>& t) {
-  t.in[0] = ge_(p.x, a[0]) & le_(p.x, a[3]);
-  t.in[1] = ge_(p.y, a[1]) & le_(p.y, a[4]);
-  t.in[2] = ge_(p.z, a[2]) & le_(p.z, a[5]);
   op_elongate(p, a);
+  // q - clamp(q, lo, hi) is exactly 0 inside [lo, hi] (the clamp returns q itself there): one compare per coordinate
+  t.in[0] = eq_(p.x, T(0));
+  t.in[1] = eq_(p.y, T(0));
+  t.in[2] = eq_(p.z, T(0));
 }
 template <typename P>
 AB_DEV void pb_elongate(Dual<P, 3>& v, const TapeElongate<P>& t) {

@@ -424,6 +424,7 @@ AB_PACK_CMP(lt_, <)
 AB_PACK_CMP(le_, <=)
 AB_PACK_CMP(gt_, >)
 AB_PACK_CMP(ge_, >=)
+AB_PACK_CMP(eq_, ==)
 
 template <int W>
 AB_DEV Mask<W> operator&(const Mask<W>& a, const Mask<W>& b) {
