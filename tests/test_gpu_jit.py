@@ -87,6 +87,29 @@ def test_compiled_gradient_kernels_on_point_lists(golden, name):
     assert np.max(np.abs(ga - gb)[:, keep]) <= 2e-5 * scale
 
 
+@pytest.mark.parametrize("name", ["c3_deep_tree", "c1_sphere_box_smooth_union"])
+def test_forward_tangent_build_matches_the_interpreter_gradient_to_the_bit(golden, name):
+    """AB_JIT_ADJOINT=0 / generate(adjoint=False): the straight-line kernel that carries three tangents forward like the
+    interpreter. fp64: field AND gradient bit-identical to the interpreter (the pull-back build is only rounding-close)."""
+    from aegolius_b200 import codegen as cg
+    c = load_case(golden, name)
+    sig = cg.signature(c["prog"])
+    forward = cg.binary_path(cg.generate(sig, "f64", "spatial", adjoint=False))
+    default = cg.binary_path(cg.generate(sig, "f64", "spatial"))
+    if not (os.path.exists(forward) and os.path.exists(default)):
+        pytest.skip("kernels not prebuilt (python tools/prebuild_jit.py)")
+    rng = np.random.default_rng(7)
+    co = rng.uniform(-0.45, 0.45, size=(3, 10007)) * np.asarray(c["size"]).reshape(3, 1)
+    cg.ensure(c["prog"], "f64", "spatial")  # the default build first, so that create() does not register it over ours
+    cg._register(forward, sig, "f64", "spatial", 0)  # re-registration replaces the launcher of this structure
+    try:
+        (fa, ga), (fb, gb), hits = _both(c["prog"], co, "f64", grad="spatial")
+    finally:
+        cg._register(default, sig, "f64", "spatial", 0)
+    assert hits >= 1
+    assert np.array_equal(fa, fb, equal_nan=True) and np.array_equal(ga, gb, equal_nan=True)
+
+
 def test_compiled_slabs_concatenate_bit_identically(golden):
     import aegolius_b200 as ab
     from aegolius_b200 import cabi

@@ -60,9 +60,30 @@ def items():
     return out
 
 
+FORWARD_TANGENT_CASES = ("c3_deep_tree", "c1_sphere_box_smooth_union")
+
+
+def forward_tangent_sources():
+    """fp64 field + gradient kernels built WITHOUT the pull-backs (adjoint=False) for two goldens: tests/test_gpu_jit.py
+    checks that this build returns the interpreter's gradient to the bit (AB_JIT_ADJOINT=0)."""
+    import numpy as np
+    from aegolius_b200 import codegen
+    from aegolius_b200.program import Program
+    out = []
+    with np.load(os.path.join(ROOT, "tests", "golden", "scenarios.npz"), allow_pickle=False) as d:
+        for name in FORWARD_TANGENT_CASES:
+            keys = {k[len(name) + 1:]: d[k] for k in d.files if k.startswith(name + "/")}
+            prog = Program.from_arrays(keys, prefix="prog_")
+            out.append(codegen.generate(codegen.signature(prog), "f64", "spatial", adjoint=False))
+    return out
+
+
 def main(verbose=True):
     from aegolius_b200 import codegen
-    return codegen.prebuild(items(), verbose=verbose)
+    res = codegen.prebuild(items(), verbose=verbose)
+    for src in forward_tangent_sources():
+        codegen.build_source(src)
+    return res
 
 
 if __name__ == "__main__":
