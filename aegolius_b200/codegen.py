@@ -404,6 +404,7 @@ class _AdjointEmitter(_Emitter):
             e(head)
             to = self.lca(self.acc_node, self.v_node[a])
             self.pull(f"V{a}", self.v_node[a], to)
+            self.v_node[a] = to
             self.pull("acc", self.acc_node, to)
             e(f"    acc = op_extrude_end<S, T>(acc, V{a});")
             self.acc_node = to
@@ -413,6 +414,7 @@ class _AdjointEmitter(_Emitter):
             to = self.lca(self.acc_node, self.v_node[a])
             e(f"    // {i}: operands of the combine into their common frame")
             self.pull(f"V{a}", self.v_node[a], to)
+            self.v_node[a] = to  # (the slot now holds the pulled-back gradient, should it be read again)
             self.pull("acc", self.acc_node, to)
             self.acc_node = to
             super().op(i)
