@@ -259,6 +259,9 @@ def _secondary(ab, engine, cabi, prog, spec, dev, local):
     probes = [
         ("sphere_1025^3_f32", ab.flatten(sph), ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
         ("C1_tree_1025^3_f32", ab.flatten(ab.workloads.build_c1()), ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
+        ("sphere_1025^3_f32_field+gradient", ab.flatten(sph), ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", "spatial"),
+        ("C1_tree_1025^3_f32_field+gradient", ab.flatten(ab.workloads.build_c1()), ab.GridSpec((4, 4, 4), (1024,) * 3), "f32",
+         "spatial"),
         ("C5_tree_1025^3_f32_value_only", prog, spec, "f32", None),
         ("C5_field+gradient_1025^3_f64", prog, spec, "f64", "spatial"),
     ]

@@ -34,6 +34,7 @@ def cases():
         parts.append(g)
     un = ab.CombineGeometry("UNION").combine(*parts)
     return {
+        "sphereg": (sph, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", "spatial"),
         "twist": (tw, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
         "union12": (un, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
         "sphere0": (sph0, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),

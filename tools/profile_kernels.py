@@ -30,6 +30,15 @@ def main():
         prog = ab.flatten(obj)
         engine.compile_program(prog, dtype="f32")
         engine.create_torch(prog, big, dtype="f32", out=buf)
+    if "--lite" in sys.argv:  # the four shallow-tree launches only: value, then field + gradient (pull-back builds)
+        gbuf = torch.empty((3, (big.n_points + 7) // 8 * 8), dtype=torch.float32, device=dev)
+        for obj in (sph, workloads.build_c1()):
+            prog = ab.flatten(obj)
+            engine.compile_program(prog, dtype="f32", grad="spatial")
+            engine.create_torch(prog, big, dtype="f32", grad="spatial", out=buf, out_grad=gbuf)
+        torch.cuda.synchronize()
+        print("profile_kernels ok (lite)")
+        return
     del buf
     torch.cuda.empty_cache()
     res = (513, 513, 513)
