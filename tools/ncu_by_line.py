@@ -72,6 +72,15 @@ def main():
     print("--- by call site in the interpreter (outermost frame) ---")
     for k, v in outer.most_common(top):
         print(f"{100 * v / tot:6.2f}%  {k}")
+    if os.environ.get("NCU_BY_OPCODE"):  # executed instructions per (outermost line, opcode class)
+        byop = collections.Counter()
+        for (where, sass), (_, n, st) in zip(lines, counts):
+            t = sass.split()
+            op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
+            byop[(where.split(" <- ")[-1], op)] += n
+        print("--- by (outermost line, opcode) ---")
+        for (w, op), v in byop.most_common(top):
+            print(f"{100 * v / tot:6.2f}%  {w}  {op}")
     print("--- by innermost line ---")
     for k, v in agg.most_common(top):
         print(f"{100 * v / tot:6.2f}%  stall {100 * stall[k] / tst:5.1f}%  {k}")
