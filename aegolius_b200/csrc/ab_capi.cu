@@ -255,6 +255,9 @@ static int upload_cloud(const double* pts, uint64_t m, int dim, uint64_t row_str
   } else {
     CUDA_TRY(cudaMalloc(&d, m * sizeof(V4)));
     CUDA_TRY(cudaMemcpy(d, rec.data(), m * sizeof(V4), cudaMemcpyHostToDevice));
+    // a copy from pageable memory returns once the data is STAGED; the DMA into `d` may still be in flight, and the
+    // consumers run on non-blocking streams that do not order themselves after the legacy stream: wait for it here
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
   }
   *out_dev = d;
   return AB_OK;
