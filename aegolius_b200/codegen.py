@@ -583,7 +583,15 @@ def generate(sig, dtype="f32", grad="none", **opts) -> str:
     if adjoint and dtype == "f32":  # fewer live registers than three tangents per coordinate: one more CTA per SM fits
         lite = all((int(w) & 0xffff) in LITE_OPS for w in sig)
         # (C5 field + gradient on compact tiles: 2 points per thread 15.4 ms, 4 points 13.8 ms at 6 CTAs / SM, 79 registers)
-        tuned = dict(width=4, min_ctas=6) if opts.get("compact") else (dict(width=4, min_ctas=5, rowsplit=True) if lite else {})
+        has_search = any((int(w) & 0xffff) == oc.CURVE_INST for w in sig)
+        if opts.get("compact"):
+            tuned = dict(width=4, min_ctas=6)
+        elif lite:  # (a 36-op union: 6.05 ms with the second body, 5.87 without)
+            tuned = dict(width=4, min_ctas=5, rowsplit=len(sig) <= 12)
+        elif not has_search and len(sig) <= 48:  # twisted torus 769^3: 2 points 1.47 ms, 4 points 1.30 ms (87 % of the HBM peak)
+            tuned = dict(width=4, min_ctas=6 if len(sig) <= 16 else 5)
+        else:  # flat walk with the instance search: 2 points per thread (C3 513^3: 2.19 ms against 2.26)
+            tuned = {}
         o.update({k: v for k, v in tuned.items() if opts.get(k) is None})
     elif adjoint and opts.get("min_ctas") is None:  # fp64: 64 registers are enough now (C3 256^3: 0.918 -> 0.900 ms)
         o.update(min_ctas=8)

@@ -35,6 +35,8 @@ def cases():
     un = ab.CombineGeometry("UNION").combine(*parts)
     return {
         "sphereg": (sph, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", "spatial"),
+        "twistg": (tw, ab.GridSpec((4, 4, 4), (768,) * 3), "f32", "spatial"),
+        "union12g": (un, ab.GridSpec((4, 4, 4), (768,) * 3), "f32", "spatial"),
         "twist": (tw, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
         "union12": (un, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
         "sphere0": (sph0, ab.GridSpec((4, 4, 4), (1024,) * 3), "f32", None),
