@@ -112,3 +112,49 @@ def test_long_programs_stay_on_the_interpreter():
     prog = ab.flatten(u)
     assert len(cg.signature(prog)) > cg.MAX_COMPILED_OPS
     assert cg.ensure(prog, "f32", None, how="sync") is False
+
+
+from aegolius_b200 import codegen as cg  # noqa: E402
+
+
+def _body(src):
+    return src.split("namespace ab {", 1)[1].split("#define AB_PROG_EXPORT", 1)[0]
+
+
+def test_gradient_kernels_pull_back_through_the_coordinate_ops_in_reverse_order():
+    """_AdjointEmitter on the C3 tree: coordinate ops on plain points with tapes, the deep branch pulled back to the frame
+    of the saved point (where the second child lives) right before the combine, the mirror's flip last."""
+    import aegolius_b200 as ab
+    prog = ab.flatten(ab.workloads.build_c3())
+    body = _body(cg.generate(cg.signature(prog), "f32", "spatial"))
+    assert "Pt<P> p;" in body and "Pt<S> p;" not in body
+    order = [body.index(k) for k in ("fwd_curve_inst(", "fwd_rotsym(", "fwd_bend(", "fwd_twist(", "fwd_elongate(", "grad_torus(",
+                                     "grad_sphere(", "pb_elongate(V0", "pb_affine(V0", "pb_twist(V0", "pb_bend(V0", "pb_rot(V0",
+                                     "pb_curve_inst(V0", "smin_poly3(V0, acc", "pb_flip<0>(acc")]
+    assert order == sorted(order)
+    # forward tangents on request, and for programs with an op that has no pull-back
+    assert "pb_" not in _body(cg.generate(cg.signature(prog), "f32", "spatial", adjoint=False))
+    cloud = ab.PointCloud3D(np.random.default_rng(0).uniform(-1, 1, size=(3, 50)))
+    cloud.move((0.1, 0.0, 0.0))
+    fallback = _body(cg.generate(cg.signature(ab.flatten(cloud)), "f32", "spatial"))
+    assert "Pt<S> p;" in fallback and "pb_" not in fallback
+    # value kernels and parameter-tangent kernels are untouched
+    assert "pb_" not in _body(cg.generate(cg.signature(prog), "f32", "none"))
+    assert "pb_" not in _body(cg.generate(cg.signature(prog), "f64", "param"))
+
+
+def test_extrusion_and_translations_in_the_pull_back_emitter():
+    """EXTRUDE_BEGIN stores |z| - h in the frame before z is zeroed; EXTRUDE_END pulls both operands to their common frame.
+    Translations and repetitions have an identity Jacobian: no pull-back statement, no frame."""
+    import aegolius_b200 as ab
+    c = ab.Circle(0.5)
+    c.extrusion(0.4)
+    c.twist(0.7)
+    body = _body(cg.generate(cg.signature(ab.flatten(c)), "f64", "spatial"))
+    assert body.index("fwd_twist(") < body.index("seed_local(q, p); V0 = abs_(q.z)") < body.index("pb_zero_z(acc)") \
+        < body.index("op_extrude_end<S, T>(acc, V0)") < body.index("pb_twist(acc")
+    s = ab.Sphere(0.3)
+    s.infinite_repetition((1.0, 1.0, 1.0))
+    s.move((0.2, 0.1, 0.0))
+    body = _body(cg.generate(cg.signature(ab.flatten(s)), "f32", "spatial"))
+    assert "op_rep_inf(p" in body and "pb_" not in body.split("// gradient back to grid coordinates")[1].split("emit")[0]
