@@ -110,6 +110,27 @@ def test_forward_tangent_build_matches_the_interpreter_gradient_to_the_bit(golde
     assert np.array_equal(fa, fb, equal_nan=True) and np.array_equal(ga, gb, equal_nan=True)
 
 
+@pytest.mark.parametrize("name", ["struct_2d_mirror_rotsym", "c2"])
+def test_compiled_gradient_kernels_on_2d_grids(golden, name):
+    """Field + gradient on a 2D GRID (flavour bit 0: in-kernel coordinates of a (nx, ny) grid, z = 0): the pull-back build
+    against the interpreter, fp64 and fp32, odd row length."""
+    import aegolius_b200 as ab
+    if name == "c2":
+        prog, size, ext = ab.flatten(ab.workloads.build_c2()), (8.0, 8.0), 8.0
+    else:
+        c = load_case(golden, name)
+        prog, size, ext = c["prog"], tuple(float(v) for v in c["size"][:2]), c["extent"]
+    spec = ab.GridSpec(size, (300, 212))  # 301 x 213 samples
+    _, margin = interp_np.run_grid(prog, spec.size, spec.res, return_margin=True)
+    keep = margin > 1e-4 * ext
+    for dt, tol_f, tol_g in (("f64", 0.0, 1e-11), ("f32", 2e-6 * ext, 2e-5)):
+        (fa, ga), (fb, gb), hits = _both(prog, spec, dt, grad="spatial")
+        assert hits >= 1, f"{name}: no compiled {dt} gradient kernel for 2D grids (python tools/prebuild_jit.py)"
+        scale = max(1.0, float(np.max(np.abs(gb[:, keep]))))
+        assert np.max(np.abs(fa - fb)[keep]) <= tol_f
+        assert np.max(np.abs(ga - gb)[:, keep]) <= tol_g * scale
+
+
 def test_compiled_slabs_concatenate_bit_identically(golden):
     import aegolius_b200 as ab
     from aegolius_b200 import cabi

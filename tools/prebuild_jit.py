@@ -36,6 +36,8 @@ def items():
                 for dt in ("f32", "f64"):
                     out.append((prog, dt, None, False))
                     out.append((prog, dt, "spatial", False))
+                    if is2d:  # and on its own 2D grid (tests/test_gpu_jit.py::test_compiled_gradient_kernels_on_2d_grids)
+                        out.append((prog, dt, "spatial", True))
     for build, is2d in ((workloads.build_c1, False), (workloads.build_c2, True), (workloads.build_c3, False)):
         prog = ab.flatten(build())
         for dt in ("f32", "f64"):
