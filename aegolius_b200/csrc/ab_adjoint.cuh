@@ -128,7 +128,7 @@ template <typename P, typename T>
 AB_DEV void pb_bend(Dual<P, 3>& v, const T* a, const TapeBend<P>& t) {
   const T r = a[0], c = a[2], s = a[3];
   const P gx = v.d[0], gy = v.d[1];
-  const P inv = select_(gt_(t.n, T(0)), rcp_(t.n), P(T(0)));
+  const P inv = rcp_norm_(t.n);
   const P ux = t.x * inv, uy = t.qy * inv;  // unit vector from the bend centre: d out_y / d (x, y)
   const P k = (gx * r) * inv;               // d out_x / d (x, y) = r (-uy, ux) / n
   P ix = fma_(gy, ux, -(k * uy));
@@ -166,7 +166,7 @@ struct TapeRevolve {
 template <typename P, typename T>
 AB_DEV void fwd_revolve(Pt<P>& p, const T* a, TapeRevolve<P>& t) {
   const P n = norm2_(p.x, p.z);
-  const P inv = select_(gt_(n, T(0)), rcp_(n), P(T(0)));
+  const P inv = rcp_norm_(n);
   t.ux = p.x * inv;
   t.uz = p.z * inv;
   p.x = n - a[0];
@@ -230,7 +230,7 @@ AB_DEV void fwd_axis_revolve(Pt<P>& p, const T* a, TapeRevolve<P>& t) {
   const P xr = fma_(p.x, c, p.y * s);
   const P yr = fma_(p.y, c, -(p.x * s));
   const P m = norm2_(xr, p.z);
-  const P inv = select_(gt_(m, T(0)), rcp_(m), P(T(0)));
+  const P inv = rcp_norm_(m);
   t.ux = xr * inv;
   t.uz = p.z * inv;
   p.x = fma_(m, c, -(yr * s)) - a[0];
@@ -256,7 +256,7 @@ template <typename P, typename T>
 AB_DEV Dual<P, 3> grad_sphere(const Pt<P>& p, const T* a) {
   Dual<P, 3> r;
   const P n = norm3_(p.x, p.y, p.z);
-  const P inv = select_(gt_(n, T(0)), rcp_(n), P(T(0)));
+  const P inv = rcp_norm_(n);
   r.v = n - a[0];
   r.d[0] = p.x * inv;
   r.d[1] = p.y * inv;
@@ -269,8 +269,8 @@ AB_DEV Dual<P, 3> grad_torus(const Pt<P>& p, const T* a) {
   const P m = norm2_(p.x, p.y);
   const P q = m - a[0];
   const P n = norm2_(q, p.z);
-  const P im = select_(gt_(m, T(0)), rcp_(m), P(T(0)));
-  const P in = select_(gt_(n, T(0)), rcp_(n), P(T(0)));
+  const P im = rcp_norm_(m);
+  const P in = rcp_norm_(n);
   const P gq = (q * in) * im;
   r.v = n - a[1];
   r.d[0] = gq * p.x;
@@ -288,7 +288,7 @@ AB_DEV Dual<P, 3> grad_box(const Pt<P>& p, const T* a) {
   const P m12 = max_(q1, q2);
   const P mx = max_(q0, m12);
   r.v = n + min_(mx, T(0));
-  const P inv = select_(gt_(n, T(0)), rcp_(n), P(T(0)));
+  const P inv = rcp_norm_(n);
   const Mask<W> inner = le_(mx, T(0));        // min_(mx, 0) passes mx's tangent
   const Mask<W> first = ge_(q0, m12);         // max_(q0, m12) picks q0
   const Mask<W> second = ge_(q1, q2);         // max_(q1, q2) picks q1
@@ -312,8 +312,8 @@ AB_DEV Dual<P, 3> grad_cylinder(const Pt<P>& p, const T* a) {
   const P n = norm2_(o0, o1);
   const P mx = max_(d0, d1);
   r.v = min_(mx, T(0)) + n;
-  const P inv = select_(gt_(n, T(0)), rcp_(n), P(T(0)));
-  const P im = select_(gt_(m, T(0)), rcp_(m), P(T(0)));
+  const P inv = rcp_norm_(n);
+  const P im = rcp_norm_(m);
   const Mask<W> inner = le_(mx, T(0));
   const Mask<W> first = ge_(d0, d1);
   const P one(T(1)), zero(T(0));

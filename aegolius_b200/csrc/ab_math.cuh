@@ -311,6 +311,12 @@ AB_PACK_BINARY(div_, s_div)
 AB_PACK_BINARY(mod_, s_mod)
 AB_PACK_BINARY(pow_, s_pow)
 
+// 1 / n for a Euclidean norm n >= 0 that multiplies quantities vanishing with n (components of the vector whose norm n is):
+// the reciprocal of max(n, tiny) instead of a compare and a select around it (tiny = the square root of the smallest
+// normal number: below it the squares that make up n underflow). At n = 0 the products are exactly 0, as before.
+template <typename T, int W>
+AB_DEV Pack<T, W> rcp_norm_(const Pack<T, W>& n) { return rcp_(max_(n, T(sizeof(T) == 4 ? 1e-18 : 1e-150))); }
+
 // atan2 — fp64: libm per lane. fp32: atan(t) = t + t^3 Q(t^2) on t = min/max in [0,1] (Q of degree 8 fitted to 0.9 ulp,
 // tools/fit_atan.py), quadrant fixed up afterwards; the Horner chain runs as packed FFMA2 (two points per issue slot).
 // ~23 issue slots per pair of points instead of ~47 per point for atan2f; total error <= ~2 ulp like atan2f.
@@ -745,7 +751,7 @@ template <typename P, int K>
 AB_DEV Dual<P, K> norm2_(const Dual<P, K>& a, const Dual<P, K>& b) {
   Dual<P, K> r;
   r.v = sqrt_(fma_(a.v, a.v, b.v * b.v));
-  const P inv = select_(gt_(r.v, AB_DUAL_T(0)), rcp_(r.v), P(AB_DUAL_T(0)));
+  const P inv = rcp_norm_(r.v);
 #pragma unroll
   AB_DK r.d[k] = fma_(a.v, a.d[k], b.v * b.d[k]) * inv;
   return r;
@@ -754,7 +760,7 @@ template <typename P, int K>
 AB_DEV Dual<P, K> norm3_(const Dual<P, K>& a, const Dual<P, K>& b, const Dual<P, K>& c) {
   Dual<P, K> r;
   r.v = sqrt_(fma_(c.v, c.v, fma_(b.v, b.v, a.v * a.v)));
-  const P inv = select_(gt_(r.v, AB_DUAL_T(0)), rcp_(r.v), P(AB_DUAL_T(0)));
+  const P inv = rcp_norm_(r.v);
 #pragma unroll
   AB_DK r.d[k] = fma_(c.v, c.d[k], fma_(b.v, b.d[k], a.v * a.d[k])) * inv;
   return r;

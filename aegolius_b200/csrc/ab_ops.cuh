@@ -545,7 +545,10 @@ AB_DEV Dual<P, K> smin_poly_dual(const Dual<P, K>& x, const Dual<P, K>& y, const
   Dual<P, K> r;
   const Mask<P::width> xle = le_(x.v, y.v);
   r.v = order == 2 ? min_(x.v, y.v) - h * h * (w * T(0.25)) : min_(x.v, y.v) - h * h * h * (w * T(1.0 / 6.0));
-  const P g = (order == 2 ? h : h * h) * T(0.5) * sign_(u);  // 0 where h == 0: plain min
+  // sign(u) from the comparison that picks the minimum (at u == 0 this gives the mean of the two tangents, which is the
+  // derivative of the smooth minimum there); 0 where h == 0: plain min
+  const P gm = (order == 2 ? h : h * h) * T(0.5);
+  const P g = select_(xle, -gm, gm);
 #pragma unroll
   for (int k = 0; k < K; k++) r.d[k] = fma_(g, x.d[k] - y.d[k], select_(xle, x.d[k], y.d[k]));
   return r;
