@@ -133,6 +133,7 @@ class _Emitter:
         self.n_p = 0
         self.n_v = 0
         self.tables = any((w & 0xffff) in TABLE_OPS for w in self.sig)
+        self.leaf_point = "p"  # the variable a primitive reads its point from (the pull-back emitter seeds a dual copy `q`)
 
     def arg(self, i):
         code = self.sig[i] & 0xffff
@@ -256,13 +257,13 @@ class _Emitter:
             if b:
                 e("    " + self.store_v(b - 1))
         elif code in prims:
-            e(f"    acc = {prims[code]}(p, {A});")
+            e(f"    acc = {prims[code]}({self.leaf_point}, {A});")
         elif code in (oc.P_OINF_CONE, oc.P_INF_CONE):
-            e(f"    acc = prim_inf_cone(p, {A}, {'true' if code == oc.P_OINF_CONE else 'false'});")
+            e(f"    acc = prim_inf_cone({self.leaf_point}, {A}, {'true' if code == oc.P_OINF_CONE else 'false'});")
         elif code in (oc.P_SEGLINE, oc.P_SEGLINE2D):
-            e(f"    acc = prim_segline(p, {A}, {3 if code == oc.P_SEGLINE else 2});")
+            e(f"    acc = prim_segline({self.leaf_point}, {A}, {3 if code == oc.P_SEGLINE else 2});")
         elif code == oc.P_AXIS:
-            e(f"    {{ auto a = {A}; acc = p.{xyz[a]} - a[0]; }}")
+            e(f"    {{ auto a = {A}; acc = {self.leaf_point}.{xyz[a]} - a[0]; }}")
         elif code == oc.P_FIELD:
             e(f"    load_field(kp.blob[{b}], idx, kp.n, acc);")
         elif code == oc.P_POINT_CLOUD:
@@ -425,14 +426,18 @@ class _AdjointEmitter(_Emitter):
         elif (oc.P_SPHERE <= code <= oc.P_AXIS and code not in (oc.P_POINT_CLOUD, oc.P_FIELD)) or oc.P_CIRCLE <= code <= oc.P_POLYGON2D:
             # the primitive on an identity-seeded dual point: value + gradient in local coordinates
             n0 = len(self.lines)
-            super().op(i)
+            self.leaf_point = "q"
+            try:
+                super().op(i)
+            finally:
+                self.leaf_point = "p"
             body = self.lines[n0 + 1:]
             del self.lines[n0 + 1:]
             e("    {")
             e("      Pt<S> q;")
             e("      seed_local(q, p);")
             for ln in body:
-                e("  " + ln.replace("(p, ", "(q, ").replace("= p.", "= q."))
+                e("  " + ln)
             e("    }")
             self.acc_node = self.cur
         else:
