@@ -267,7 +267,7 @@ class _Emitter:
         elif code == oc.P_FIELD:
             e(f"    load_field(kp.blob[{b}], idx, kp.n, acc);")
         elif code == oc.P_POINT_CLOUD:
-            e(f"    acc = prim_point_cloud<S, T>(p, kp.blob[{b}], kp.blob_count[{b}], {a}, kp.blob_tree[{b}]);")
+            e(f"    acc = prim_point_cloud<S, T>({self.leaf_point}, kp.blob[{b}], kp.blob_count[{b}], {a}, kp.blob_tree[{b}]);")
         else:
             raise NotImplementedError(f"codegen: opcode {code} ({name})")
 
@@ -423,7 +423,7 @@ class _AdjointEmitter(_Emitter):
             e(head)
             e(f"    acc = {local_gradient[code]}(p, {A});")
             self.acc_node = self.cur
-        elif (oc.P_SPHERE <= code <= oc.P_AXIS and code not in (oc.P_POINT_CLOUD, oc.P_FIELD)) or oc.P_CIRCLE <= code <= oc.P_POLYGON2D:
+        elif oc.P_SPHERE <= code <= oc.P_POINT_CLOUD or oc.P_CIRCLE <= code <= oc.P_POLYGON2D:  # (not P_FIELD: no derivative)
             # the primitive on an identity-seeded dual point: value + gradient in local coordinates
             n0 = len(self.lines)
             self.leaf_point = "q"

@@ -93,5 +93,5 @@ GRADIENT_CASES = (
     "mod_symmetry", "mod_mirror", "mod_rotational_symmetry", "mod_linear_instancing", "mod_curve_instancing",
     "mod_aligned_curve_instancing", "mod_fully_aligned_curve_instancing", "mod_scale_sdf", "mod_rotate_sdf",
     "mod_chain_twist_elong_round", "mod_onion", "comb_UNION_3", "comb_SMOOTH_SUBTRACT2", "struct_plate_revolved_union",
-    "struct_deep_combines", "struct_2d_mirror_rotsym", "ex_pawn_3D", "ex_rod_3D", "ex_chip_3D",
+    "struct_deep_combines", "struct_2d_mirror_rotsym", "ex_pawn_3D", "ex_rod_3D", "ex_chip_3D", "ex_pointcloud_terrain_3D",
 )

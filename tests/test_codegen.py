@@ -121,7 +121,7 @@ def _body(src):
     return src.split("namespace ab {", 1)[1].split("#define AB_PROG_EXPORT", 1)[0]
 
 
-def test_gradient_kernels_pull_back_through_the_coordinate_ops_in_reverse_order():
+def test_gradient_kernels_pull_back_through_the_coordinate_ops_in_reverse_order(golden):
     """_AdjointEmitter on the C3 tree: coordinate ops on plain points with tapes, the deep branch pulled back to the frame
     of the saved point (where the second child lives) right before the combine, the mirror's flip last."""
     import aegolius_b200 as ab
@@ -134,10 +134,14 @@ def test_gradient_kernels_pull_back_through_the_coordinate_ops_in_reverse_order(
     assert order == sorted(order)
     # forward tangents on request, and for programs with an op that has no pull-back
     assert "pb_" not in _body(cg.generate(cg.signature(prog), "f32", "spatial", adjoint=False))
-    cloud = ab.PointCloud3D(np.random.default_rng(0).uniform(-1, 1, size=(3, 50)))
-    cloud.move((0.1, 0.0, 0.0))
-    fallback = _body(cg.generate(cg.signature(ab.flatten(cloud)), "f32", "spatial"))
+    polygon = load_case(golden, "shape_closed_segmented_line_polygon")["prog"]  # POLY_SIGN has no pull-back
+    fallback = _body(cg.generate(cg.signature(polygon), "f32", "spatial"))
     assert "Pt<S> p;" in fallback and "pb_" not in fallback
+    # a point cloud is a leaf like any other: evaluated on the identity-seeded copy of the point
+    cloud = ab.PointCloud3D(np.random.default_rng(0).uniform(-1, 1, size=(3, 50)))
+    cloud.twist(0.4)
+    body = _body(cg.generate(cg.signature(ab.flatten(cloud)), "f32", "spatial"))
+    assert "prim_point_cloud<S, T>(q, " in body and body.index("fwd_twist(") < body.index("pb_twist(acc")
     # value kernels and parameter-tangent kernels are untouched
     assert "pb_" not in _body(cg.generate(cg.signature(prog), "f32", "none"))
     assert "pb_" not in _body(cg.generate(cg.signature(prog), "f64", "param"))
