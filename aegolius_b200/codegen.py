@@ -419,6 +419,10 @@ class _AdjointEmitter(_Emitter):
             self.pull("acc", self.acc_node, to)
             self.acc_node = to
             super().op(i)
+        elif code == oc.POLY_SIGN:  # the interior sign at the coordinates saved in slot a: a factor -1 / +1, the frame stays
+            self.n_p = max(self.n_p, a + 1)
+            e(head)
+            e(f"    acc = op_poly_sign(acc, S(P{a}.x), S(P{a}.y), {A}, {b});")
         elif code in local_gradient:
             e(head)
             e(f"    acc = {local_gradient[code]}(p, {A});")

@@ -134,9 +134,11 @@ def test_gradient_kernels_pull_back_through_the_coordinate_ops_in_reverse_order(
     assert order == sorted(order)
     # forward tangents on request, and for programs with an op that has no pull-back
     assert "pb_" not in _body(cg.generate(cg.signature(prog), "f32", "spatial", adjoint=False))
-    polygon = load_case(golden, "shape_closed_segmented_line_polygon")["prog"]  # POLY_SIGN has no pull-back
-    fallback = _body(cg.generate(cg.signature(polygon), "f32", "spatial"))
+    staged = load_case(golden, "stencil_signed_union3d")["prog"]  # P_FIELD (a grid stencil's output) has no derivative
+    fallback = _body(cg.generate(cg.signature(staged), "f32", "spatial"))
     assert "Pt<S> p;" in fallback and "pb_" not in fallback
+    polygon = load_case(golden, "shape_closed_segmented_line_polygon")["prog"]  # the interior sign multiplies the value
+    assert "op_poly_sign(acc, S(P" in _body(cg.generate(cg.signature(polygon), "f32", "spatial"))
     # a point cloud is a leaf like any other: evaluated on the identity-seeded copy of the point
     cloud = ab.PointCloud3D(np.random.default_rng(0).uniform(-1, 1, size=(3, 50)))
     cloud.twist(0.4)
