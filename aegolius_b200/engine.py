@@ -302,7 +302,7 @@ def _create_staged(prog, spec, code, npdt, device):
             want = tuple(resolution_conversion(int(r)) for r in st["res"] if r)
             if want != tuple(spec.res[:len(want)]) or (len(want) == 2 and spec.res[2] != 1):
                 raise ValueError(f"Cannot reshape the pattern with shape ({n},)")  # what smarter_reshape raises
-            pre = prog.prefix(prog.stage_op_index(st))
+            pre = prog.prefix(prog.stage_op_index(st)).pruned()  # without the subtrees an earlier stage's field replaced
             d_in, d_out = _DevBuf(n * item, device), _DevBuf(n * item, device)
             bufs += [d_in, d_out]
             cp = cabi.CProgram(pre, device_blobs=bound)
@@ -320,8 +320,9 @@ def _create_staged(prog, spec, code, npdt, device):
             bound[st["blob"]] = (d_out.ptr.value, n)
         d_res = _DevBuf(n * item, device)
         bufs.append(d_res)
-        cp = cabi.CProgram(prog, device_blobs=bound)
-        codegen.ensure(prog, jdt, None, is2d=_is_2d(spec))
+        final = prog.pruned()  # the subtrees that fed the stages are dead code now: P_FIELD overwrites their value
+        cp = cabi.CProgram(final, device_blobs=bound)
+        codegen.ensure(final, jdt, None, is2d=_is_2d(spec))
         cabi.check(lib.ab_eval_grid(cp.ref(), C.byref(g), code, cabi.AB_GRAD_NONE, d_res.ptr, None, 0, device, None))
         field = np.empty(n, dtype=npdt)
         d_res.download(field)

@@ -80,6 +80,82 @@ class Program:
                       [st for st in self.stages if self.stage_op_index(st) < op_index])
         return pre
 
+    def pruned(self):
+        """Dead-code elimination by one backward liveness pass over the op list (registers: the point p, the value acc,
+        the P / V slots). What it is for: a stencil stage replaces a subtree's value by a P_FIELD op, but the subtree's ops
+        stay in the list in front of it; every later prefix program and the final program would evaluate them again although
+        P_FIELD overwrites their result. Argument offsets are absolute, so dropping ops needs no repacking."""
+        ops = self.ops[:-1]
+        n = len(ops)
+        keep = np.zeros(n, dtype=bool)
+        live_p, live_acc, live_P, live_V = False, True, set(), set()
+        coord = {oc.AFFINE, oc.TRANSLATE, oc.SCALE_P, oc.ELONGATE, oc.TWIST, oc.BEND, oc.ABSX_SUB, oc.SYMMETRY, oc.ROTSYM,
+                 oc.REVOLVE, oc.AXIS_REVOLVE, oc.REP_INF, oc.REP_FIN, oc.LIN_INST, oc.CURVE_INST, oc.ZERO_Z}
+        unary = {oc.ROUND, oc.ABS, oc.NEG, oc.SIGN, oc.ONION, oc.CONCENTRIC, oc.SCALE_V} | set(range(oc.PP_SIGMOID, oc.PP_GAUSS_FALLOFF + 1))
+        for i in range(n - 1, -1, -1):
+            code, a, b = int(ops["opcode"][i]), int(ops["a"][i]), int(ops["b"][i])
+            if code == oc.SAVE_P:
+                if a in live_P:
+                    keep[i] = True
+                    live_P.discard(a)
+                    live_p = True
+            elif code == oc.LOAD_P:
+                if live_p:
+                    keep[i] = True
+                    live_p = False
+                    live_P.add(a)
+            elif code == oc.PUSH_V:
+                if a in live_V:
+                    keep[i] = True
+                    live_V.discard(a)
+                    live_acc = True
+            elif code in (oc.NEXT_AFFINE, oc.NEXT_TRANSLATE, oc.NEXT_LOAD):  # [V[b-1] = acc;] p = P[a] [transformed]
+                need_v = b > 0 and (b - 1) in live_V
+                if live_p or need_v:
+                    keep[i] = True
+                    live_p = False
+                    live_P.add(a)
+                    if need_v:
+                        live_V.discard(b - 1)
+                        live_acc = True
+            elif code in coord:  # p = f(p)
+                keep[i] = live_p
+            elif code == oc.EXTRUDE_BEGIN:  # V[a] = |p.z| - h; p.z = 0
+                if live_p or a in live_V:
+                    keep[i] = True
+                    live_V.discard(a)
+                    live_p = True
+            elif code == oc.EXTRUDE_END:  # acc = f(acc, V[a])
+                if live_acc:
+                    keep[i] = True
+                    live_V.add(a)
+            elif code == oc.POLY_SIGN:  # acc = acc * sign(P[a])
+                if live_acc:
+                    keep[i] = True
+                    live_P.add(a)
+            elif code in unary:  # acc = f(acc)
+                keep[i] = live_acc
+            elif oc.C_UNION <= code <= oc.C_BOLTZ_SUB:  # acc = f(V[a], acc); [V[b-1] = acc]
+                need_v = b > 0 and (b - 1) in live_V
+                if live_acc or need_v:
+                    keep[i] = True
+                    if need_v:
+                        live_V.discard(b - 1)
+                    live_acc = True
+                    live_V.add(a)
+            elif code >= oc.P_SPHERE:  # a leaf: acc = f(p) (P_FIELD reads its blob only)
+                if live_acc:
+                    keep[i] = True
+                    live_acc = False
+                    if code != oc.P_FIELD:
+                        live_p = True
+            else:
+                raise FlattenError(f"pruned(): opcode {code} not classified")
+        if keep.all():
+            return self
+        out = np.concatenate([ops[keep], self.ops[-1:]])
+        return Program(out, self.args, self.blobs, self.n_pslots, self.n_vslots, list(self.stages))
+
     @classmethod
     def from_arrays(cls, d, prefix="prog_"):
         ops = np.ascontiguousarray(d[prefix + "ops"]).view(OP_DTYPE).reshape(-1)

@@ -261,3 +261,41 @@ def test_affine_after_aligned_instancing_is_folded_into_the_frames():
     prog = engine.program_tangent(build, [0.3], 0)
     k = codes(prog).index(oc.CURVE_INST)
     assert codes(prog)[k + 1] == oc.AFFINE and np.any(prog.dargs != 0)
+
+
+def test_pruned_drops_exactly_the_dead_ops(golden):
+    """Program.pruned(): backward liveness over (p, acc, P slots, V slots). No golden program without a stencil stage
+    holds dead code; a staged one loses the subtree whose value its P_FIELD op overwrites; and a program with a dead
+    branch spliced in evaluates (oracle) to the same field after pruning."""
+    import numpy as np
+    import aegolius_b200 as ab
+    from aegolius_b200 import opcodes as oc
+    from aegolius_b200.program import Program, OP_DTYPE
+    from conftest import golden_names, load_case
+    from oracle import interp_np
+    names = lambda p: [oc.NAMES[int(c)] for c in p.ops["opcode"]]
+    for name in golden_names():
+        prog = load_case(golden, name)["prog"]
+        if not prog.stages:
+            assert prog.pruned() is prog, name
+    tree = load_case(golden, "stencil_conv_averaging_tree3d")["prog"]
+    assert names(tree.pruned()) == ["P_FIELD", "END"]
+    second = tree.prefix(tree.stage_op_index(sorted(tree.stages, key=tree.stage_op_index)[1]))
+    assert names(second.pruned()) == ["SAVE_P", "P_FIELD", "ROUND", "NEXT_AFFINE", "P_BOX", "C_SMIN3", "END"]
+    # C1 (a smooth union that uses P and V slots), then a leaf that overwrites its value: only the leaf's inputs survive
+    c1 = ab.flatten(ab.workloads.build_c1())
+    sph = ab.Sphere(0.7)
+    sph.move((0.2, -0.1, 0.3))
+    tail = ab.flatten(sph)  # TRANSLATE, P_SPHERE, END with its own argument pool
+    shift = len(c1.args)
+    tail_ops = tail.ops[:-1].copy()
+    tail_ops["arg"] += shift
+    load = np.array([(oc.LOAD_P, 0, 0, 0)], dtype=OP_DTYPE)
+    ops = np.concatenate([c1.ops[:-1], load, tail_ops, c1.ops[-1:]])
+    spliced = Program(ops, np.concatenate([c1.args, tail.args]), [], c1.n_pslots, c1.n_vslots, [])
+    assert int(c1.ops["opcode"][0]) == oc.SAVE_P and int(c1.ops["a"][0]) == 0  # slot 0 holds the grid point
+    pruned = spliced.pruned()
+    assert names(pruned) == ["SAVE_P", "LOAD_P", "TRANSLATE", "P_SPHERE", "END"]
+    co = np.random.default_rng(1).uniform(-2, 2, size=(3, 4000))
+    assert np.array_equal(interp_np.run(pruned, co), interp_np.run(spliced, co))
+    assert np.array_equal(interp_np.run(pruned, co), interp_np.run(tail, co))

@@ -26,9 +26,9 @@ def items():
             prog = Program.from_arrays(keys, prefix="prog_")
             res = tuple(int(r) for r in keys["res"])
             is2d = not res[2] > 1
-            progs = [prog]
-            for st in prog.stages:  # staged programs run their prefixes too
-                progs.append(prog.prefix(prog.stage_op_index(st)))
+            progs = [prog.pruned() if prog.stages else prog]
+            for st in prog.stages:  # staged programs run their (pruned) prefixes too
+                progs.append(prog.prefix(prog.stage_op_index(st)).pruned())
             for p in progs:
                 for dt in ("f32", "f64"):
                     out.append((p, dt, None, is2d))
